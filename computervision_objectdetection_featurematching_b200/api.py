@@ -1,0 +1,242 @@
+"""Host-side mirror of the reference's hot-path calls on top of libcvgraft's C ABI.
+
+    Context.match_knn2        <- cv::BFMatcher(NORM_L2).knnMatch(q, t, 2) + ratio test
+                                 reference src/TestsDetector.cpp:59-72
+    Context.find_homography   <- cv::findHomography(src, dst, RANSAC, 5.0, mask)    :77-78
+    Context.detect_pairs      <- body of the view loop of detectAtScale             :58-95
+    Models                    <- ObjectModel descriptors resident in HBM            include/objectModel.hpp:11-16
+
+Error behaviour follows OpenCV where the reference relies on it: find_homography raises for n < 4.
+numpy arrays in, numpy arrays out; all compute happens on the GPU (no CPU fallback).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import DetectParams, PairResult, RansacParams
+
+ACCEPT, LT4_MATCHES, H_EMPTY, LT4_INLIERS, DET_REJECT = range(5)
+RANSAC_NO_EARLY_STOP = 1
+RANSAC_NO_REFINE = 2
+FORCE_EXACT_MATCH = 1
+PATH_TENSOR, PATH_EXACT = 1, 2
+
+PAIR_DTYPE = np.dtype([("status", "<i4"), ("n_good", "<i4"), ("n_inliers", "<i4"), ("ransac_iters", "<i4"),
+                       ("H", "<f8", (9,)), ("det", "<f8")])
+assert PAIR_DTYPE.itemsize == C.sizeof(PairResult)
+
+
+class CvgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"cvgraft error {code}: {msg}")
+        self.code = code
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a, cols):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a.reshape(-1, cols)
+
+
+def ransac_params(threshold=5.0, max_iters=2000, confidence=0.995, flags=0):
+    p = RansacParams()
+    _lib.load().cvg_ransac_params_default(C.byref(p))
+    p.threshold = threshold; p.max_iters = max_iters; p.confidence = confidence; p.flags = flags
+    return p
+
+
+def detect_params(ratio=0.9, min_inliers=4, det_lo=0.1, det_hi=10.0, ransac=None):
+    p = DetectParams()
+    _lib.load().cvg_detect_params_default(C.byref(p))
+    p.ratio = ratio; p.min_inliers = min_inliers; p.det_lo = det_lo; p.det_hi = det_hi
+    if ransac is not None:
+        p.ransac = ransac
+    return p
+
+
+class Models:
+    """Model-view descriptors (+ keypoints) resident in HBM — the hook after src/ModelsDetector.cpp:80."""
+
+    def __init__(self, ctx, handle, view_offsets):
+        self.ctx, self.handle = ctx, handle
+        self.view_offsets = np.asarray(view_offsets, np.int32)
+
+    @property
+    def n_views(self):
+        return len(self.view_offsets) - 1
+
+    @property
+    def n_rows(self):
+        return int(self.view_offsets[-1])
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.cvg_models_free(self.ctx.handle, self.handle)
+            self.handle = None
+
+
+class Scenes:
+    def __init__(self, ctx, handle, offsets):
+        self.ctx, self.handle = ctx, handle
+        self.offsets = np.asarray(offsets, np.int64)
+
+    @property
+    def n_scenes(self):
+        return len(self.offsets) - 1
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.cvg_scenes_free(self.ctx.handle, self.handle)
+            self.handle = None
+
+
+class Context:
+    def __init__(self, device=0, flags=0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.cvg_create(C.byref(h), device, flags)
+        if rc:
+            raise CvgError(rc, self.lib.cvg_last_error().decode())
+        self.handle = h
+        self.device = device
+
+    def close(self):
+        if self.handle:
+            self.lib.cvg_destroy(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc:
+            raise CvgError(rc, self.lib.cvg_last_error().decode())
+
+    # ---- resident sets -----------------------------------------------------------------------
+    def upload_models(self, descriptors, keypoints_xy, view_offsets, view_model=None):
+        d = _f32(descriptors, 128)
+        k = _f32(keypoints_xy, 2) if keypoints_xy is not None else None
+        vo = np.ascontiguousarray(view_offsets, np.int32)
+        vm = np.ascontiguousarray(view_model, np.int32) if view_model is not None else None
+        h = C.c_void_p()
+        self._check(self.lib.cvg_models_upload(self.handle, _ptr(d), _ptr(k), _ptr(vo), _ptr(vm), len(vo) - 1, C.byref(h)))
+        return Models(self, h, vo)
+
+    def upload_scenes(self, descriptors, keypoints_xy, offsets):
+        d = _f32(descriptors, 128)
+        k = _f32(keypoints_xy, 2) if keypoints_xy is not None else None
+        off = np.ascontiguousarray(offsets, np.int64)
+        h = C.c_void_p()
+        self._check(self.lib.cvg_scenes_upload(self.handle, _ptr(d), _ptr(k), _ptr(off), len(off) - 1, C.byref(h)))
+        return Scenes(self, h, off)
+
+    # ---- match stage ---------------------------------------------------------------------------
+    def match_knn2(self, query, train, ratio=0.9, view=-1):
+        """query: Models (resident, optionally one view) or an [nq,128] array.  -> idx[nq,2] (-1 = absent),
+        dist[nq,2], accept[nq]."""
+        t = _f32(train, 128)
+        if isinstance(query, Models):
+            nq = query.n_rows if view < 0 else int(query.view_offsets[view + 1] - query.view_offsets[view])
+        else:
+            q = _f32(query, 128)
+            nq = q.shape[0]
+        idx = np.full((nq, 2), -1, np.int32); dist = np.zeros((nq, 2), np.float32); acc = np.zeros(nq, np.uint8)
+        if isinstance(query, Models):
+            rc = self.lib.cvg_match_knn2(self.handle, query.handle, view, _ptr(t), t.shape[0], ratio,
+                                         _ptr(idx), _ptr(dist), _ptr(acc))
+        else:
+            rc = self.lib.cvg_match_knn2_raw(self.handle, _ptr(q), nq, _ptr(t), t.shape[0], ratio,
+                                             _ptr(idx), _ptr(dist), _ptr(acc))
+        self._check(rc)
+        return idx, dist, acc
+
+    @property
+    def last_match_path(self):
+        return self.lib.cvg_last_match_path(self.handle)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.cvg_launch_count(self.handle))
+
+    def set_timing(self, on=True):
+        self._check(self.lib.cvg_set_timing(self.handle, int(on)))
+
+    def last_timing(self):
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        self.lib.cvg_last_timing(self.handle, C.byref(a), C.byref(b), C.byref(c))
+        return {"match_ms": a.value, "ransac_ms": b.value, "total_ms": c.value}
+
+    # ---- verify stage --------------------------------------------------------------------------
+    def find_homography(self, src, dst, threshold=5.0, max_iters=2000, confidence=0.995, flags=0,
+                        want_ransac_mask=False):
+        """cv2.findHomography(src, dst, cv2.RANSAC, threshold, maxIters=, confidence=)
+        -> (H 3x3 or None, mask uint8 [n]) (+ RANSAC-stage mask).  Raises for n < 4 like OpenCV."""
+        s = _f32(src, 2); d = _f32(dst, 2)
+        n = s.shape[0]
+        if d.shape[0] != n:
+            raise ValueError("src and dst must have the same number of points")
+        H = np.zeros(9); mask = np.zeros(max(n, 1), np.uint8); found = C.c_int(0)
+        rmask = np.zeros(max(n, 1), np.uint8) if want_ransac_mask else None
+        p = ransac_params(threshold, max_iters, confidence, flags)
+        self._check(self.lib.cvg_find_homography(self.handle, _ptr(s), _ptr(d), n, C.byref(p), _ptr(H), _ptr(mask),
+                                                 C.byref(found), _ptr(rmask)))
+        Hm = H.reshape(3, 3) if found.value else None
+        return (Hm, mask[:n], rmask[:n]) if want_ransac_mask else (Hm, mask[:n])
+
+    def find_homography_batch(self, src, dst, offsets, threshold=5.0, max_iters=2000, confidence=0.995, flags=0,
+                              want_ransac_mask=False):
+        s = _f32(src, 2); d = _f32(dst, 2)
+        off = np.ascontiguousarray(offsets, np.int64)
+        P = len(off) - 1
+        H = np.zeros((P, 9)); mask = np.zeros(max(s.shape[0], 1), np.uint8)
+        found = np.zeros(P, np.int32); iters = np.zeros(P, np.int32)
+        rmask = np.zeros(max(s.shape[0], 1), np.uint8) if want_ransac_mask else None
+        p = ransac_params(threshold, max_iters, confidence, flags)
+        self._check(self.lib.cvg_find_homography_batch(self.handle, _ptr(s), _ptr(d), _ptr(off), P, C.byref(p),
+                                                       _ptr(H), _ptr(mask), _ptr(found), _ptr(iters), _ptr(rmask)))
+        out = {"H": H.reshape(P, 3, 3), "mask": mask[:s.shape[0]], "found": found.astype(bool), "iters": iters}
+        if want_ransac_mask:
+            out["ransac_mask"] = rmask[:s.shape[0]]
+        return out
+
+    # ---- fused path ----------------------------------------------------------------------------
+    def detect_pairs(self, models, scene_desc, scene_kpt_xy, scale=1.0, params=None, want_inliers=True):
+        """All views of `models` against one scene: replaces the view loop src/TestsDetector.cpp:58-95.
+        -> (per_view structured array, inlier_xy [k,2], inlier_offsets [V+1])."""
+        t = _f32(scene_desc, 128); k = _f32(scene_kpt_xy, 2)
+        p = params if params is not None else detect_params()
+        V = models.n_views
+        res = np.zeros(max(V, 1), PAIR_DTYPE)
+        inl = np.zeros((max(models.n_rows, 1), 2), np.float32) if want_inliers else None
+        ioff = np.zeros(V + 1, np.int32) if want_inliers else None
+        self._check(self.lib.cvg_detect_pairs(self.handle, models.handle, _ptr(t), _ptr(k), t.shape[0], float(scale),
+                                              C.byref(p), _ptr(res), _ptr(inl), _ptr(ioff)))
+        if want_inliers:
+            return res[:V], inl[:ioff[V]], ioff
+        return res[:V], None, None
+
+    def detect_scenes(self, models, scenes, scales=None, params=None):
+        """Every view x every resident scene (no host->device input traffic). -> [S, V] structured array."""
+        p = params if params is not None else detect_params()
+        S, V = scenes.n_scenes, models.n_views
+        res = np.zeros(max(S * V, 1), PAIR_DTYPE)
+        sc = np.ascontiguousarray(scales, np.float32) if scales is not None else None
+        self._check(self.lib.cvg_detect_scenes(self.handle, models.handle, scenes.handle, _ptr(sc), C.byref(p), _ptr(res)))
+        return res[:S * V].reshape(S, V)
+
+    # ---- device-pointer building blocks (multi-GPU train-tile shards) ---------------------------
+    def dev_match_top2(self, query_ptr, n_query, train_ptr, n_train, index_base, dist_ptr, idx_ptr, stream=None):
+        self._check(self.lib.cvg_dev_match_top2(self.handle, stream, query_ptr, n_query, train_ptr, n_train,
+                                                index_base, dist_ptr, idx_ptr))
+
+    def dev_merge_top2(self, dist_parts_ptr, idx_parts_ptr, n_parts, n_query, ratio, idx_ptr, dist_ptr, accept_ptr,
+                       stream=None):
+        self._check(self.lib.cvg_dev_merge_top2(self.handle, stream, dist_parts_ptr, idx_parts_ptr, n_parts, n_query,
+                                                ratio, idx_ptr, dist_ptr, accept_ptr))

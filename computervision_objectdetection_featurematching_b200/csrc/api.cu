@@ -1,0 +1,831 @@
+// api.cu — the C ABI of libcvgraft (include/cvgraft.h): context, resident model/scene sets and the
+// host-side orchestration of the match and verify kernels.  No CPU fallback exists: every entry point
+// needs a CUDA device and fails loudly otherwise.
+#include "common.cuh"
+#include <algorithm>
+#include <string>
+#include <vector>
+#include <string.h>
+#include <stdarg.h>
+#include <math.h>
+
+using namespace cvg;
+
+static thread_local char g_err[512] = "";
+
+static int set_err(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_CHECK(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess)                                                                \
+            return set_err(CVG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                           __FILE__, __LINE__);                                                \
+    } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct SegInfo { int rows; int64_t f32_row0; int64_t pad_row0; int ct; };
+
+struct TrainSet {                      // a prepared set of train segments on the device
+    int n_segs = 0;
+    std::vector<SegInfo> segs;
+    int64_t rows_total = 0, rows_pad_total = 0;
+    int max_rows = 0;
+    float* d_f32 = nullptr;            // [rows_total, 128]
+    __nv_bfloat16* d_b = nullptr;      // [rows_pad_total, 128]
+    __nv_bfloat16* d_aug = nullptr;    // [rows_pad_total, 16]
+    float* d_kpt = nullptr;            // [rows_total, 2] or null
+    int64_t* d_kpt_offsets = nullptr;  // [S+1]
+    int nonint = -1;                   // host-known flag (-1 unknown)
+};
+
+struct cvg_models {
+    int n_rows = 0, n_pad = 0, n_views = 0;
+    std::vector<int32_t> view_offsets, view_model;
+    float* d_f32 = nullptr; __nv_bfloat16* d_b = nullptr; __nv_bfloat16* d_aug = nullptr;
+    float* d_norm = nullptr; float* d_kpt = nullptr; int32_t* d_view_offsets = nullptr;
+    int nonint = 0;
+};
+
+struct cvg_scenes {
+    TrainSet ts;
+    DevBuf f32, b, aug, kpt, kptoff;
+    // cached match plan for a given model set
+    const cvg_models* plan_models = nullptr;
+    int plan_units = 0, plan_slots = 0;
+    DevBuf units, dir;
+};
+
+struct cvg_ctx {
+    int device = 0; unsigned flags = 0; int n_sms = 148;
+    cudaStream_t stream = nullptr;
+    int* d_flags = nullptr;            // [0] train nonint, [1] query nonint, [8..16) kernel debug words
+    uint32_t* d_rng = nullptr; int64_t rng_len = 0;
+    int last_match_path = 0; int64_t launches = 0;
+    int timing = 0; float t_match = 0, t_ransac = 0, t_total = 0;
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    // scratch
+    DevBuf q_f32, q_b, q_aug, q_norm;                  // raw-query path
+    DevBuf t_f32, t_b, t_aug, t_kpt, t_kptoff;         // per-call train path
+    DevBuf units, dir, parts, idx, dist, accept;
+    DevBuf pts, starts, counts_n, sample_pos, n_samples, counts, best_iter, best_count, iters_run, sel;
+    DevBuf H, mask, rmask, found, sflags, results, inl_xy, inl_cnt, scales, src, dst;
+};
+
+extern "C" {
+
+const char* cvg_last_error(void) { return g_err; }
+const char* cvg_version(void) { return "cvgraft 0.1.0 (sm_100a)"; }
+
+void cvg_ransac_params_default(cvg_ransac_params* p)
+{
+    memset(p, 0, sizeof *p);
+    p->size = sizeof *p; p->flags = 0; p->threshold = 5.0; p->confidence = 0.995; p->max_iters = 2000;
+}
+
+void cvg_detect_params_default(cvg_detect_params* p)
+{
+    memset(p, 0, sizeof *p);
+    p->size = sizeof *p; p->ratio = 0.9f; p->min_inliers = 4; p->det_lo = 0.1f; p->det_hi = 10.0f;
+    cvg_ransac_params_default(&p->ransac);
+}
+
+int cvg_create(cvg_ctx** out, int device, unsigned flags)
+{
+    if (!out) return set_err(CVG_ERR_INVALID, "cvg_create: out is NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return set_err(CVG_ERR_CUDA, "cvg_create: no CUDA device (%s); libcvgraft has no CPU fallback",
+                       cudaGetErrorString(e));
+    if (device < 0 || device >= n_dev) return set_err(CVG_ERR_INVALID, "cvg_create: device %d of %d", device, n_dev);
+    CU_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return set_err(CVG_ERR_CUDA, "cvg_create: device %d is sm_%d%d; libcvgraft is built for sm_100a only",
+                       device, prop.major, prop.minor);
+    cvg_ctx* c = new cvg_ctx();
+    c->device = device; c->flags = flags; c->n_sms = prop.multiProcessorCount;
+    CU_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU_CHECK(cudaMalloc(&c->d_flags, 64 * sizeof(int)));
+    CU_CHECK(cudaMemset(c->d_flags, 0, 64 * sizeof(int)));
+    for (int i = 0; i < 4; i++) CU_CHECK(cudaEventCreate(&c->ev[i]));
+    char err[256];
+    if (tc_init(err, sizeof err)) { delete c; return set_err(CVG_ERR_CUDA, "%s", err); }
+    *out = c;
+    return CVG_OK;
+}
+
+void cvg_destroy(cvg_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = { &c->q_f32, &c->q_b, &c->q_aug, &c->q_norm, &c->t_f32, &c->t_b, &c->t_aug, &c->t_kpt, &c->t_kptoff,
+                       &c->units, &c->dir, &c->parts, &c->idx, &c->dist, &c->accept, &c->pts, &c->starts, &c->counts_n,
+                       &c->sample_pos, &c->n_samples, &c->counts, &c->best_iter, &c->best_count, &c->iters_run, &c->sel,
+                       &c->H, &c->mask, &c->rmask, &c->found, &c->sflags, &c->results, &c->inl_xy, &c->inl_cnt,
+                       &c->scales, &c->src, &c->dst };
+    for (DevBuf* b : bufs) b->release();
+    if (c->d_flags) cudaFree(c->d_flags);
+    if (c->d_rng) cudaFree(c->d_rng);
+    for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int cvg_last_match_path(const cvg_ctx* c) { return c ? c->last_match_path : 0; }
+int64_t cvg_launch_count(const cvg_ctx* c) { return c ? c->launches : 0; }
+int cvg_set_timing(cvg_ctx* c, int enabled) { if (!c) return CVG_ERR_INVALID; c->timing = enabled; return CVG_OK; }
+int cvg_last_timing(const cvg_ctx* c, float* m, float* r, float* t)
+{
+    if (!c) return CVG_ERR_INVALID;
+    if (m) *m = c->t_match; if (r) *r = c->t_ransac; if (t) *t = c->t_total;
+    return CVG_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// internals
+// ---------------------------------------------------------------------------------------------------
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+static int ensure_rng(cvg_ctx* c, int max_iters)
+{
+    int64_t want = std::max<int64_t>(1 << 20, (int64_t)max_iters * 6 + (1 << 16));
+    if (want > 0x7fff0000LL) want = 0x7fff0000LL;
+    if (c->rng_len >= want) return CVG_OK;
+    std::vector<uint32_t> tab((size_t)want);
+    uint64_t state = 0xFFFFFFFFFFFFFFFFull;                     // RNG rng((uint64)-1), SURVEY App. B.2
+    for (int64_t i = 0; i < want; i++) {
+        state = (uint64_t)(uint32_t)state * 4164903690U + (uint32_t)(state >> 32);
+        tab[(size_t)i] = (uint32_t)state;
+    }
+    if (c->d_rng) cudaFree(c->d_rng);
+    c->d_rng = nullptr; c->rng_len = 0;
+    CU_CHECK(cudaMalloc(&c->d_rng, (size_t)want * 4));
+    CU_CHECK(cudaMemcpyAsync(c->d_rng, tab.data(), (size_t)want * 4, cudaMemcpyHostToDevice, c->stream));
+    CU_CHECK(cudaStreamSynchronize(c->stream));
+    c->rng_len = want;
+    return CVG_OK;
+}
+
+// Prepare (convert) a train set that is already in device fp32 memory.
+static int prep_train(cvg_ctx* c, TrainSet& ts, DevBuf& b, DevBuf& aug, int flag_slot)
+{
+    CU_CHECK(b.ensure((size_t)std::max<int64_t>(ts.rows_pad_total, 1) * DIM * 2));
+    CU_CHECK(aug.ensure((size_t)std::max<int64_t>(ts.rows_pad_total, 1) * KAUG * 2));
+    ts.d_b = b.as<__nv_bfloat16>(); ts.d_aug = aug.as<__nv_bfloat16>();
+    for (const SegInfo& s : ts.segs) {
+        const int n_pad = s.ct * TILE_N;
+        launch_prep_rows(ts.d_f32 + s.f32_row0 * DIM, s.rows, n_pad, 1, ts.d_b + s.pad_row0 * DIM,
+                         ts.d_aug + s.pad_row0 * KAUG, nullptr, c->d_flags + flag_slot, c->stream);
+        c->launches++;
+    }
+    CU_CHECK(cudaGetLastError());
+    return CVG_OK;
+}
+
+static void layout_segments(TrainSet& ts, const int64_t* offsets, int n)
+{
+    ts.n_segs = n; ts.segs.resize(n);
+    int64_t pad = 0; int mx = 0;
+    for (int s = 0; s < n; s++) {
+        SegInfo& g = ts.segs[s];
+        g.rows = (int)(offsets[s + 1] - offsets[s]);
+        g.f32_row0 = offsets[s];
+        g.ct = (g.rows + TILE_N - 1) / TILE_N;
+        g.pad_row0 = pad;
+        pad += (int64_t)g.ct * TILE_N;
+        mx = std::max(mx, g.rows);
+    }
+    ts.rows_total = offsets[n]; ts.rows_pad_total = pad; ts.max_rows = mx;
+}
+
+struct QuerySide {
+    const float* d_f32; const __nv_bfloat16* d_b; const __nv_bfloat16* d_aug; const float* d_norm;
+    int row_begin, row_end;        // absolute rows matched
+    int n_pad;                     // rows of the padded operand matrices
+};
+
+// Build the unit list for query rows [row_begin,row_end) x all segments.  Returns units sorted by size
+// (largest first) and the merge directory [seg][rowblock].
+static void build_plan(const QuerySide& q, const TrainSet& ts, int n_sms, std::vector<MatchUnit>& units,
+                       std::vector<MergeEntry>& dir, int& n_rb)
+{
+    const int nq = q.row_end - q.row_begin;
+    n_rb = (nq + TILE_M - 1) / TILE_M;
+    int64_t total_tiles = 0;
+    int max_ct = 1;
+    for (const SegInfo& s : ts.segs) { total_tiles += (int64_t)n_rb * s.ct; max_ct = std::max(max_ct, s.ct); }
+    // chunk length: minimise the estimated makespan (tiles per CTA incl. an A-reload cost of 0.5 tile)
+    int best_ch = 1; double best_cost = 1e300;
+    for (int ch = 1; ch <= max_ct; ch++) {
+        int64_t n_units = 0;
+        for (const SegInfo& s : ts.segs) n_units += (int64_t)n_rb * ((s.ct + ch - 1) / ch);
+        const double waves = ceil((double)n_units / n_sms);
+        const double cost = waves * (ch + 0.5);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best_ch = ch; }
+    }
+    units.clear(); dir.assign((size_t)ts.n_segs * n_rb, MergeEntry{ 0, 0 });
+    int slot = 0;
+    for (int s = 0; s < ts.n_segs; s++) {
+        const SegInfo& g = ts.segs[s];
+        const int n_chunks = (g.ct + best_ch - 1) / best_ch;
+        for (int rb = 0; rb < n_rb; rb++) {
+            dir[(size_t)s * n_rb + rb] = MergeEntry{ slot, n_chunks };
+            for (int ck = 0; ck < n_chunks; ck++) {
+                // spread tiles evenly over the chunks of this segment
+                const int t0 = (int)((int64_t)g.ct * ck / n_chunks), t1 = (int)((int64_t)g.ct * (ck + 1) / n_chunks);
+                MatchUnit u;
+                u.q_row0 = q.row_begin + rb * TILE_M;
+                u.t_row0 = (int32_t)(g.pad_row0 + (int64_t)t0 * TILE_N);
+                u.n_tiles = t1 - t0;
+                u.t_local0 = t0 * TILE_N;
+                u.part_slot = slot++;
+                u.seg_cols = g.rows;
+                u.t_row0_f32 = (int32_t)(g.f32_row0 + (int64_t)t0 * TILE_N);
+                u.pad1 = 0;
+                units.push_back(u);
+            }
+        }
+    }
+    std::stable_sort(units.begin(), units.end(), [](const MatchUnit& a, const MatchUnit& b) { return a.n_tiles > b.n_tiles; });
+}
+
+// Launch the match kernels for a plan already on the device.  path_hint: 1 = tensor-core only,
+// 2 = exact only, 0 = decide on the device from d_flags[0] | d_flags[1].
+static int launch_match(cvg_ctx* c, const QuerySide& q, const TrainSet& ts, const MatchUnit* d_units, int n_units,
+                        const MergeEntry* d_dir, int n_rb, float ratio, int path_hint, Top2* d_parts,
+                        int32_t* d_idx, float* d_dist, uint8_t* d_accept)
+{
+    const int nq = q.row_end - q.row_begin;
+    if (n_units > 0) {
+        if (path_hint != 2) {
+            TcOperands op{ q.d_b, q.d_aug, q.d_norm, q.n_pad, ts.d_b, ts.d_aug, (int)ts.rows_pad_total };
+            char err[256];
+            if (launch_match_tc(op, d_units, n_units, d_parts, path_hint == 0 ? c->d_flags + 2 : nullptr,
+                                c->d_flags + 8, c->n_sms, c->stream, err, sizeof err))
+                return set_err(CVG_ERR_CUDA, "%s", err);
+            c->launches++;
+        }
+        if (path_hint != 1) {
+            launch_match_exact(q.d_f32, q.row_end, ts.d_f32, d_units, n_units, d_parts,
+                               path_hint == 0 ? c->d_flags + 2 : nullptr, c->stream);
+            c->launches++;
+        }
+    }
+    launch_merge(d_parts, d_dir, ts.n_segs, n_rb, nq, ratio, d_idx, d_dist, d_accept, c->stream);
+    c->launches++;
+    CU_CHECK(cudaGetLastError());
+    return CVG_OK;
+}
+
+__global__ void combine_flags_kernel(int* f, int force_exact)
+{
+    f[2] = (f[0] | f[1] | force_exact) ? 1 : 0;
+}
+
+// Verify stage on a device correspondence pool.
+static int run_ransac(cvg_ctx* c, const float4* d_pts, const int64_t* d_starts, const int32_t* d_counts_n,
+                      int n_sets, int max_n, int64_t pool_rows, const cvg_ransac_params* p, bool want_rmask)
+{
+    if (n_sets <= 0) return CVG_OK;
+    int rc = ensure_rng(c, p->max_iters);
+    if (rc) return rc;
+    const int mi = std::max(p->max_iters, 1);
+    CU_CHECK(c->sample_pos.ensure((size_t)n_sets * mi * 4));
+    CU_CHECK(c->counts.ensure((size_t)n_sets * mi * 4));
+    CU_CHECK(c->n_samples.ensure((size_t)n_sets * 4));
+    CU_CHECK(c->best_iter.ensure((size_t)n_sets * 4));
+    CU_CHECK(c->best_count.ensure((size_t)n_sets * 4));
+    CU_CHECK(c->iters_run.ensure((size_t)n_sets * 4));
+    CU_CHECK(c->sflags.ensure((size_t)n_sets * 4));
+    CU_CHECK(c->found.ensure((size_t)n_sets * 4));
+    CU_CHECK(c->H.ensure((size_t)n_sets * 9 * 8));
+    CU_CHECK(c->sel.ensure((size_t)std::max<int64_t>(pool_rows, 1) * 4));
+    CU_CHECK(c->mask.ensure((size_t)std::max<int64_t>(pool_rows, 1)));
+    if (want_rmask) CU_CHECK(c->rmask.ensure((size_t)std::max<int64_t>(pool_rows, 1)));
+    RansacWork w;
+    w.pts = d_pts; w.starts = d_starts; w.counts_n = d_counts_n; w.n_sets = n_sets; w.max_n = max_n;
+    w.max_iters = mi;
+    const double thr = p->threshold > 0 ? p->threshold : 3.0;        // defaultRANSACReprojThreshold
+    w.thr2 = (float)(thr * thr);
+    w.conf = p->confidence; w.flags = p->flags;
+    w.rng_tab = c->d_rng; w.rng_len = c->rng_len;
+    w.sample_pos = c->sample_pos.as<int32_t>(); w.n_samples = c->n_samples.as<int32_t>();
+    w.counts = c->counts.as<int32_t>(); w.best_iter = c->best_iter.as<int32_t>();
+    w.best_count = c->best_count.as<int32_t>(); w.iters_run = c->iters_run.as<int32_t>();
+    w.sel = c->sel.as<int32_t>(); w.H = c->H.as<double>(); w.mask = c->mask.as<uint8_t>();
+    w.ransac_mask = want_rmask ? c->rmask.as<uint8_t>() : nullptr;
+    w.found = c->found.as<int32_t>(); w.status_flags = c->sflags.as<int32_t>();
+    launch_ransac(w, c->stream);
+    c->launches += 4;
+    CU_CHECK(cudaGetLastError());
+    return CVG_OK;
+}
+
+static int check_params(const cvg_ransac_params* p)
+{
+    if (!p || p->size != sizeof(cvg_ransac_params)) return set_err(CVG_ERR_INVALID, "cvg_ransac_params: bad size field");
+    if (!(p->confidence > 0 && p->confidence < 1)) return set_err(CVG_ERR_INVALID, "confidence must be in (0,1)");
+    if (p->max_iters < 1 || p->max_iters > (1 << 24)) return set_err(CVG_ERR_LIMIT, "max_iters out of range [1, 2^24]");
+    return CVG_OK;
+}
+
+static int sync_and_check(cvg_ctx* c)
+{
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+        int dbg[4] = { 0, 0, 0, 0 };
+        return set_err(CVG_ERR_CUDA, "device execution failed: %s (dbg %d)", cudaGetErrorString(e), dbg[0]);
+    }
+    return CVG_OK;
+}
+
+extern "C" {
+
+// ---- models ---------------------------------------------------------------------------------------
+int cvg_models_upload(cvg_ctx* c, const float* desc, const float* kpt_xy, const int32_t* view_offsets,
+                      const int32_t* view_model, int n_views, cvg_models** out)
+{
+    if (!c || !out || !view_offsets || n_views < 0) return set_err(CVG_ERR_INVALID, "cvg_models_upload: bad argument");
+    *out = nullptr;
+    CU_CHECK(cudaSetDevice(c->device));
+    const int n = view_offsets[n_views];
+    if (n < 0 || (n > 0 && !desc)) return set_err(CVG_ERR_INVALID, "cvg_models_upload: bad row count / NULL desc");
+    for (int v = 0; v < n_views; v++)
+        if (view_offsets[v + 1] < view_offsets[v]) return set_err(CVG_ERR_INVALID, "view_offsets must be non-decreasing");
+    cvg_models* m = new cvg_models();
+    m->n_rows = n; m->n_views = n_views;
+    m->n_pad = round_up(std::max(n, 1), TILE_M) + TILE_M;          // slack: a view's last tile may overrun
+    m->view_offsets.assign(view_offsets, view_offsets + n_views + 1);
+    if (view_model) m->view_model.assign(view_model, view_model + n_views);
+    CU_CHECK(cudaMalloc(&m->d_f32, (size_t)m->n_pad * DIM * 4));
+    CU_CHECK(cudaMalloc(&m->d_b, (size_t)m->n_pad * DIM * 2));
+    CU_CHECK(cudaMalloc(&m->d_aug, (size_t)m->n_pad * KAUG * 2));
+    CU_CHECK(cudaMalloc(&m->d_norm, (size_t)m->n_pad * 4));
+    CU_CHECK(cudaMalloc(&m->d_kpt, (size_t)std::max(n, 1) * 8));
+    CU_CHECK(cudaMalloc(&m->d_view_offsets, (size_t)(n_views + 1) * 4));
+    CU_CHECK(cudaMemsetAsync(m->d_f32, 0, (size_t)m->n_pad * DIM * 4, c->stream));
+    if (n > 0) CU_CHECK(cudaMemcpyAsync(m->d_f32, desc, (size_t)n * DIM * 4, cudaMemcpyHostToDevice, c->stream));
+    if (n > 0 && kpt_xy) CU_CHECK(cudaMemcpyAsync(m->d_kpt, kpt_xy, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    CU_CHECK(cudaMemcpyAsync(m->d_view_offsets, view_offsets, (size_t)(n_views + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    CU_CHECK(cudaMemsetAsync(c->d_flags + 1, 0, 4, c->stream));
+    launch_prep_rows(m->d_f32, n, m->n_pad, 0, m->d_b, m->d_aug, m->d_norm, c->d_flags + 1, c->stream);
+    c->launches++;
+    int flag = 0;
+    CU_CHECK(cudaMemcpyAsync(&flag, c->d_flags + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(cudaStreamSynchronize(c->stream));
+    m->nonint = flag;
+    *out = m;
+    return CVG_OK;
+}
+
+void cvg_models_free(cvg_ctx* c, cvg_models* m)
+{
+    if (!m) return;
+    if (c) cudaSetDevice(c->device);
+    cudaFree(m->d_f32); cudaFree(m->d_b); cudaFree(m->d_aug); cudaFree(m->d_norm); cudaFree(m->d_kpt);
+    cudaFree(m->d_view_offsets);
+    delete m;
+}
+
+int cvg_models_num_views(const cvg_models* m) { return m ? m->n_views : 0; }
+int cvg_models_num_rows(const cvg_models* m) { return m ? m->n_rows : 0; }
+
+}  // extern "C"
+
+// match `q` against a host train matrix; results to host
+static int match_host_train(cvg_ctx* c, QuerySide q, int q_nonint, const float* train, int n_train, float ratio,
+                            int32_t* idx, float* dist, uint8_t* accept)
+{
+    const int nq = q.row_end - q.row_begin;
+    if (nq <= 0) return CVG_OK;
+    if (n_train < 0 || (n_train > 0 && !train)) return set_err(CVG_ERR_INVALID, "bad train matrix");
+    if (!idx || !dist) return set_err(CVG_ERR_INVALID, "idx/dist must not be NULL");
+    TrainSet ts;
+    const int64_t offs[2] = { 0, n_train };
+    layout_segments(ts, offs, 1);
+    CU_CHECK(c->t_f32.ensure((size_t)std::max(n_train, 1) * DIM * 4));
+    ts.d_f32 = c->t_f32.as<float>();
+    if (n_train > 0) CU_CHECK(cudaMemcpyAsync(ts.d_f32, train, (size_t)n_train * DIM * 4, cudaMemcpyHostToDevice, c->stream));
+    CU_CHECK(cudaMemsetAsync(c->d_flags, 0, 4, c->stream));
+    int rc = prep_train(c, ts, c->t_b, c->t_aug, 0);
+    if (rc) return rc;
+    CU_CHECK(cudaMemcpyAsync(c->d_flags + 1, &q_nonint, 4, cudaMemcpyHostToDevice, c->stream));
+    combine_flags_kernel<<<1, 1, 0, c->stream>>>(c->d_flags, (c->flags & CVG_FORCE_EXACT_MATCH) ? 1 : 0);
+    c->launches++;
+    std::vector<MatchUnit> units; std::vector<MergeEntry> dir; int n_rb;
+    build_plan(q, ts, c->n_sms, units, dir, n_rb);
+    CU_CHECK(c->units.ensure(std::max<size_t>(units.size(), 1) * sizeof(MatchUnit)));
+    CU_CHECK(c->dir.ensure(std::max<size_t>(dir.size(), 1) * sizeof(MergeEntry)));
+    CU_CHECK(c->parts.ensure(std::max<size_t>(units.size(), 1) * TILE_M * sizeof(Top2)));
+    CU_CHECK(c->idx.ensure((size_t)nq * 8)); CU_CHECK(c->dist.ensure((size_t)nq * 8)); CU_CHECK(c->accept.ensure((size_t)nq));
+    if (!units.empty())
+        CU_CHECK(cudaMemcpyAsync(c->units.p, units.data(), units.size() * sizeof(MatchUnit), cudaMemcpyHostToDevice, c->stream));
+    CU_CHECK(cudaMemcpyAsync(c->dir.p, dir.data(), dir.size() * sizeof(MergeEntry), cudaMemcpyHostToDevice, c->stream));
+    rc = launch_match(c, q, ts, c->units.as<MatchUnit>(), (int)units.size(), c->dir.as<MergeEntry>(), n_rb, ratio, 0,
+                      c->parts.as<Top2>(), c->idx.as<int32_t>(), c->dist.as<float>(), c->accept.as<uint8_t>());
+    if (rc) return rc;
+    int flag = 0;
+    CU_CHECK(cudaMemcpyAsync(idx, c->idx.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(cudaMemcpyAsync(dist, c->dist.p, (size_t)nq * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (accept) CU_CHECK(cudaMemcpyAsync(accept, c->accept.p, (size_t)nq, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(cudaMemcpyAsync(&flag, c->d_flags + 2, 4, cudaMemcpyDeviceToHost, c->stream));
+    rc = sync_and_check(c);
+    if (rc) return rc;
+    c->last_match_path = flag ? 2 : 1;
+    return CVG_OK;
+}
+
+extern "C" {
+
+int cvg_match_knn2(cvg_ctx* c, const cvg_models* m, int view, const float* train, int n_train, float ratio,
+                   int32_t* idx, float* dist, uint8_t* accept)
+{
+    if (!c || !m) return set_err(CVG_ERR_INVALID, "cvg_match_knn2: NULL context/models");
+    if (view < -1 || view >= m->n_views) return set_err(CVG_ERR_INVALID, "cvg_match_knn2: view %d of %d", view, m->n_views);
+    CU_CHECK(cudaSetDevice(c->device));
+    QuerySide q{ m->d_f32, m->d_b, m->d_aug, m->d_norm, 0, m->n_rows, m->n_pad };
+    if (view >= 0) { q.row_begin = m->view_offsets[view]; q.row_end = m->view_offsets[view + 1]; }
+    return match_host_train(c, q, m->nonint, train, n_train, ratio, idx, dist, accept);
+}
+
+int cvg_match_knn2_raw(cvg_ctx* c, const float* query, int n_query, const float* train, int n_train, float ratio,
+                       int32_t* idx, float* dist, uint8_t* accept)
+{
+    if (!c) return set_err(CVG_ERR_INVALID, "cvg_match_knn2_raw: NULL context");
+    if (n_query < 0 || (n_query > 0 && !query)) return set_err(CVG_ERR_INVALID, "bad query matrix");
+    if (n_query == 0) return CVG_OK;
+    CU_CHECK(cudaSetDevice(c->device));
+    const int n_pad = round_up(n_query, TILE_M);
+    CU_CHECK(c->q_f32.ensure((size_t)n_pad * DIM * 4)); CU_CHECK(c->q_b.ensure((size_t)n_pad * DIM * 2));
+    CU_CHECK(c->q_aug.ensure((size_t)n_pad * KAUG * 2)); CU_CHECK(c->q_norm.ensure((size_t)n_pad * 4));
+    CU_CHECK(cudaMemcpyAsync(c->q_f32.p, query, (size_t)n_query * DIM * 4, cudaMemcpyHostToDevice, c->stream));
+    CU_CHECK(cudaMemsetAsync(c->d_flags + 3, 0, 4, c->stream));
+    launch_prep_rows(c->q_f32.as<float>(), n_query, n_pad, 0, c->q_b.as<__nv_bfloat16>(), c->q_aug.as<__nv_bfloat16>(),
+                     c->q_norm.as<float>(), c->d_flags + 3, c->stream);
+    c->launches++;
+    int qflag = 0;
+    CU_CHECK(cudaMemcpyAsync(&qflag, c->d_flags + 3, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(cudaStreamSynchronize(c->stream));
+    QuerySide q{ c->q_f32.as<float>(), c->q_b.as<__nv_bfloat16>(), c->q_aug.as<__nv_bfloat16>(), c->q_norm.as<float>(),
+                 0, n_query, n_pad };
+    return match_host_train(c, q, qflag, train, n_train, ratio, idx, dist, accept);
+}
+
+// ---- verify stage ---------------------------------------------------------------------------------
+int cvg_find_homography_batch(cvg_ctx* c, const float* src_xy, const float* dst_xy, const int64_t* offsets,
+                              int n_sets, const cvg_ransac_params* p, double* H, uint8_t* mask, int32_t* found,
+                              int32_t* iters, uint8_t* ransac_mask)
+{
+    if (!c || !offsets || n_sets < 0) return set_err(CVG_ERR_INVALID, "cvg_find_homography_batch: bad argument");
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (n_sets == 0) return CVG_OK;
+    CU_CHECK(cudaSetDevice(c->device));
+    const int64_t total = offsets[n_sets];
+    if (total < 0 || (total > 0 && (!src_xy || !dst_xy))) return set_err(CVG_ERR_INVALID, "bad point arrays");
+    std::vector<int64_t> starts(n_sets); std::vector<int32_t> cnts(n_sets);
+    int max_n = 0;
+    for (int k = 0; k < n_sets; k++) {
+        const int64_t n = offsets[k + 1] - offsets[k];
+        if (n < 0 || n > 0x7fffffff) return set_err(CVG_ERR_INVALID, "offsets must be non-decreasing");
+        starts[k] = offsets[k]; cnts[k] = (int32_t)n; max_n = std::max(max_n, (int)n);
+    }
+    const size_t tot = (size_t)std::max<int64_t>(total, 1);
+    CU_CHECK(c->src.ensure(tot * 8)); CU_CHECK(c->dst.ensure(tot * 8)); CU_CHECK(c->pts.ensure(tot * 16));
+    CU_CHECK(c->starts.ensure((size_t)n_sets * 8)); CU_CHECK(c->counts_n.ensure((size_t)n_sets * 4));
+    if (total > 0) {
+        CU_CHECK(cudaMemcpyAsync(c->src.p, src_xy, (size_t)total * 8, cudaMemcpyHostToDevice, c->stream));
+        CU_CHECK(cudaMemcpyAsync(c->dst.p, dst_xy, (size_t)total * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU_CHECK(cudaMemcpyAsync(c->starts.p, starts.data(), (size_t)n_sets * 8, cudaMemcpyHostToDevice, c->stream));
+    CU_CHECK(cudaMemcpyAsync(c->counts_n.p, cnts.data(), (size_t)n_sets * 4, cudaMemcpyHostToDevice, c->stream));
+    launch_pack_points(c->src.as<float>(), c->dst.as<float>(), total, c->pts.as<float4>(), c->stream);
+    c->launches++;
+    if (c->timing) cudaEventRecord(c->ev[0], c->stream);
+    rc = run_ransac(c, c->pts.as<float4>(), c->starts.as<int64_t>(), c->counts_n.as<int32_t>(), n_sets, max_n, total, p,
+                    ransac_mask != nullptr);
+    if (rc) return rc;
+    if (c->timing) cudaEventRecord(c->ev[1], c->stream);
+    if (H) CU_CHECK(cudaMemcpyAsync(H, c->H.p, (size_t)n_sets * 72, cudaMemcpyDeviceToHost, c->stream));
+    if (mask && total > 0) CU_CHECK(cudaMemcpyAsync(mask, c->mask.p, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+    if (ransac_mask && total > 0) CU_CHECK(cudaMemcpyAsync(ransac_mask, c->rmask.p, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+    if (found) CU_CHECK(cudaMemcpyAsync(found, c->found.p, (size_t)n_sets * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (iters) CU_CHECK(cudaMemcpyAsync(iters, c->iters_run.p, (size_t)n_sets * 4, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<int32_t> sflags(n_sets);
+    CU_CHECK(cudaMemcpyAsync(sflags.data(), c->sflags.p, (size_t)n_sets * 4, cudaMemcpyDeviceToHost, c->stream));
+    rc = sync_and_check(c);
+    if (rc) return rc;
+    if (c->timing) { cudaEventElapsedTime(&c->t_ransac, c->ev[0], c->ev[1]); c->t_match = 0; c->t_total = c->t_ransac; }
+    for (int k = 0; k < n_sets; k++)
+        if (sflags[k] & 1) return set_err(CVG_ERR_LIMIT, "set %d: RNG draw table exhausted (pathological rejection rate)", k);
+    return CVG_OK;
+}
+
+int cvg_find_homography(cvg_ctx* c, const float* src_xy, const float* dst_xy, int n, const cvg_ransac_params* p,
+                        double H[9], uint8_t* mask, int* found, uint8_t* ransac_mask)
+{
+    if (n < 4) return set_err(CVG_ERR_TOO_FEW_POINTS, "findHomography needs at least 4 correspondences (got %d)", n);
+    const int64_t offs[2] = { 0, n };
+    int32_t f = 0;
+    int rc = cvg_find_homography_batch(c, src_xy, dst_xy, offs, 1, p, H, mask, &f, nullptr, ransac_mask);
+    if (found) *found = f;
+    return rc;
+}
+
+}  // extern "C"
+
+// ---- fused detect over a prepared train set --------------------------------------------------------
+static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, TrainSet& ts, const float* d_scales,
+                         const cvg_detect_params* p, cvg_pair_result* per_pair, float* inlier_xy, int32_t* inlier_counts,
+                         bool host_needs_inliers)
+{
+    const int S = ts.n_segs, V = m->n_views, nq = m->n_rows;
+    const int P = S * V;
+    if (P == 0) return CVG_OK;
+    QuerySide q{ m->d_f32, m->d_b, m->d_aug, m->d_norm, 0, nq, m->n_pad };
+    int n_units = 0, n_rb = 0;
+    const MatchUnit* d_units; const MergeEntry* d_dir;
+    if (cache && cache->plan_models == m) {
+        n_units = cache->plan_units; n_rb = (nq + TILE_M - 1) / TILE_M;
+        d_units = cache->units.as<MatchUnit>(); d_dir = cache->dir.as<MergeEntry>();
+    } else {
+        std::vector<MatchUnit> units; std::vector<MergeEntry> dir;
+        build_plan(q, ts, c->n_sms, units, dir, n_rb);
+        DevBuf& ub = cache ? cache->units : c->units; DevBuf& db = cache ? cache->dir : c->dir;
+        CU_CHECK(ub.ensure(std::max<size_t>(units.size(), 1) * sizeof(MatchUnit)));
+        CU_CHECK(db.ensure(std::max<size_t>(dir.size(), 1) * sizeof(MergeEntry)));
+        if (!units.empty()) CU_CHECK(cudaMemcpyAsync(ub.p, units.data(), units.size() * sizeof(MatchUnit), cudaMemcpyHostToDevice, c->stream));
+        if (!dir.empty()) CU_CHECK(cudaMemcpyAsync(db.p, dir.data(), dir.size() * sizeof(MergeEntry), cudaMemcpyHostToDevice, c->stream));
+        CU_CHECK(cudaStreamSynchronize(c->stream));       // host vectors go out of scope
+        n_units = (int)units.size();
+        d_units = ub.as<MatchUnit>(); d_dir = db.as<MergeEntry>();
+        if (cache) { cache->plan_models = m; cache->plan_units = n_units; }
+    }
+    const size_t rows = (size_t)S * std::max(nq, 1);
+    CU_CHECK(c->parts.ensure(std::max<size_t>(n_units, 1) * TILE_M * sizeof(Top2)));
+    CU_CHECK(c->idx.ensure(rows * 8)); CU_CHECK(c->dist.ensure(rows * 8)); CU_CHECK(c->accept.ensure(rows));
+    CU_CHECK(c->pts.ensure(rows * 16)); CU_CHECK(c->starts.ensure((size_t)P * 8)); CU_CHECK(c->counts_n.ensure((size_t)P * 4));
+    CU_CHECK(c->results.ensure((size_t)P * sizeof(cvg_pair_result)));
+    CU_CHECK(c->inl_cnt.ensure((size_t)P * 4));
+    if (host_needs_inliers) CU_CHECK(c->inl_xy.ensure(rows * 8));
+
+    if (c->timing) cudaEventRecord(c->ev[0], c->stream);
+    const int path = (c->flags & CVG_FORCE_EXACT_MATCH) ? 2 : ((m->nonint || ts.nonint > 0) ? 2 : (ts.nonint == 0 ? 1 : 0));
+    if (path == 0) {
+        const int qn = m->nonint;
+        CU_CHECK(cudaMemcpyAsync(c->d_flags + 1, &qn, 4, cudaMemcpyHostToDevice, c->stream));
+        combine_flags_kernel<<<1, 1, 0, c->stream>>>(c->d_flags, 0);
+        c->launches++;
+    }
+    int rc = launch_match(c, q, ts, d_units, n_units, d_dir, n_rb, p->ratio, path, c->parts.as<Top2>(),
+                          c->idx.as<int32_t>(), c->dist.as<float>(), c->accept.as<uint8_t>());
+    if (rc) return rc;
+    CompactWork cw;
+    cw.n_segments = S; cw.n_views = V; cw.n_query = nq; cw.view_offsets = m->d_view_offsets;
+    cw.model_kpt = m->d_kpt; cw.scene_kpt = ts.d_kpt; cw.seg_kpt_offsets = ts.d_kpt_offsets;
+    cw.idx = c->idx.as<int32_t>(); cw.accept = c->accept.as<uint8_t>();
+    cw.pts = c->pts.as<float4>(); cw.starts = c->starts.as<int64_t>(); cw.n_good = c->counts_n.as<int32_t>();
+    launch_compact(cw, c->stream);
+    c->launches++;
+    if (c->timing) cudaEventRecord(c->ev[1], c->stream);
+    int max_view = 0;
+    for (int v = 0; v < V; v++) max_view = std::max(max_view, m->view_offsets[v + 1] - m->view_offsets[v]);
+    rc = run_ransac(c, c->pts.as<float4>(), c->starts.as<int64_t>(), c->counts_n.as<int32_t>(), P, max_view,
+                    (int64_t)rows, &p->ransac, false);
+    if (rc) return rc;
+    GateWork g;
+    g.n_pairs = P; g.pts = c->pts.as<float4>(); g.starts = c->starts.as<int64_t>(); g.counts_n = c->counts_n.as<int32_t>();
+    g.mask = c->mask.as<uint8_t>(); g.found = c->found.as<int32_t>(); g.H = c->H.as<double>();
+    g.iters_run = c->iters_run.as<int32_t>(); g.pair_scale = d_scales;
+    g.min_inliers = p->min_inliers; g.det_lo = p->det_lo; g.det_hi = p->det_hi;
+    g.results = c->results.as<cvg_pair_result>();
+    g.inlier_xy = host_needs_inliers ? c->inl_xy.as<float>() : nullptr; g.inlier_count = c->inl_cnt.as<int32_t>();
+    launch_gates(g, c->stream);
+    c->launches++;
+    if (c->timing) cudaEventRecord(c->ev[2], c->stream);
+    CU_CHECK(cudaGetLastError());
+    CU_CHECK(cudaMemcpyAsync(per_pair, c->results.p, (size_t)P * sizeof(cvg_pair_result), cudaMemcpyDeviceToHost, c->stream));
+    if (host_needs_inliers) {
+        CU_CHECK(cudaMemcpyAsync(inlier_counts, c->inl_cnt.p, (size_t)P * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU_CHECK(cudaMemcpyAsync(inlier_xy, c->inl_xy.p, rows * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    int flag = 0;
+    if (path == 0) CU_CHECK(cudaMemcpyAsync(&flag, c->d_flags + 2, 4, cudaMemcpyDeviceToHost, c->stream));
+    rc = sync_and_check(c);
+    if (rc) return rc;
+    c->last_match_path = path == 0 ? (flag ? 2 : 1) : path;
+    if (c->timing) {
+        cudaEventElapsedTime(&c->t_match, c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&c->t_ransac, c->ev[1], c->ev[2]);
+        cudaEventElapsedTime(&c->t_total, c->ev[0], c->ev[2]);
+    }
+    return CVG_OK;
+}
+
+static int check_detect_params(const cvg_detect_params* p)
+{
+    if (!p || p->size != sizeof(cvg_detect_params)) return set_err(CVG_ERR_INVALID, "cvg_detect_params: bad size field");
+    return check_params(&p->ransac);
+}
+
+extern "C" {
+
+int cvg_detect_pairs(cvg_ctx* c, const cvg_models* m, const float* scene_desc, const float* scene_kpt_xy, int n_train,
+                     float scale, const cvg_detect_params* p, cvg_pair_result* per_view, float* inlier_scene_xy,
+                     int32_t* inlier_offsets)
+{
+    if (!c || !m || !per_view) return set_err(CVG_ERR_INVALID, "cvg_detect_pairs: NULL argument");
+    int rc = check_detect_params(p);
+    if (rc) return rc;
+    if (n_train < 0 || (n_train > 0 && (!scene_desc || !scene_kpt_xy))) return set_err(CVG_ERR_INVALID, "bad scene arrays");
+    CU_CHECK(cudaSetDevice(c->device));
+    const int V = m->n_views;
+    TrainSet ts;
+    const int64_t offs[2] = { 0, n_train };
+    layout_segments(ts, offs, 1);
+    CU_CHECK(c->t_f32.ensure((size_t)std::max(n_train, 1) * DIM * 4));
+    CU_CHECK(c->t_kpt.ensure((size_t)std::max(n_train, 1) * 8));
+    CU_CHECK(c->t_kptoff.ensure(16));
+    CU_CHECK(c->scales.ensure((size_t)std::max(V, 1) * 4));
+    ts.d_f32 = c->t_f32.as<float>(); ts.d_kpt = c->t_kpt.as<float>(); ts.d_kpt_offsets = c->t_kptoff.as<int64_t>();
+    if (n_train > 0) {
+        CU_CHECK(cudaMemcpyAsync(ts.d_f32, scene_desc, (size_t)n_train * DIM * 4, cudaMemcpyHostToDevice, c->stream));
+        CU_CHECK(cudaMemcpyAsync(ts.d_kpt, scene_kpt_xy, (size_t)n_train * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    CU_CHECK(cudaMemcpyAsync(ts.d_kpt_offsets, offs, 16, cudaMemcpyHostToDevice, c->stream));
+    std::vector<float> scales(std::max(V, 1), scale);
+    CU_CHECK(cudaMemcpyAsync(c->scales.p, scales.data(), scales.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU_CHECK(cudaMemsetAsync(c->d_flags, 0, 4, c->stream));
+    rc = prep_train(c, ts, c->t_b, c->t_aug, 0);
+    if (rc) return rc;
+    ts.nonint = -1;                                    // decided on the device
+    const bool want_inl = inlier_scene_xy != nullptr && inlier_offsets != nullptr;
+    std::vector<float> pool; std::vector<int32_t> cnt;
+    if (want_inl) { pool.resize((size_t)std::max(m->n_rows, 1) * 2); cnt.resize(std::max(V, 1)); }
+    rc = detect_common(c, m, nullptr, ts, c->scales.as<float>(), p, per_view, want_inl ? pool.data() : nullptr,
+                       want_inl ? cnt.data() : nullptr, want_inl);
+    if (rc) return rc;
+    if (want_inl) {
+        int32_t o = 0;
+        for (int v = 0; v < V; v++) {
+            inlier_offsets[v] = o;
+            const size_t start = (size_t)m->view_offsets[v];
+            memcpy(inlier_scene_xy + 2 * (size_t)o, pool.data() + 2 * start, (size_t)cnt[v] * 8);
+            o += cnt[v];
+        }
+        inlier_offsets[V] = o;
+    }
+    return CVG_OK;
+}
+
+int cvg_scenes_upload(cvg_ctx* c, const float* desc, const float* kpt_xy, const int64_t* offsets, int n_scenes,
+                      cvg_scenes** out)
+{
+    if (!c || !out || !offsets || n_scenes < 0) return set_err(CVG_ERR_INVALID, "cvg_scenes_upload: bad argument");
+    *out = nullptr;
+    CU_CHECK(cudaSetDevice(c->device));
+    for (int s = 0; s < n_scenes; s++)
+        if (offsets[s + 1] < offsets[s]) return set_err(CVG_ERR_INVALID, "offsets must be non-decreasing");
+    const int64_t total = offsets[n_scenes];
+    if (total > 0 && !desc) return set_err(CVG_ERR_INVALID, "NULL desc");
+    cvg_scenes* sc = new cvg_scenes();
+    layout_segments(sc->ts, offsets, n_scenes);
+    if (sc->ts.rows_pad_total > 0x7fffff00LL) { delete sc; return set_err(CVG_ERR_LIMIT, "scene batch too large (>2^31 padded rows)"); }
+    CU_CHECK(sc->f32.ensure((size_t)std::max<int64_t>(total, 1) * DIM * 4));
+    CU_CHECK(sc->kpt.ensure((size_t)std::max<int64_t>(total, 1) * 8));
+    CU_CHECK(sc->kptoff.ensure((size_t)(n_scenes + 1) * 8));
+    sc->ts.d_f32 = sc->f32.as<float>(); sc->ts.d_kpt = sc->kpt.as<float>(); sc->ts.d_kpt_offsets = sc->kptoff.as<int64_t>();
+    if (total > 0) CU_CHECK(cudaMemcpyAsync(sc->ts.d_f32, desc, (size_t)total * DIM * 4, cudaMemcpyHostToDevice, c->stream));
+    if (total > 0 && kpt_xy) CU_CHECK(cudaMemcpyAsync(sc->ts.d_kpt, kpt_xy, (size_t)total * 8, cudaMemcpyHostToDevice, c->stream));
+    else if (total > 0) CU_CHECK(cudaMemsetAsync(sc->ts.d_kpt, 0, (size_t)total * 8, c->stream));
+    CU_CHECK(cudaMemcpyAsync(sc->ts.d_kpt_offsets, offsets, (size_t)(n_scenes + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU_CHECK(cudaMemsetAsync(c->d_flags, 0, 4, c->stream));
+    int rc = prep_train(c, sc->ts, sc->b, sc->aug, 0);
+    if (rc) { delete sc; return rc; }
+    int flag = 0;
+    CU_CHECK(cudaMemcpyAsync(&flag, c->d_flags, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(cudaStreamSynchronize(c->stream));
+    sc->ts.nonint = flag;
+    *out = sc;
+    return CVG_OK;
+}
+
+void cvg_scenes_free(cvg_ctx* c, cvg_scenes* sc)
+{
+    if (!sc) return;
+    if (c) cudaSetDevice(c->device);
+    sc->f32.release(); sc->b.release(); sc->aug.release(); sc->kpt.release(); sc->kptoff.release();
+    sc->units.release(); sc->dir.release();
+    delete sc;
+}
+
+int cvg_detect_scenes(cvg_ctx* c, const cvg_models* m, const cvg_scenes* scenes, const float* scales,
+                      const cvg_detect_params* p, cvg_pair_result* per_pair)
+{
+    if (!c || !m || !scenes || !per_pair) return set_err(CVG_ERR_INVALID, "cvg_detect_scenes: NULL argument");
+    int rc = check_detect_params(p);
+    if (rc) return rc;
+    CU_CHECK(cudaSetDevice(c->device));
+    cvg_scenes* sc = const_cast<cvg_scenes*>(scenes);
+    const int S = sc->ts.n_segs, V = m->n_views;
+    const float* d_scales = nullptr;
+    if (scales && S * V > 0) {
+        std::vector<float> ps((size_t)S * V);
+        for (int s = 0; s < S; s++) for (int v = 0; v < V; v++) ps[(size_t)s * V + v] = scales[s];
+        CU_CHECK(c->scales.ensure(ps.size() * 4));
+        CU_CHECK(cudaMemcpyAsync(c->scales.p, ps.data(), ps.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        CU_CHECK(cudaStreamSynchronize(c->stream));
+        d_scales = c->scales.as<float>();
+    }
+    return detect_common(c, m, sc, sc->ts, d_scales, p, per_pair, nullptr, nullptr, false);
+}
+
+// ---- device-pointer building blocks -----------------------------------------------------------------
+int cvg_dev_match_top2(cvg_ctx* c, void* stream, const float* query_dev, int n_query, const float* train_dev,
+                       int n_train, int32_t train_index_base, float* dist_dev, int32_t* idx_dev)
+{
+    if (!c || n_query < 0 || n_train < 0) return set_err(CVG_ERR_INVALID, "cvg_dev_match_top2: bad argument");
+    if (n_query == 0) return CVG_OK;
+    CU_CHECK(cudaSetDevice(c->device));
+    cudaStream_t user = (cudaStream_t)stream;
+    // order our stream after the caller's and back (the context owns its scratch and its stream)
+    CU_CHECK(cudaEventRecord(c->ev[3], user));
+    CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev[3], 0));
+    const int n_pad = round_up(n_query, TILE_M);
+    CU_CHECK(c->q_b.ensure((size_t)n_pad * DIM * 2)); CU_CHECK(c->q_aug.ensure((size_t)n_pad * KAUG * 2));
+    CU_CHECK(c->q_norm.ensure((size_t)n_pad * 4));
+    CU_CHECK(cudaMemsetAsync(c->d_flags, 0, 16, c->stream));
+    launch_prep_rows(query_dev, n_query, n_pad, 0, c->q_b.as<__nv_bfloat16>(), c->q_aug.as<__nv_bfloat16>(),
+                     c->q_norm.as<float>(), c->d_flags + 1, c->stream);
+    c->launches++;
+    TrainSet ts;
+    const int64_t offs[2] = { 0, n_train };
+    layout_segments(ts, offs, 1);
+    ts.d_f32 = const_cast<float*>(train_dev);
+    int rc = prep_train(c, ts, c->t_b, c->t_aug, 0);
+    if (rc) return rc;
+    combine_flags_kernel<<<1, 1, 0, c->stream>>>(c->d_flags, (c->flags & CVG_FORCE_EXACT_MATCH) ? 1 : 0);
+    c->launches++;
+    QuerySide q{ query_dev, c->q_b.as<__nv_bfloat16>(), c->q_aug.as<__nv_bfloat16>(), c->q_norm.as<float>(), 0, n_query, n_pad };
+    std::vector<MatchUnit> units; std::vector<MergeEntry> dir; int n_rb;
+    build_plan(q, ts, c->n_sms, units, dir, n_rb);
+    CU_CHECK(c->units.ensure(std::max<size_t>(units.size(), 1) * sizeof(MatchUnit)));
+    CU_CHECK(c->dir.ensure(std::max<size_t>(dir.size(), 1) * sizeof(MergeEntry)));
+    CU_CHECK(c->parts.ensure(std::max<size_t>(units.size(), 1) * TILE_M * sizeof(Top2)));
+    CU_CHECK(c->idx.ensure((size_t)n_query * 8)); CU_CHECK(c->dist.ensure((size_t)n_query * 8));
+    if (!units.empty()) CU_CHECK(cudaMemcpyAsync(c->units.p, units.data(), units.size() * sizeof(MatchUnit), cudaMemcpyHostToDevice, c->stream));
+    CU_CHECK(cudaMemcpyAsync(c->dir.p, dir.data(), dir.size() * sizeof(MergeEntry), cudaMemcpyHostToDevice, c->stream));
+    CU_CHECK(cudaStreamSynchronize(c->stream));
+    rc = launch_match(c, q, ts, c->units.as<MatchUnit>(), (int)units.size(), c->dir.as<MergeEntry>(), n_rb, 0.9f, 0,
+                      c->parts.as<Top2>(), c->idx.as<int32_t>(), c->dist.as<float>(), nullptr);
+    if (rc) return rc;
+    launch_shift_index(c->idx.as<int32_t>(), c->dist.as<float>(), n_query, train_index_base, dist_dev, idx_dev, c->stream);
+    c->launches++;
+    CU_CHECK(cudaEventRecord(c->ev[3], c->stream));
+    CU_CHECK(cudaStreamWaitEvent(user, c->ev[3], 0));
+    return CVG_OK;
+}
+
+int cvg_dev_merge_top2(cvg_ctx* c, void* stream, const float* dist_parts_dev, const int32_t* idx_parts_dev, int n_parts,
+                       int n_query, float ratio, int32_t* idx_dev, float* dist_dev, uint8_t* accept_dev)
+{
+    if (!c || n_parts < 1 || n_query < 0) return set_err(CVG_ERR_INVALID, "cvg_dev_merge_top2: bad argument");
+    CU_CHECK(cudaSetDevice(c->device));
+    launch_merge_parts(dist_parts_dev, idx_parts_dev, n_parts, n_query, ratio, idx_dev, dist_dev, accept_dev,
+                       (cudaStream_t)stream);
+    c->launches++;
+    CU_CHECK(cudaGetLastError());
+    return CVG_OK;
+}
+
+}  // extern "C"

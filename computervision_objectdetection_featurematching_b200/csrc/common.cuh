@@ -1,0 +1,127 @@
+// common.cuh — shared declarations of libcvgraft's translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/cvgraft.h"
+
+namespace cvg {
+
+constexpr int DIM = CVG_DESC_DIM;       // 128
+constexpr int KAUG = 16;                // extra K columns that fold ||t||^2 into the contraction
+constexpr int TILE_M = 128;             // query rows per tile (TMEM lanes)
+constexpr int TILE_N = 256;             // train rows per tile (TMEM columns of one accumulator)
+
+// One unit of match work: 128 query rows against a run of train tiles of one segment (a segment is
+// one scene / one train matrix).  A unit produces one partial top-2 record per query row.
+struct MatchUnit {
+    int32_t q_row0;          // first query row (multiple of TILE_M)
+    int32_t t_row0;          // first train row in the concatenated, padded train matrix
+    int32_t n_tiles;         // number of TILE_N-wide train tiles
+    int32_t t_local0;        // index of t_row0 inside its segment (train index reported = local)
+    int32_t part_slot;       // partial record block: parts[part_slot * TILE_M + row]
+    int32_t seg_cols;        // valid train rows of the segment (for masking the padded tail)
+    int32_t t_row0_f32;      // first train row in the unpadded fp32 train matrix (exact kernel)
+    int32_t pad1;
+};
+
+// Partial / final top-2 record of one query row.
+struct __align__(16) Top2 {
+    float d1; int32_t i1; float d2; int32_t i2;
+};
+
+// Per (segment, row-block) directory entry for the merge kernel.
+struct MergeEntry {
+    int32_t first_slot;      // first partial slot
+    int32_t n_slots;         // consecutive slots (ascending train order)
+};
+
+// ---- launchers (defined in the .cu files) --------------------------------------------------------
+// prep.cu
+void launch_prep_rows(const float* X, int n_rows, int n_pad, int is_train, __nv_bfloat16* Xb,
+                      __nv_bfloat16* Xaug, float* norms, int* nonint_flag, cudaStream_t st);
+void launch_pack_points(const float* src_xy, const float* dst_xy, int64_t n, float4* pts, cudaStream_t st);
+
+// match_exact.cu — fp32 SIMT kernel in cv::batchDistance's summation order
+void launch_match_exact(const float* Q, int n_query, const float* T, const MatchUnit* units, int n_units,
+                        Top2* parts, const int* run_if_flag /*device flag: run only if *flag != 0, or NULL*/,
+                        cudaStream_t st);
+
+// match_tc.cu — tcgen05 / TMEM / TMA kernel
+struct TcOperands {
+    const __nv_bfloat16* Qb; const __nv_bfloat16* Qaug; const float* qnorm; int nq_pad;
+    const __nv_bfloat16* Tb; const __nv_bfloat16* Taug; int nt_pad;
+};
+int  tc_init(char* err, size_t errlen);     // resolves cuTensorMapEncodeTiled; 0 = ok
+int  launch_match_tc(const TcOperands& op, const MatchUnit* units, int n_units, Top2* parts,
+                     const int* skip_if_flag /*device flag: skip if *flag != 0*/, int* dbg, int n_sms,
+                     cudaStream_t st, char* err, size_t errlen);
+
+// merge.cu (in match_exact.cu)
+void launch_merge(const Top2* parts, const MergeEntry* dir, int n_segments, int n_rowblocks, int n_query,
+                  float ratio, int32_t* idx, float* dist, uint8_t* accept, cudaStream_t st);
+void launch_merge_parts(const float* dist_parts, const int32_t* idx_parts, int n_parts, int n_query, float ratio,
+                        int32_t* idx, float* dist, uint8_t* accept, cudaStream_t st);
+void launch_shift_index(const int32_t* idx_in, const float* dist_in, int n_query, int32_t idx_base,
+                        float* dist, int32_t* idx, cudaStream_t st);
+
+// ransac.cu
+struct RansacWork {
+    const float4* pts;          // correspondence pool, (X, Y, x, y)
+    const int64_t* starts;      // [P] first pool row of set k
+    const int32_t* counts_n;    // [P] number of correspondences of set k
+    int n_sets;
+    int max_n;                  // upper bound of counts_n (host-known; sizes nothing, tunes launches)
+    int max_iters;
+    float thr2;                 // (float)(thr*thr)
+    double conf;
+    uint32_t flags;
+    const uint32_t* rng_tab;    // raw cv::RNG outputs for the fixed seed, [rng_len]
+    int64_t rng_len;
+    // scratch
+    int32_t* sample_pos;        // [P, max_iters] draw position where the accepted attempt starts
+    int32_t* n_samples;         // [P]
+    int32_t* counts;            // [P, max_iters]
+    int32_t* best_iter;         // [P]
+    int32_t* best_count;        // [P]
+    int32_t* iters_run;         // [P]
+    int32_t* sel;               // [total] compacted inlier indices
+    // outputs
+    double* H;                  // [P, 9]
+    uint8_t* mask;              // [total]
+    uint8_t* ransac_mask;       // [total] or NULL
+    int32_t* found;             // [P]
+    int32_t* status_flags;      // [P] bit0: rng table exhausted
+};
+void launch_ransac(const RansacWork& w, cudaStream_t st);
+
+// detect glue (ransac.cu)
+struct GateWork {
+    int n_pairs;
+    const float4* pts; const int64_t* starts; const int32_t* counts_n;   // per pair correspondences
+    const uint8_t* mask; const int32_t* found; const double* H; const int32_t* iters_run;
+    const float* pair_scale;                        // [n_pairs] or NULL
+    int min_inliers; float det_lo, det_hi;
+    cvg_pair_result* results;                       // [n_pairs] device
+    float* inlier_xy;                               // [total, 2] compacted per pair at offsets, or NULL
+    int32_t* inlier_count;                          // [n_pairs]
+};
+void launch_gates(const GateWork& g, cudaStream_t st);
+
+// compaction of accepted matches into correspondences, per (segment, view) pair
+struct CompactWork {
+    int n_segments, n_views, n_query;
+    const int32_t* view_offsets;                    // [V+1] device
+    const float* model_kpt;                         // [n_query, 2]
+    const float* scene_kpt;                         // concatenated scene keypoints
+    const int64_t* seg_kpt_offsets;                 // [S+1] rows into scene_kpt
+    const int32_t* idx; const uint8_t* accept;      // [S, n_query, 2], [S, n_query]
+    float4* pts;                                    // [S * n_query] pool: pair (s,v) at s*n_query + view_offsets[v]
+    int64_t* starts;                                // [S*V]
+    int32_t* n_good;                                // [S*V]
+};
+void launch_compact(const CompactWork& c, cudaStream_t st);
+
+}  // namespace cvg

@@ -1,0 +1,356 @@
+// match_tc.cu — tensor-core match kernel for sm_100a: TMA -> shared memory -> tcgen05.mma -> TMEM ->
+// fused per-query top-2 epilogue.  No distance matrix ever reaches HBM.
+//
+// Reference: BFMatcher(NORM_L2).knnMatch(view_desc, scene_desc, 2), src/TestsDetector.cpp:59-60.
+// The accumulator is  acc' = 2 q.t - ||t||^2  (operands prepared by prep.cu; exact for integer
+// descriptors), so the nearest train row maximises acc' and  d^2 = ||q||^2 - acc'.
+//
+// CTA = 320 threads, one CTA per SM, persistent over a static list of units (128 query rows x a run
+// of 256-wide train tiles):
+//   warp 0      TMA producer   : A tile (queries, resident per unit, double-buffered) and a 2-stage
+//                                ring of B tiles (train rows), SWIZZLE_128B, + the 16-column norm
+//                                augmentation (SWIZZLE_32B)
+//   warp 1      MMA issuer     : 8 x tcgen05.mma (M128 N256 K16, bf16 -> fp32) + 1 augmentation MMA per
+//                                tile into one of two 256-column TMEM accumulators; owns TMEM alloc
+//   warps 2-9   epilogue       : tcgen05.ld 32x32b.x32 (thread = query row, 32 train columns per
+//                                load), running top-2 per row kept in registers across the unit, two
+//                                warps per TMEM lane quarter (column halves), merged at unit end
+// Pipelines: a_full/a_empty, b_full/b_empty (TMA <-> MMA), t_full/t_empty (MMA <-> epilogue).
+#include "common.cuh"
+#include <cuda.h>
+#include <string.h>
+
+namespace cvg {
+
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;                // 320
+constexpr uint32_t A_ATOM_BYTES = TILE_M * 128;                   // 128 rows x 64 bf16          16 KB
+constexpr uint32_t A_AUG_BYTES = TILE_M * KAUG * 2;               // 128 rows x 16 bf16           4 KB
+constexpr uint32_t A_BYTES = 2 * A_ATOM_BYTES + A_AUG_BYTES;      //                             36 KB
+constexpr uint32_t B_ATOM_BYTES = TILE_N * 128;                   //                             32 KB
+constexpr uint32_t B_AUG_BYTES = TILE_N * KAUG * 2;               //                              8 KB
+constexpr uint32_t B_BYTES = 2 * B_ATOM_BYTES + B_AUG_BYTES;      //                             72 KB
+constexpr uint32_t OFF_A = 0;
+constexpr uint32_t OFF_B = 2 * A_BYTES;                           //  72 KB
+constexpr uint32_t OFF_SCRATCH = OFF_B + 2 * B_BYTES;             // 216 KB
+constexpr uint32_t SCRATCH_BYTES = TILE_M * 16;
+constexpr uint32_t OFF_BAR = OFF_SCRATCH + SCRATCH_BYTES;
+constexpr uint32_t TC_SMEM_BYTES = OFF_BAR + 256 + 1024;          // + alignment slack
+constexpr float ABSENT_BELOW = -5.0e8f;                           // padded train rows carry -2^30
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* dbg, int code)
+{
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); spin++) {
+        if (spin > (1u << 26)) {
+            if (dbg) { dbg[0] = code; dbg[1] = (int)blockIdx.x; dbg[2] = (int)threadIdx.x; }
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptors (K-major).  Bits: [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4,
+// [46,48) version = 1 (Blackwell), [61,64) layout type (2 = SWIZZLE_128B, 6 = SWIZZLE_32B).
+__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ uint64_t desc_sw32(uint32_t saddr)
+{
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46) | (6ull << 61);
+}
+// instruction descriptor, kind::f16: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1),
+// both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+
+struct TcMaps { CUtensorMap q, qaug, t, taug; };
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ qnorm,
+                const MatchUnit* __restrict__ units, int n_units, Top2* __restrict__ parts,
+                const int* __restrict__ skip_if_flag, int* dbg)
+{
+    if (skip_if_flag && *skip_if_flag != 0) return;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bar0 = smem_base + OFF_BAR;
+    // barrier slots (8 bytes each)
+    const uint32_t a_full = bar0, a_empty = bar0 + 16, b_full = bar0 + 32, b_empty = bar0 + 48;
+    const uint32_t t_full = bar0 + 64, t_empty = bar0 + 80;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 128);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; i++) {
+            mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1);
+            mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1);
+            mbar_init(t_full + 8 * i, 1); mbar_init(t_empty + 8 * i, TC_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t ua = 0, bs = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ua++) {
+                const MatchUnit un = units[u];
+                const uint32_t ab = ua & 1;
+                mbar_wait(a_empty + 8 * ab, ((ua >> 1) & 1) ^ 1, dbg, 1);
+                const uint32_t sa = smem_base + OFF_A + ab * A_BYTES;
+                mbar_expect_tx(a_full + 8 * ab, A_BYTES);
+                tma_load_2d(sa, &maps.q, 0, un.q_row0, a_full + 8 * ab);
+                tma_load_2d(sa + A_ATOM_BYTES, &maps.q, 64, un.q_row0, a_full + 8 * ab);
+                tma_load_2d(sa + 2 * A_ATOM_BYTES, &maps.qaug, 0, un.q_row0, a_full + 8 * ab);
+                for (int t = 0; t < un.n_tiles; t++, bs++) {
+                    const uint32_t s = bs & 1;
+                    mbar_wait(b_empty + 8 * s, ((bs >> 1) & 1) ^ 1, dbg, 2);
+                    const uint32_t sb = smem_base + OFF_B + s * B_BYTES;
+                    const int row = un.t_row0 + t * TILE_N;
+                    mbar_expect_tx(b_full + 8 * s, B_BYTES);
+                    tma_load_2d(sb, &maps.t, 0, row, b_full + 8 * s);
+                    tma_load_2d(sb + B_ATOM_BYTES, &maps.t, 64, row, b_full + 8 * s);
+                    tma_load_2d(sb + 2 * B_ATOM_BYTES, &maps.taug, 0, row, b_full + 8 * s);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t ua = 0, bs = 0, tc = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ua++) {
+                const int n_tiles = units[u].n_tiles;
+                const uint32_t ab = ua & 1;
+                mbar_wait(a_full + 8 * ab, (ua >> 1) & 1, dbg, 3);
+                const uint32_t sa = smem_base + OFF_A + ab * A_BYTES;
+                for (int t = 0; t < n_tiles; t++, bs++, tc++) {
+                    const uint32_t s = bs & 1, acc = tc & 1;
+                    mbar_wait(b_full + 8 * s, (bs >> 1) & 1, dbg, 4);
+                    mbar_wait(t_empty + 8 * acc, ((tc >> 1) & 1) ^ 1, dbg, 5);
+                    tc_fence_after();
+                    const uint32_t sb = smem_base + OFF_B + s * B_BYTES;
+                    const uint32_t d_tmem = tmem_base + acc * TILE_N;
+                    #pragma unroll
+                    for (int k = 0; k < DIM / 16; k++) {
+                        const uint32_t koff = (uint32_t)(k & 3) * 32u;       // 16 bf16 = 32 B inside the swizzle atom
+                        const uint64_t da = desc_sw128(sa + (k >> 2) * A_ATOM_BYTES + koff);
+                        const uint64_t db = desc_sw128(sb + (k >> 2) * B_ATOM_BYTES + koff);
+                        tc_mma_bf16(d_tmem, da, db, TC_IDESC, k > 0 ? 1u : 0u);
+                    }
+                    tc_mma_bf16(d_tmem, desc_sw32(sa + 2 * A_ATOM_BYTES), desc_sw32(sb + 2 * B_ATOM_BYTES), TC_IDESC, 1u);
+                    tc_commit(b_empty + 8 * s);          // smem stage reusable once these MMAs retire
+                    tc_commit(t_full + 8 * acc);         // accumulator ready for the epilogue
+                }
+                tc_commit(a_empty + 8 * ab);
+            }
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int ew = warp - 2;
+        const int quarter = warp & 3;                    // TMEM lanes this warp may touch: 32*(warp%4)..
+        const int half = ew >> 2;                        // which 128 columns of the 256-wide accumulator
+        const int row_in_tile = quarter * 32 + lane;
+        Top2* scratch = reinterpret_cast<Top2*>(smem + OFF_SCRATCH);
+        uint32_t tc = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const MatchUnit un = units[u];
+            float b1 = -INFINITY, b2 = -INFINITY;
+            int i1 = -1, i2 = -1;
+            for (int t = 0; t < un.n_tiles; t++, tc++) {
+                const uint32_t acc = tc & 1;
+                mbar_wait(t_full + 8 * acc, (tc >> 1) & 1, dbg, 6);
+                tc_fence_after();
+                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TILE_N + half * 128;
+                const int col_base = un.t_local0 + t * TILE_N + half * 128;
+                #pragma unroll 1
+                for (int ch = 0; ch < 4; ch++) {
+                    uint32_t r[32];
+                    tc_ld32(tbase + ch * 32, r);
+                    tc_wait_ld();
+                    float m = __uint_as_float(r[0]);
+                    #pragma unroll
+                    for (int j = 1; j < 32; j++) m = fmaxf(m, __uint_as_float(r[j]));
+                    if (m > b2) {
+                        const int c0 = col_base + ch * 32;
+                        #pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            const float v = __uint_as_float(r[j]);
+                            if (v > b2) {                               // strict: earlier (lower) index wins ties
+                                if (v > b1) { b2 = b1; i2 = i1; b1 = v; i1 = c0 + j; }
+                                else        { b2 = v; i2 = c0 + j; }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t_empty + 8 * acc);
+            }
+            // ---- unit flush: merge the two column halves, convert to distances, write the partial ----
+            if (b1 < ABSENT_BELOW) { i1 = -1; }
+            if (b2 < ABSENT_BELOW) { i2 = -1; }
+            if (half == 1) {
+                Top2 o; o.d1 = b1; o.i1 = i1; o.d2 = b2; o.i2 = i2;
+                scratch[row_in_tile] = o;
+            }
+            asm volatile("bar.sync 1, %0;" :: "n"(32 * TC_EPI_WARPS) : "memory");
+            if (half == 0) {
+                const Top2 o = scratch[row_in_tile];
+                // larger acc' first, ties -> lower train index
+                const float cv[2] = { o.d1, o.d2 };
+                const int ci[2] = { o.i1, o.i2 };
+                #pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    const float v = cv[k]; const int i = ci[k];
+                    if (i < 0) continue;
+                    if (i1 < 0 || v > b1 || (v == b1 && i < i1)) { b2 = b1; i2 = i1; b1 = v; i1 = i; }
+                    else if (i2 < 0 || v > b2 || (v == b2 && i < i2)) { b2 = v; i2 = i; }
+                }
+                const float qn = qnorm[un.q_row0 + row_in_tile];
+                Top2 out;
+                out.i1 = i1; out.i2 = i2;
+                out.d1 = i1 >= 0 ? sqrtf(fmaxf(qn - b1, 0.f)) : INFINITY;
+                out.d2 = i2 >= 0 ? sqrtf(fmaxf(qn - b2, 0.f)) : INFINITY;
+                parts[(size_t)un.part_slot * TILE_M + row_in_tile] = out;
+            }
+            asm volatile("bar.sync 1, %0;" :: "n"(32 * TC_EPI_WARPS) : "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base) : "memory");
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+int tc_init(char* err, size_t errlen)
+{
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+        snprintf(err, errlen, "cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
+        return 1;
+    }
+    g_encode = (EncodeTiledFn)fn;
+    e = cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+    if (e != cudaSuccess) {
+        snprintf(err, errlen, "cudaFuncSetAttribute(match_tc_kernel): %s", cudaGetErrorString(e));
+        g_encode = nullptr;
+        return 1;
+    }
+    return 0;
+}
+
+static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint32_t cols, uint32_t box_cols,
+                    uint32_t box_rows, CUtensorMapSwizzle sw, char* err, size_t errlen)
+{
+    cuuint64_t gdim[2] = { cols, rows };
+    cuuint64_t gstride[1] = { (cuuint64_t)cols * 2 };
+    cuuint32_t box[2] = { box_cols, box_rows };
+    cuuint32_t estr[2] = { 1, 1 };
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(err, errlen, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%u", (int)r, (unsigned long long)rows, cols);
+        return 1;
+    }
+    return 0;
+}
+
+int launch_match_tc(const TcOperands& op, const MatchUnit* units, int n_units, Top2* parts,
+                    const int* skip_if_flag, int* dbg, int n_sms, cudaStream_t st, char* err, size_t errlen)
+{
+    if (n_units <= 0) return 0;
+    if (tc_init(err, errlen)) return 1;
+    TcMaps maps;
+    if (make_map(&maps.q, op.Qb, op.nq_pad, DIM, 64, TILE_M, CU_TENSOR_MAP_SWIZZLE_128B, err, errlen)) return 1;
+    if (make_map(&maps.qaug, op.Qaug, op.nq_pad, KAUG, KAUG, TILE_M, CU_TENSOR_MAP_SWIZZLE_32B, err, errlen)) return 1;
+    if (make_map(&maps.t, op.Tb, op.nt_pad, DIM, 64, TILE_N, CU_TENSOR_MAP_SWIZZLE_128B, err, errlen)) return 1;
+    if (make_map(&maps.taug, op.Taug, op.nt_pad, KAUG, KAUG, TILE_N, CU_TENSOR_MAP_SWIZZLE_32B, err, errlen)) return 1;
+    const int grid = n_units < n_sms ? n_units : n_sms;
+    match_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, op.qnorm, units, n_units, parts, skip_if_flag, dbg);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(err, errlen, "match_tc_kernel launch: %s", cudaGetErrorString(e));
+        return 1;
+    }
+    return 0;
+}
+
+}  // namespace cvg

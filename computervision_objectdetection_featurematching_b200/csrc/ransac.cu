@@ -1,0 +1,607 @@
+// ransac.cu — batched verify stage: cv::findHomography(src, dst, RANSAC, thr, mask) for P independent
+// correspondence sets at once, plus the gates of the reference's view loop.
+//
+// Replaces reference src/TestsDetector.cpp:77-94 (findHomography :78, H.empty :79, countNonZero :81,
+// determinant :84, inlier gather + rescale :87-94).  Semantics: cv2 4.13.0, SURVEY.md App. B / D.
+//
+// OpenCV's loop is serial (one RNG stream with data-dependent consumption, adaptive stop).  The
+// parallel decomposition keeps its results bit for bit (App. D.5):
+//   1. sample kernel   — replays cv::RNG + getSubset + checkSubset.  The raw RNG stream for the fixed
+//                        per-call seed is a constant table in HBM, so an attempt starting at draw
+//                        position p can be evaluated independently; a block evaluates 128 speculative
+//                        attempts at p, p+4, ... in parallel and accepts the regular prefix.
+//   2. hypothesis kernel — one hypothesis per thread: 4-point normalised DLT (9x9 Jacobi, fp64, no FMA),
+//                        then fp32 scoring of all correspondences staged through shared memory
+//                        (each point is read once per 128 hypotheses, broadcast to the warp).
+//   3. select kernel   — the sequential "good > max(best,3)" / RANSACUpdateNumIters scan, one warp per
+//                        set, so the winner is the hypothesis the serial loop would have kept.
+//   4. finish kernel   — winner's inlier mask, DLT refit on the inliers, 9-parameter LM (10 iterations),
+//                        mask recomputed from the refined H.  Sets with <= EXACT_MAX_INLIERS inliers use
+//                        OpenCV's exact summation order (bit-exact H); larger sets use block reductions.
+#include "common.cuh"
+#include "homography_math.cuh"
+
+namespace cvg {
+
+constexpr int RS_THREADS = 128;
+constexpr int EXACT_MAX_INLIERS = 128;
+constexpr int SMEM_PTS = 1024;              // correspondences staged per shared-memory tile
+
+// ---- draw 4 distinct indices starting at table position p (getSubset's inner loop) ----------------
+// returns the number of draws consumed, or -1 when the table would be overrun
+__device__ __forceinline__ int draw_subset(const uint32_t* __restrict__ tab, int64_t tab_len, int64_t p,
+                                           uint32_t n, int idx[4])
+{
+    int64_t pos = p;
+    #pragma unroll
+    for (int i = 0; i < 4; i++) {
+        for (;;) {
+            if (pos >= tab_len) return -1;
+            const int v = (int)(tab[pos++] % n);
+            bool dup = false;
+            #pragma unroll
+            for (int k = 0; k < 4; k++) dup |= (k < i) && (idx[k] == v);
+            if (!dup) { idx[i] = v; break; }
+        }
+    }
+    return (int)(pos - p);
+}
+
+// ---- 1. sample kernel ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RS_THREADS)
+ransac_sample_kernel(RansacWork w)
+{
+    const int set = blockIdx.x;
+    const int n = w.counts_n[set];
+    int32_t* out = w.sample_pos + (size_t)set * w.max_iters;
+    if (n <= 4) {                                   // n < 4: nothing; n == 4: handled by finish kernel
+        if (threadIdx.x == 0) { w.n_samples[set] = 0; w.status_flags[set] = 0; }
+        return;
+    }
+    const float4* __restrict__ pts = w.pts + w.starts[set];
+    __shared__ float4 spts[SMEM_PTS];
+    __shared__ int s_first[RS_THREADS / 32];
+    __shared__ int s_cons, s_ok;
+    const bool staged = n <= SMEM_PTS;
+    if (staged) {
+        for (int i = threadIdx.x; i < n; i += RS_THREADS) spts[i] = pts[i];
+        __syncthreads();
+    }
+    int64_t pos = 0;
+    int iter = 0, attempts = 0, flags = 0;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    while (iter < w.max_iters) {
+        // speculative attempt starting at pos + 4*t
+        const int64_t p = pos + 4 * (int64_t)threadIdx.x;
+        int idx[4];
+        int cons = draw_subset(w.rng_tab, w.rng_len, p, (uint32_t)n, idx);
+        bool ok = false;
+        if (cons > 0) {
+            float ms1[8], ms2[8];
+            #pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float4 q = staged ? spts[idx[i]] : pts[idx[i]];
+                ms1[2 * i] = q.x; ms1[2 * i + 1] = q.y; ms2[2 * i] = q.z; ms2[2 * i + 1] = q.w;
+            }
+            ok = check_subset4(ms1, ms2);
+        }
+        const bool regular = ok && cons == 4;
+        const unsigned bal = __ballot_sync(0xffffffffu, !regular);
+        if (lane == 0) s_first[wid] = bal ? (wid * 32 + __ffs(bal) - 1) : RS_THREADS;
+        __syncthreads();
+        int first = RS_THREADS;
+        #pragma unroll
+        for (int k = RS_THREADS / 32 - 1; k >= 0; k--) if (s_first[k] < RS_THREADS) first = s_first[k];
+        if ((int)threadIdx.x == first) { s_cons = cons; s_ok = ok ? 1 : 0; }
+        const int m = min(first, w.max_iters - iter);
+        if ((int)threadIdx.x < m) out[iter + threadIdx.x] = (int32_t)p;
+        __syncthreads();
+        iter += m;
+        pos += 4 * (int64_t)m;
+        if (m > 0) attempts = 0;
+        if (first < RS_THREADS && iter < w.max_iters) {
+            const int c = s_cons;
+            if (c < 0) { flags |= 1; break; }                    // RNG table exhausted
+            if (s_ok) {
+                if (threadIdx.x == 0) out[iter] = (int32_t)pos;
+                iter++; attempts = 0;
+            } else {
+                if (++attempts >= 10000) break;                  // getSubset gave up
+            }
+            pos += c;
+        }
+        if (pos + 4 * RS_THREADS + 64 >= 0x7fffffffLL) { flags |= 1; break; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { w.n_samples[set] = iter; w.status_flags[set] = flags; }
+}
+
+// ---- 2. hypothesis kernel: solve + score ------------------------------------------------------------
+__device__ __forceinline__ bool solve_hypothesis(const RansacWork& w, const float4* __restrict__ pts, int n,
+                                                 int32_t pos, float Hf[8], double* Hd)
+{
+    int idx[4];
+    draw_subset(w.rng_tab, w.rng_len, pos, (uint32_t)n, idx);
+    float ms1[8], ms2[8];
+    #pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float4 q = pts[idx[i]];
+        ms1[2 * i] = q.x; ms1[2 * i + 1] = q.y; ms2[2 * i] = q.z; ms2[2 * i + 1] = q.w;
+    }
+    double H[9], LtL[81], V[81];
+    Pts4 P{ ms1, ms2 };
+    if (!run_kernel_seq(P, 4, H, LtL, V)) return false;
+    #pragma unroll
+    for (int i = 0; i < 8; i++) Hf[i] = (float)H[i];
+    if (Hd) for (int i = 0; i < 9; i++) Hd[i] = H[i];
+    return true;
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+ransac_hyp_kernel(RansacWork w)
+{
+    const int set = blockIdx.y;
+    const int n = w.counts_n[set];
+    const int n_samples = w.n_samples[set];
+    const int iter0 = blockIdx.x * RS_THREADS;
+    if (iter0 >= n_samples) return;
+    const float4* __restrict__ pts = w.pts + w.starts[set];
+    const int iter = iter0 + threadIdx.x;
+    const bool active = iter < n_samples;
+    float Hf[8];
+    bool valid = false;
+    if (active) valid = solve_hypothesis(w, pts, n, w.sample_pos[(size_t)set * w.max_iters + iter], Hf, nullptr);
+    if (!valid) {
+        #pragma unroll
+        for (int i = 0; i < 8; i++) Hf[i] = 0.f;
+    }
+    __shared__ float4 spts[SMEM_PTS];
+    int good = 0;
+    for (int base = 0; base < n; base += SMEM_PTS) {
+        const int cnt = min(SMEM_PTS, n - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt; i += RS_THREADS) spts[i] = pts[base + i];
+        __syncthreads();
+        #pragma unroll 4
+        for (int i = 0; i < cnt; i++) {
+            const float4 q = spts[i];                              // broadcast read
+            const float e = reproj_err(Hf, q.x, q.y, q.z, q.w);
+            good += (e <= w.thr2) ? 1 : 0;                         // NaN -> not an inlier
+        }
+    }
+    if (active) w.counts[(size_t)set * w.max_iters + iter] = valid ? good : -1;
+}
+
+// ---- 3. select kernel: the serial scan of RANSACPointSetRegistrator::run --------------------------
+__global__ void ransac_select_kernel(RansacWork w)
+{
+    const int set = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (set >= w.n_sets) return;
+    const int n = w.counts_n[set];
+    const int n_samples = w.n_samples[set];
+    const int32_t* __restrict__ counts = w.counts + (size_t)set * w.max_iters;
+    int niters = max(w.max_iters, 1);
+    int best = 0, best_iter = -1;
+    int base = 0;
+    while (base < niters && base < n_samples) {
+        const int it = base + lane;
+        const int c = (it < n_samples) ? counts[it] : -1;
+        int start = 0;
+        for (;;) {
+            const bool cand = lane >= start && it < niters && it < n_samples && c > max(best, 3);
+            const unsigned bal = __ballot_sync(0xffffffffu, cand);
+            if (!bal) break;
+            const int f = __ffs(bal) - 1;
+            best = __shfl_sync(0xffffffffu, c, f);
+            best_iter = base + f;
+            if (!(w.flags & CVG_RANSAC_NO_EARLY_STOP))
+                niters = update_num_iters(w.conf, (double)(n - best) / n, niters);
+            start = f + 1;
+        }
+        base += 32;
+    }
+    if (lane == 0) {
+        w.best_iter[set] = best_iter;
+        w.best_count[set] = best;
+        // value of `iter` when the reference loop exits
+        w.iters_run[set] = n <= 4 ? 0 : min(niters, n_samples);
+    }
+}
+
+// ---- block reductions (parallel mode of the finish kernel) ----------------------------------------
+__device__ __forceinline__ double shfl_down_d(double v, int o)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_down_sync(0xffffffffu, lo, o);
+    hi = __shfl_down_sync(0xffffffffu, hi, o);
+    return __hiloint2double(hi, lo);
+}
+
+// sums vals[0..K) over the block; result valid in every thread (through out[]); fixed order
+template <int K>
+__device__ void block_sum(double* vals, double* s_part /*[4*K]*/, double* s_out /*[K]*/)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    #pragma unroll
+    for (int k = 0; k < K; k++) {
+        double v = vals[k];
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = v + shfl_down_d(v, o);
+        if (lane == 0) s_part[wid * K + k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < K) {
+        double v = s_part[threadIdx.x];
+        #pragma unroll
+        for (int q = 1; q < RS_THREADS / 32; q++) v = v + s_part[q * K + threadIdx.x];
+        s_out[threadIdx.x] = v;
+    }
+    __syncthreads();
+    #pragma unroll
+    for (int k = 0; k < K; k++) vals[k] = s_out[k];
+    __syncthreads();
+}
+
+struct FinishShared {
+    double part[4 * 56];
+    double out[56];
+    LmState lm;
+    double H[9];
+    double scratch_a[81], scratch_v[81];
+    float Hf[8];
+    int flag;
+    int warp_cnt[RS_THREADS / 32];
+    int base_cnt;
+};
+
+// S, rmax and optionally A, v at parameters h, reduced over the block (parallel mode)
+__device__ double lm_eval_block(const float4* __restrict__ pts, const int32_t* __restrict__ sel, int count,
+                                const double* h, double* A, double* v, double* rmax, FinishShared& sh)
+{
+    double acc[56];
+    #pragma unroll
+    for (int k = 0; k < 56; k++) acc[k] = 0;
+    double rm = 0;
+    const bool wantJ = A != nullptr;
+    for (int i = threadIdx.x; i < count; i += RS_THREADS) {
+        const float4 q = pts[sel[i]];
+        double r0, r1, J0[9], J1[9];
+        refine_row(h, q.x, q.y, q.z, q.w, r0, r1, wantJ ? J0 : nullptr, wantJ ? J1 : nullptr);
+        acc[55] += r0 * r0; acc[55] += r1 * r1;
+        rm = fmax(rm, fmax(fabs(r0), fabs(r1)));
+        if (wantJ) {
+            int e = 0;
+            #pragma unroll
+            for (int j = 0; j < 9; j++) {
+                #pragma unroll
+                for (int k = j; k < 9; k++) { acc[e] += J0[j] * J0[k]; acc[e] += J1[j] * J1[k]; e++; }
+                acc[45 + j] += J0[j] * r0; acc[45 + j] += J1[j] * r1;
+            }
+        }
+    }
+    // max via the same machinery (monotone: reduce as a sum of one-hot is not possible) -> separate
+    acc[54] = 0;
+    block_sum<56>(acc, sh.part, sh.out);
+    // rmax: warp + block max
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rm = fmax(rm, shfl_down_d(rm, o));
+    if ((threadIdx.x & 31) == 0) sh.part[threadIdx.x >> 5] = rm;
+    __syncthreads();
+    rm = fmax(fmax(sh.part[0], sh.part[1]), fmax(sh.part[2], sh.part[3]));
+    __syncthreads();
+    if (wantJ) {
+        int e = 0;
+        for (int j = 0; j < 9; j++) {
+            for (int k = j; k < 9; k++) { A[j * 9 + k] = acc[e]; A[k * 9 + j] = acc[e]; e++; }
+            v[j] = acc[45 + j];
+        }
+    }
+    if (rmax) *rmax = rm;
+    return acc[55];
+}
+
+// ---- 4. finish kernel -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(RS_THREADS)
+ransac_finish_kernel(RansacWork w)
+{
+    const int set = blockIdx.x;
+    const int n = w.counts_n[set];
+    const int64_t start = w.starts[set];
+    const float4* __restrict__ pts = w.pts + start;
+    uint8_t* mask = w.mask + start;
+    uint8_t* rmask = w.ransac_mask ? w.ransac_mask + start : nullptr;
+    int32_t* sel = w.sel + start;
+    double* Hout = w.H + (size_t)set * 9;
+    __shared__ FinishShared sh;
+    const int tid = threadIdx.x;
+
+    auto fail = [&]() {
+        for (int i = tid; i < n; i += RS_THREADS) { mask[i] = 0; if (rmask) rmask[i] = 0; }
+        if (tid < 9) Hout[tid] = 0.0;
+        if (tid == 0) w.found[set] = 0;
+    };
+    if (n < 4) { fail(); return; }
+    if (n == 4) {                                            // B.1: direct runKernel, mask of ones, no LM
+        if (tid == 0) {
+            PtsStrided P{ pts, nullptr };
+            sh.flag = run_kernel_seq(P, 4, sh.H, sh.scratch_a, sh.scratch_v) ? 1 : 0;
+        }
+        __syncthreads();
+        if (!sh.flag) { fail(); return; }
+        if (tid < 4) { mask[tid] = 1; if (rmask) rmask[tid] = 1; }
+        if (tid < 9) Hout[tid] = sh.H[tid];
+        if (tid == 0) w.found[set] = 1;
+        return;
+    }
+    const int best_iter = w.best_iter[set];
+    if (best_iter < 0) { fail(); return; }
+
+    // winner's model again (deterministic) -> its mask, in original order
+    if (tid == 0) {
+        float Hf[8];
+        solve_hypothesis(w, pts, n, w.sample_pos[(size_t)set * w.max_iters + best_iter], Hf, sh.H);
+        for (int i = 0; i < 8; i++) sh.Hf[i] = Hf[i];
+        sh.base_cnt = 0;
+    }
+    __syncthreads();
+    float Hf[8];
+    #pragma unroll
+    for (int i = 0; i < 8; i++) Hf[i] = sh.Hf[i];
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int base = 0; base < n; base += RS_THREADS) {       // ordered compaction of inlier indices
+        const int i = base + tid;
+        bool in = false;
+        if (i < n) {
+            const float4 q = pts[i];
+            in = reproj_err(Hf, q.x, q.y, q.z, q.w) <= w.thr2;
+            if (rmask) rmask[i] = in ? 1 : 0;
+            if (w.flags & CVG_RANSAC_NO_REFINE) mask[i] = in ? 1 : 0;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) sh.warp_cnt[wid] = __popc(bal);
+        __syncthreads();
+        int off = sh.base_cnt;
+        for (int k = 0; k < wid; k++) off += sh.warp_cnt[k];
+        if (in) sel[off + __popc(bal & ((1u << lane) - 1))] = i;
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int k = 0; k < RS_THREADS / 32; k++) t += sh.warp_cnt[k]; sh.base_cnt += t; }
+        __syncthreads();
+    }
+    const int n_inl = sh.base_cnt;
+    if (w.flags & CVG_RANSAC_NO_REFINE) {
+        if (tid < 9) Hout[tid] = sh.H[tid];
+        if (tid == 0) w.found[set] = 1;
+        return;
+    }
+    if (n_inl > 0) {
+        PtsStrided P{ pts, sel };
+        if (n_inl <= EXACT_MAX_INLIERS) {
+            // exact mode: OpenCV's sequential summation order, one thread
+            if (tid == 0) {
+                double Hn[9];
+                if (run_kernel_seq(P, n_inl, Hn, sh.scratch_a, sh.scratch_v))     // B.7 refit
+                    for (int i = 0; i < 9; i++) sh.H[i] = Hn[i];
+                lm_refine_seq(P, n_inl, sh.H, 10, sh.lm, sh.scratch_a, sh.scratch_v);   // B.8
+            }
+            __syncthreads();
+        } else {
+            // parallel mode: block reductions (deterministic, not OpenCV's order; H agrees to ~1e-8)
+            double s[8];
+            #pragma unroll
+            for (int k = 0; k < 8; k++) s[k] = 0;
+            for (int i = tid; i < n_inl; i += RS_THREADS) {
+                const float4 q = pts[sel[i]];
+                s[0] += q.z; s[1] += q.w; s[2] += q.x; s[3] += q.y;
+            }
+            block_sum<4>(s, sh.part, sh.out);
+            const double cmx = s[0] / n_inl, cmy = s[1] / n_inl, cMx = s[2] / n_inl, cMy = s[3] / n_inl;
+            #pragma unroll
+            for (int k = 0; k < 4; k++) s[k] = 0;
+            for (int i = tid; i < n_inl; i += RS_THREADS) {
+                const float4 q = pts[sel[i]];
+                s[0] += fabs(q.z - cmx); s[1] += fabs(q.w - cmy); s[2] += fabs(q.x - cMx); s[3] += fabs(q.y - cMy);
+            }
+            block_sum<4>(s, sh.part, sh.out);
+            const bool ok = !(fabs(s[0]) < DBL_EPSILON || fabs(s[1]) < DBL_EPSILON ||
+                              fabs(s[2]) < DBL_EPSILON || fabs(s[3]) < DBL_EPSILON);
+            if (ok) {
+                const double smx = n_inl / s[0], smy = n_inl / s[1], sMx = n_inl / s[2], sMy = n_inl / s[3];
+                double L[45];
+                #pragma unroll
+                for (int k = 0; k < 45; k++) L[k] = 0;
+                for (int i = tid; i < n_inl; i += RS_THREADS) {
+                    const float4 q = pts[sel[i]];
+                    const double x = (q.z - cmx) * smx, y = (q.w - cmy) * smy;
+                    const double X = (q.x - cMx) * sMx, Y = (q.y - cMy) * sMy;
+                    const double Lx[9] = { X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x };
+                    const double Ly[9] = { 0, 0, 0, X, Y, 1, -y * X, -y * Y, -y };
+                    int e = 0;
+                    #pragma unroll
+                    for (int j = 0; j < 9; j++)
+                        #pragma unroll
+                        for (int k = j; k < 9; k++) { L[e] += Lx[j] * Lx[k] + Ly[j] * Ly[k]; e++; }
+                }
+                block_sum<45>(L, sh.part, sh.out);
+                if (tid == 0) {
+                    double* LtL = sh.scratch_a;
+                    int e = 0;
+                    for (int j = 0; j < 9; j++)
+                        for (int k = j; k < 9; k++) { LtL[j * 9 + k] = L[e]; LtL[k * 9 + j] = L[e]; e++; }
+                    double Hn[9];
+                    dlt_finish(LtL, sh.scratch_v, cMx, cMy, cmx, cmy, sMx, sMy, smx, smy, Hn);
+                    for (int i = 0; i < 9; i++) sh.H[i] = Hn[i];
+                }
+                __syncthreads();
+            }
+            // LM with block-evaluated reductions; thread 0 runs the scalar schedule
+            LmState& st = sh.lm;
+            if (tid < 9) st.x[tid] = sh.H[tid];
+            __syncthreads();
+            {
+                double A[81], v[9], rmax;
+                const double S = lm_eval_block(pts, sel, n_inl, st.x, A, v, &rmax, sh);
+                if (tid == 0) {
+                    for (int i = 0; i < 81; i++) st.A[i] = A[i];
+                    for (int i = 0; i < 9; i++) st.v[i] = v[i];
+                    st.S = S; st.rmax = rmax;
+                    lm_begin(st);
+                }
+                __syncthreads();
+            }
+            for (;;) {
+                if (tid == 0) lm_step(st, sh.scratch_a, sh.scratch_v);
+                __syncthreads();
+                const double Sd = lm_eval_block(pts, sel, n_inl, st.xd, nullptr, nullptr, nullptr, sh);
+                if (tid == 0) sh.flag = lm_update(st, Sd, sh.scratch_a, sh.scratch_v) ? 1 : 0;
+                __syncthreads();
+                if (sh.flag) {
+                    if (tid < 9) st.x[tid] = st.xd[tid];
+                    __syncthreads();
+                    double A[81], v[9], rmax;
+                    const double S = lm_eval_block(pts, sel, n_inl, st.x, A, v, &rmax, sh);
+                    if (tid == 0) {
+                        for (int i = 0; i < 81; i++) st.A[i] = A[i];
+                        for (int i = 0; i < 9; i++) st.v[i] = v[i];
+                        st.S = S; st.rmax = rmax;
+                    }
+                    __syncthreads();
+                }
+                if (tid == 0) sh.flag = lm_proceed(st, 10) ? 1 : 0;
+                __syncthreads();
+                if (!sh.flag) break;
+            }
+            if (tid == 0) {
+                const double sc = 1. / st.x[8];
+                for (int i = 0; i < 9; i++) sh.H[i] = st.x[i] * sc;
+            }
+            __syncthreads();
+        }
+        // B.9: returned mask = err(H_final) <= thr^2 over ALL correspondences
+        #pragma unroll
+        for (int i = 0; i < 8; i++) Hf[i] = (float)sh.H[i];
+        for (int i = tid; i < n; i += RS_THREADS) {
+            const float4 q = pts[i];
+            mask[i] = reproj_err(Hf, q.x, q.y, q.z, q.w) <= w.thr2 ? 1 : 0;
+        }
+    } else {
+        for (int i = tid; i < n; i += RS_THREADS) mask[i] = 0;
+    }
+    if (tid < 9) Hout[tid] = sh.H[tid];
+    if (tid == 0) w.found[set] = 1;
+}
+
+void launch_ransac(const RansacWork& w, cudaStream_t st)
+{
+    if (w.n_sets <= 0) return;
+    ransac_sample_kernel<<<w.n_sets, RS_THREADS, 0, st>>>(w);
+    dim3 grid((w.max_iters + RS_THREADS - 1) / RS_THREADS, w.n_sets);
+    ransac_hyp_kernel<<<grid, RS_THREADS, 0, st>>>(w);
+    const int warps_per_block = 4;
+    ransac_select_kernel<<<(w.n_sets + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(w);
+    ransac_finish_kernel<<<w.n_sets, RS_THREADS, 0, st>>>(w);
+}
+
+// ---- gates + inlier gather: reference src/TestsDetector.cpp:74-94 ---------------------------------
+__global__ void gates_kernel(GateWork g)
+{
+    const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (pair >= g.n_pairs) return;
+    const int n = g.counts_n[pair];
+    const int64_t start = g.starts[pair];
+    const uint8_t* mask = g.mask + start;
+    const float4* pts = g.pts + start;
+    const bool found = n >= 4 && g.found[pair] != 0;
+    int cnt = 0;
+    if (found)
+        for (int i = lane; i < n; i += 32) cnt += mask[i] ? 1 : 0;
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    double H[9];
+    #pragma unroll
+    for (int i = 0; i < 9; i++) H[i] = found ? g.H[(size_t)pair * 9 + i] : 0.0;
+    const double det = found ? det3(H) : 0.0;
+    int status;
+    if (n < g.min_inliers) status = CVG_PAIR_LT4_MATCHES;                     // :74
+    else if (!found) status = CVG_PAIR_H_EMPTY;                              // :79
+    else if (cnt < g.min_inliers) status = CVG_PAIR_LT4_INLIERS;             // :81
+    else {
+        const double ad = fabs(det);                                          // :84, float constants promoted
+        status = (ad < (double)g.det_lo || ad > (double)g.det_hi) ? CVG_PAIR_DET_REJECT : CVG_PAIR_ACCEPT;
+    }
+    if (lane == 0) {
+        cvg_pair_result r;
+        r.status = status; r.n_good = n; r.n_inliers = found ? cnt : 0;
+        r.ransac_iters = g.iters_run ? g.iters_run[pair] : 0;
+        for (int i = 0; i < 9; i++) r.H[i] = H[i];
+        r.det = det;
+        g.results[pair] = r;
+    }
+    if (g.inlier_xy) {
+        // :87-94 — inlier scene points, in order, divided by scale when scale != 1.0f
+        int written = 0;
+        if (status == CVG_PAIR_ACCEPT) {
+            const float scale = g.pair_scale ? g.pair_scale[pair] : 1.0f;
+            float* out = g.inlier_xy + 2 * start;
+            for (int base = 0; base < n; base += 32) {
+                const int i = base + lane;
+                const bool in = i < n && mask[i];
+                const unsigned bal = __ballot_sync(0xffffffffu, in);
+                if (in) {
+                    const int o = written + __popc(bal & ((1u << lane) - 1));
+                    float x = pts[i].z, y = pts[i].w;
+                    if (scale != 1.0f) { x = __fdiv_rn(x, scale); y = __fdiv_rn(y, scale); }
+                    out[2 * o] = x; out[2 * o + 1] = y;
+                }
+                written += __popc(bal);
+            }
+        }
+        if (lane == 0) g.inlier_count[pair] = written;
+    }
+}
+
+void launch_gates(const GateWork& g, cudaStream_t st)
+{
+    if (g.n_pairs <= 0) return;
+    gates_kernel<<<(g.n_pairs + 3) / 4, 128, 0, st>>>(g);
+}
+
+// ---- compaction of ratio-test survivors into correspondences: reference src/TestsDetector.cpp:62-72 --
+// one warp per (segment, view) pair; output order = query order
+__global__ void compact_kernel(CompactWork c)
+{
+    const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (pair >= c.n_segments * c.n_views) return;
+    const int seg = pair / c.n_views, view = pair % c.n_views;
+    const int r0 = c.view_offsets[view], r1 = c.view_offsets[view + 1];
+    const int64_t start = (int64_t)seg * c.n_query + r0;
+    const int32_t* idx = c.idx + (size_t)seg * c.n_query * 2;
+    const uint8_t* acc = c.accept + (size_t)seg * c.n_query;
+    const float2* mk = reinterpret_cast<const float2*>(c.model_kpt);
+    const float2* sk = reinterpret_cast<const float2*>(c.scene_kpt) + c.seg_kpt_offsets[seg];
+    float4* out = c.pts + start;
+    int written = 0;
+    for (int base = r0; base < r1; base += 32) {
+        const int q = base + lane;
+        const bool in = q < r1 && acc[q];
+        const unsigned bal = __ballot_sync(0xffffffffu, in);
+        if (in) {
+            const float2 a = mk[q];                           // model.keypoints[i][queryIdx].pt   :68
+            const float2 b = sk[idx[2 * q]];                  // sceneKP[trainIdx].pt              :69
+            out[written + __popc(bal & ((1u << lane) - 1))] = make_float4(a.x, a.y, b.x, b.y);
+        }
+        written += __popc(bal);
+    }
+    if (lane == 0) { c.starts[pair] = start; c.n_good[pair] = written; }
+}
+
+void launch_compact(const CompactWork& c, cudaStream_t st)
+{
+    const int n = c.n_segments * c.n_views;
+    if (n <= 0) return;
+    compact_kernel<<<(n + 3) / 4, 128, 0, st>>>(c);
+}
+
+}  // namespace cvg

@@ -1,0 +1,197 @@
+/*
+ * cvgraft.h — C ABI of libcvgraft: B200-native (sm_100a) descriptor matching + RANSAC homography.
+ *
+ * Drop-in boundary for the hot path of mattreturn1/ComputerVision_ObjectDetection_FeatureMatching.
+ * The reference has no plugin/FFI interface; the seam is the pair of OpenCV calls inside
+ * detectObjects() (reference include/TestsDetector.hpp:13-17):
+ *
+ *     matcher.knnMatch(model.descriptors[i], sceneDesc, knnMatches, 2)   src/TestsDetector.cpp:59-60
+ *     ratio test + point gather                                          src/TestsDetector.cpp:62-72
+ *     findHomography(objPts, scenePts, RANSAC, 5.0, inlierMask)          src/TestsDetector.cpp:77-78
+ *     H.empty / countNonZero / determinant gates, inlier gather          src/TestsDetector.cpp:74,79-94
+ *
+ * plus the model hand-off after src/ModelsDetector.cpp:78-80 (descriptors uploaded once, resident
+ * in HBM).  Each entry point below names the reference lines it replaces.  Semantics are those of
+ * cv2 4.13.0; INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions: plain C, POD structs with a leading `size` field, int return codes (0 = ok), no
+ * exceptions across the ABI.  Unless a name says `_dev`, every pointer is caller-owned HOST memory
+ * and is not retained after the call returns.  A context is bound to one CUDA device and is not
+ * re-entrant (one in-flight call per context).  There is no CPU fallback: every entry point fails
+ * with CVG_ERR_CUDA when no sm_100 device is present.
+ */
+#ifndef CVGRAFT_H
+#define CVGRAFT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVG_DESC_DIM 128            /* SIFT descriptor length (reference: cv::SIFT, 128 x CV_32F)   */
+
+/* return codes */
+enum {
+    CVG_OK = 0,
+    CVG_ERR_INVALID = 1,            /* bad argument                                                  */
+    CVG_ERR_CUDA = 2,               /* CUDA runtime/driver failure, see cvg_last_error()             */
+    CVG_ERR_TOO_FEW_POINTS = 3,     /* findHomography with n < 4 (OpenCV throws, fundam.cpp)         */
+    CVG_ERR_NOMEM = 4,
+    CVG_ERR_LIMIT = 5               /* size beyond a documented limit                                */
+};
+
+/* per-pair gate outcome — reference src/TestsDetector.cpp:74 / :79 / :81 / :84 */
+enum {
+    CVG_PAIR_ACCEPT = 0,
+    CVG_PAIR_LT4_MATCHES = 1,       /* goodMatches.size() < MIN_INLIERS            :74               */
+    CVG_PAIR_H_EMPTY = 2,           /* H.empty()                                   :79               */
+    CVG_PAIR_LT4_INLIERS = 3,       /* countNonZero(inlierMask) < MIN_INLIERS      :81               */
+    CVG_PAIR_DET_REJECT = 4         /* fabs(determinant(H)) outside [0.1f, 10.0f]  :84               */
+};
+
+/* cvg_ransac_params.flags */
+#define CVG_RANSAC_NO_EARLY_STOP 1u /* score all max_iters hypotheses, niters never shrinks          */
+                                    /* (throughput mode of BASELINE config 5; not OpenCV semantics)  */
+#define CVG_RANSAC_NO_REFINE     2u /* stop after the RANSAC stage: no DLT refit, no LM               */
+
+/* cvg_create flags */
+#define CVG_FORCE_EXACT_MATCH 1u    /* always use the fp32 SIMT match kernel (debug / A-B tests)     */
+
+typedef struct cvg_ctx cvg_ctx;
+typedef struct cvg_models cvg_models;   /* resident model-view descriptor set                        */
+typedef struct cvg_scenes cvg_scenes;   /* resident batch of scene descriptor sets (bench / multi-GPU)*/
+
+/* findHomography(..., RANSAC, threshold, mask, maxIters, confidence) — src/TestsDetector.cpp:23,78 */
+typedef struct cvg_ransac_params {
+    uint32_t size;                  /* = sizeof(cvg_ransac_params)                                   */
+    uint32_t flags;
+    double threshold;               /* RANSAC_THRESHOLD = 5.0            src/TestsDetector.cpp:23    */
+    double confidence;              /* OpenCV default 0.995                                          */
+    int32_t max_iters;              /* OpenCV default 2000                                           */
+    int32_t reserved;
+} cvg_ransac_params;
+
+/* constants of detectObjects() — src/TestsDetector.cpp:21-25 */
+typedef struct cvg_detect_params {
+    uint32_t size;                  /* = sizeof(cvg_detect_params)                                   */
+    float ratio;                    /* MATCH_RATIO_THRESHOLD = 0.9f                       :21        */
+    int32_t min_inliers;            /* MIN_INLIERS = 4                                    :22        */
+    float det_lo;                   /* HOMOGRAPHY_DET_THRESHOLD = 0.1f                    :24        */
+    float det_hi;                   /* HOMOGRAPHY_DET_UPPER_THRESHOLD = 10.0f             :25        */
+    int32_t reserved;
+    cvg_ransac_params ransac;
+} cvg_detect_params;
+
+typedef struct cvg_pair_result {
+    int32_t status;                 /* CVG_PAIR_*                                                    */
+    int32_t n_good;                 /* matches that passed the ratio test                            */
+    int32_t n_inliers;              /* countNonZero(inlierMask) (0 when no H)                        */
+    int32_t ransac_iters;           /* RANSAC iterations the reference loop would have run           */
+    double H[9];                    /* row-major 3x3, H[8] == 1; zeros when status is LT4/H_EMPTY     */
+    double det;                     /* determinant(H)                                                */
+} cvg_pair_result;
+
+void cvg_ransac_params_default(cvg_ransac_params* p);
+void cvg_detect_params_default(cvg_detect_params* p);
+
+/* ---- context -------------------------------------------------------------------------------- */
+int  cvg_create(cvg_ctx** out, int device, unsigned flags);
+void cvg_destroy(cvg_ctx* ctx);
+const char* cvg_last_error(void);   /* thread-local message of the last failing call                 */
+const char* cvg_version(void);
+
+/* ---- model set: replaces nothing, hooks after src/ModelsDetector.cpp:78-80 -------------------
+ * desc [N,128] row-major fp32 (all views concatenated), kpt_xy [N,2] (KeyPoint.pt),
+ * view_offsets [V+1] row ranges per view, view_model [V] owning ObjectModel index (may be NULL).
+ * The copy is converted once and stays resident in HBM until cvg_models_free. */
+int  cvg_models_upload(cvg_ctx* ctx, const float* desc, const float* kpt_xy,
+                       const int32_t* view_offsets, const int32_t* view_model, int n_views,
+                       cvg_models** out);
+void cvg_models_free(cvg_ctx* ctx, cvg_models* models);
+int  cvg_models_num_views(const cvg_models* models);
+int  cvg_models_num_rows(const cvg_models* models);
+
+/* ---- match stage: replaces src/TestsDetector.cpp:59-60 (+ the compare of :67) ----------------
+ * BFMatcher(NORM_L2).knnMatch(query, train, k=2) for the rows of one view (view >= 0) or of all
+ * views (view == -1) against `train` [n_train,128].  Outputs, per query row i in order:
+ *   idx[2i..2i+1]  nearest / second nearest train index, -1 where OpenCV returns a shorter list
+ *   dist[2i..2i+1] their L2 distances (fp32, as DMatch.distance)
+ *   accept[i]      m.size()==2 && m[0].distance < ratio*m[1].distance   (may be NULL)
+ * Ties resolve to the lower train index; NaN/inf distances are never returned (App. A.1-A.4). */
+int  cvg_match_knn2(cvg_ctx* ctx, const cvg_models* models, int view,
+                    const float* train, int n_train, float ratio,
+                    int32_t* idx, float* dist, uint8_t* accept);
+
+/* Same for an arbitrary query matrix [n_query,128] in host memory. */
+int  cvg_match_knn2_raw(cvg_ctx* ctx, const float* query, int n_query,
+                        const float* train, int n_train, float ratio,
+                        int32_t* idx, float* dist, uint8_t* accept);
+
+/* ---- verify stage: replaces src/TestsDetector.cpp:77-79 --------------------------------------
+ * findHomography(src, dst, RANSAC, p->threshold, mask, p->max_iters, p->confidence).
+ * H gets the 3x3 CV_64F result (zeros if none), mask [n] the returned inlier mask, *found = 0 iff
+ * OpenCV returns an empty H.  n < 4 -> CVG_ERR_TOO_FEW_POINTS.  ransac_mask (may be NULL) receives
+ * the mask of the winning RANSAC hypothesis before refit/LM. */
+int  cvg_find_homography(cvg_ctx* ctx, const float* src_xy, const float* dst_xy, int n,
+                         const cvg_ransac_params* p, double H[9], uint8_t* mask, int* found,
+                         uint8_t* ransac_mask);
+
+/* Batched form: P independent point sets, set k = rows [offsets[k], offsets[k+1]) of src/dst.
+ * Sets with fewer than 4 points report found=0.  iters (may be NULL) [P] = RANSAC iterations. */
+int  cvg_find_homography_batch(cvg_ctx* ctx, const float* src_xy, const float* dst_xy,
+                               const int64_t* offsets, int n_sets, const cvg_ransac_params* p,
+                               double* H /*[P,9]*/, uint8_t* mask, int32_t* found /*[P]*/,
+                               int32_t* iters /*[P]*/, uint8_t* ransac_mask);
+
+/* ---- fused path: replaces the body of the view loop, src/TestsDetector.cpp:58-95 -------------
+ * All views of the resident model set against one scene (descriptors [n_train,128] + keypoints
+ * [n_train,2]).  per_view [V]: status, counts, H, det.  inlier_scene_xy receives, view after view,
+ * the scene points of the inliers of ACCEPTED views divided by `scale` when scale != 1.0f
+ * (:87-94, :48-55); inlier_offsets [V+1] delimits them.  Capacity of inlier_scene_xy: n_rows of the
+ * model set x 2 floats.  Either may be NULL. */
+int  cvg_detect_pairs(cvg_ctx* ctx, const cvg_models* models,
+                      const float* scene_desc, const float* scene_kpt_xy, int n_train, float scale,
+                      const cvg_detect_params* p, cvg_pair_result* per_view,
+                      float* inlier_scene_xy, int32_t* inlier_offsets);
+
+/* ---- resident scene batches (inputs already in HBM; used by bench.py `value` and the shards) --
+ * cvg_scenes_upload copies S scene descriptor sets (concatenated, offsets [S+1]) to the device
+ * once.  cvg_detect_scenes then runs every view of `models` against every scene: S*V pairs, no
+ * host->device input traffic.  per_pair is [S*V] (scene-major).  scales [S] may be NULL (=1). */
+int  cvg_scenes_upload(cvg_ctx* ctx, const float* desc, const float* kpt_xy,
+                       const int64_t* offsets, int n_scenes, cvg_scenes** out);
+void cvg_scenes_free(cvg_ctx* ctx, cvg_scenes* scenes);
+int  cvg_detect_scenes(cvg_ctx* ctx, const cvg_models* models, const cvg_scenes* scenes,
+                       const float* scales, const cvg_detect_params* p, cvg_pair_result* per_pair);
+
+/* ---- device-pointer building blocks (multi-GPU train-tile sharding, BASELINE config 5) --------
+ * All pointers are DEVICE memory of the context's GPU; `stream` is a cudaStream_t (NULL = default).
+ * cvg_dev_match_top2: local top-2 of every query row against this rank's train tile, as
+ *   distances dist [nq,2] (fp32, +inf where absent) and GLOBAL train indices idx [nq,2]
+ *   (local index + train_index_base, -1 where absent).
+ * cvg_dev_merge_top2: merge `n_parts` such partial results (layout [n_parts][nq][2]) in the
+ *   lexicographic (distance, idx) order that reproduces OpenCV's tie rule, then
+ *   emit idx/dist/accept. */
+int  cvg_dev_match_top2(cvg_ctx* ctx, void* stream, const float* query_dev, int n_query,
+                        const float* train_dev, int n_train, int32_t train_index_base,
+                        float* dist_dev, int32_t* idx_dev);
+int  cvg_dev_merge_top2(cvg_ctx* ctx, void* stream, const float* dist_parts_dev,
+                        const int32_t* idx_parts_dev, int n_parts, int n_query, float ratio,
+                        int32_t* idx_dev, float* dist_dev, uint8_t* accept_dev);
+
+/* ---- introspection for tests / bench --------------------------------------------------------- */
+/* Which match kernel served the last match call on this context: 1 = tcgen05 tensor-core kernel,
+ * 2 = exact fp32 SIMT kernel (non-integer descriptors), 0 = none yet. */
+int  cvg_last_match_path(const cvg_ctx* ctx);
+/* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
+int64_t cvg_launch_count(const cvg_ctx* ctx);
+/* Device time in milliseconds of the match kernels / RANSAC kernels of the last fused call,
+ * measured with CUDA events on the context's stream (0 if timing disabled). */
+int  cvg_set_timing(cvg_ctx* ctx, int enabled);
+int  cvg_last_timing(const cvg_ctx* ctx, float* match_ms, float* ransac_ms, float* total_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVGRAFT_H */

@@ -1,0 +1,275 @@
+"""GPU parity tests: libcvgraft (through its C ABI) against the CPU oracle and the cv2 goldens.
+Bit-exact for indices / accept masks / inlier masks, tolerances (stated per test) for floating point."""
+import numpy as np
+import pytest
+
+from computervision_objectdetection_featurematching_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from computervision_objectdetection_featurematching_b200 import api as _api
+    return _api
+
+
+@pytest.fixture(scope="module")
+def ctx(api):
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def ctx_exact(api):
+    c = api.Context(0, api.FORCE_EXACT_MATCH)
+    yield c
+    c.close()
+
+
+def _assert_match(got, want, check_dist_exact=True):
+    idx, dist, acc = got
+    widx, wdist, wacc = want
+    assert np.array_equal(idx, widx)
+    valid = widx >= 0
+    if check_dist_exact:
+        assert np.array_equal(dist[valid], wdist[valid])
+    else:
+        assert np.allclose(dist[valid], wdist[valid], rtol=1e-4, atol=0)      # north_star: 1e-4 relative
+    assert np.array_equal(acc, wacc)
+
+
+# ---------------------------------------------------------------- match stage
+def test_match_tensor_path_integer_descriptors(ctx, api, oracle):
+    rng = np.random.default_rng(101)
+    for nq, nt in [(300, 700), (128, 256), (1, 2), (129, 257), (500, 3000), (77, 5)]:
+        q, t, _ = synth.planted_pair(rng, nq, nt)
+        got = ctx.match_knn2(q, t)
+        assert ctx.last_match_path == api.PATH_TENSOR
+        oi, od = oracle.knn2(q, t, nthreads=8)
+        _assert_match(got, (oi, od, oracle.ratio(oi, od)))
+
+
+def test_match_ties_and_duplicates(ctx, api, gsynth):
+    q, t = gsynth["knn_int_q"], gsynth["knn_int_t"]
+    idx, dist, acc = ctx.match_knn2(q, t)
+    assert ctx.last_match_path == api.PATH_TENSOR
+    assert np.array_equal(idx, gsynth["knn_int_idx"])          # cv2 golden incl. exact distance ties
+    assert np.array_equal(dist, gsynth["knn_int_dist"])
+
+
+def test_match_exact_path_float_descriptors(ctx, api, gsynth):
+    idx, dist, acc = ctx.match_knn2(gsynth["knn_float_q"], gsynth["knn_float_t"])
+    assert ctx.last_match_path == api.PATH_EXACT             # non-integer data is routed to the fp32 kernel
+    assert np.array_equal(idx, gsynth["knn_float_idx"])
+    assert np.array_equal(dist, gsynth["knn_float_dist"])    # cv::batchDistance summation order, bit-exact
+
+
+def test_match_both_paths_agree(ctx, ctx_exact, api):
+    q, t, _ = synth.planted_pair(np.random.default_rng(102), 1000, 4000)
+    a = ctx.match_knn2(q, t)
+    b = ctx_exact.match_knn2(q, t)
+    assert ctx.last_match_path == api.PATH_TENSOR and ctx_exact.last_match_path == api.PATH_EXACT
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_match_tiny_train_sets(ctx, gsynth):
+    q, t = gsynth["knn_int_q"][:9], gsynth["knn_int_t"]
+    for nt in (1, 2):
+        idx, dist, acc = ctx.match_knn2(q, t[:nt])
+        gi, gd = gsynth[f"knn_nt{nt}_idx"], gsynth[f"knn_nt{nt}_dist"]
+        assert np.array_equal(idx, gi)
+        assert np.array_equal(dist[gi >= 0], gd[gi >= 0])
+        if nt == 1:
+            assert not acc.any()                            # m.size()==2 fails, src/TestsDetector.cpp:67
+    idx, dist, acc = ctx.match_knn2(q, t[:0])
+    assert (idx == -1).all() and not acc.any()
+
+
+def test_match_resident_models_per_view_and_all(ctx, oracle, feats, gpairs):
+    md = feats["model_desc"].astype(np.float32)
+    models = ctx.upload_models(md, feats["model_kpt"], feats["view_offsets"], feats["view_model"])
+    so = feats["scene_offsets"]
+    for s in (0, 4, 7):
+        t = feats["scene_desc"][so[s]:so[s + 1]].astype(np.float32)
+        idx, dist, acc = ctx.match_knn2(models, t)
+        assert np.array_equal(idx, gpairs["idx"][s].astype(np.int32))
+        assert np.array_equal(dist, gpairs["dist"][s])
+        assert np.array_equal(acc, gpairs["accept"][s])
+    vo = feats["view_offsets"]
+    t = feats["scene_desc"][so[2]:so[3]].astype(np.float32)
+    for v in (0, 17, 88):
+        idx, dist, acc = ctx.match_knn2(models, t, view=v)
+        assert np.array_equal(idx, gpairs["idx"][2][vo[v]:vo[v + 1]].astype(np.int32))
+        assert np.array_equal(acc, gpairs["accept"][2][vo[v]:vo[v + 1]])
+    models.free()
+
+
+def test_match_8k_round_trip_properties(ctx, api):
+    """Full-size case (BASELINE config 3 shape): planted matches must be found, self-match is exact."""
+    rng = np.random.default_rng(3000)
+    q, t, truth = synth.planted_pair(rng, 8192, 8192)
+    idx, dist, acc = ctx.match_knn2(q, t)
+    assert ctx.last_match_path == api.PATH_TENSOR
+    planted = truth >= 0
+    assert (idx[planted, 0] == truth[planted]).mean() > 0.999
+    assert np.all(dist[:, 0] <= dist[:, 1])
+    idx2, dist2, _ = ctx.match_knn2(t, t)                    # every row is its own nearest neighbour
+    assert np.array_equal(idx2[:, 0] * 0, np.zeros(8192, np.int32)) and np.all(dist2[:, 0] == 0)
+    d0 = np.sqrt(((q[:64, None, :] - t[None, idx[:64, 0], :][0]) ** 2).sum(-1)) if False else None
+    # spot-check distances against a direct fp64 evaluation
+    for i in range(0, 8192, 517):
+        d = np.sqrt(((q[i].astype(np.float64) - t[idx[i, 0]].astype(np.float64)) ** 2).sum())
+        assert abs(d - dist[i, 0]) <= 1e-4 * max(d, 1.0)
+
+
+# ---------------------------------------------------------------- verify stage
+def _check_fh(got_H, got_mask, ref, rtol=1e-5):
+    assert (got_H is not None) == ref["found"]
+    assert np.array_equal(got_mask, ref["mask"])             # bit-exact inlier mask
+    if ref["found"]:
+        rel = np.max(np.abs(got_H - ref["H"]) / np.maximum(np.abs(ref["H"]), 1e-12))
+        assert rel < rtol, rel                               # north_star: 1e-5 relative
+
+
+def test_find_homography_vs_cv2_goldens(ctx, gsynth):
+    off = gsynth["fh_offsets"]
+    exact = 0; total = 0
+    for k in range(len(off) - 1):
+        a, b = off[k], off[k + 1]
+        H, mask = ctx.find_homography(gsynth["fh_src"][a:b], gsynth["fh_dst"][a:b])
+        assert (H is not None) == bool(gsynth["fh_found"][k]), k
+        assert np.array_equal(mask, gsynth["fh_mask"][a:b]), k
+        if H is not None:
+            G = gsynth["fh_H"][k].reshape(3, 3)
+            rel = np.max(np.abs(H - G) / np.maximum(np.abs(G), 1e-12))
+            assert rel < 1e-5, (k, rel)
+            exact += np.array_equal(H, G); total += 1
+    assert exact >= 40, (exact, total)                       # small sets are bit-exact end to end
+
+
+def test_find_homography_ransac_stage_and_params(ctx, api, oracle, gsynth):
+    src, dst = gsynth["fhp_src"], gsynth["fhp_dst"]
+    for (thr, it, conf), H, mask in zip(gsynth["fhp_params"], gsynth["fhp_H"], gsynth["fhp_mask"]):
+        gH, gmask, rmask = ctx.find_homography(src, dst, float(thr), int(it), float(conf), want_ransac_mask=True)
+        ref = oracle.find_homography(src, dst, thr=float(thr), max_iters=int(it), conf=float(conf))
+        assert np.array_equal(rmask, ref["ransac_mask"])     # RANSAC-stage mask: RNG replay, bit-exact
+        assert np.array_equal(gmask, mask)
+        assert np.max(np.abs(gH.ravel() - H) / np.maximum(np.abs(H), 1e-12)) < 1e-5
+    # NO_REFINE returns the RANSAC-stage model itself
+    gH, gmask = ctx.find_homography(src, dst, flags=api.RANSAC_NO_REFINE)
+    ref = oracle.ransac_stage(src, dst)
+    assert np.array_equal(gmask, ref["mask"]) and np.array_equal(gH, ref["H"])
+
+
+def test_find_homography_small_n_bit_exact_vs_oracle(ctx, oracle):
+    rng = np.random.default_rng(202)
+    srcs, dsts, offs = [], [], [0]
+    for _ in range(200):
+        n = int(rng.integers(4, 100))
+        s, d, _ = synth.correspondences(rng, n, float(rng.uniform(0.2, 0.95)), dup=float(rng.choice([0, 0.3, 0.7])))
+        srcs.append(s); dsts.append(d); offs.append(offs[-1] + n)
+    out = ctx.find_homography_batch(np.concatenate(srcs), np.concatenate(dsts), offs, want_ransac_mask=True)
+    n_exact = 0
+    for k in range(200):
+        ref = oracle.find_homography(srcs[k], dsts[k])
+        a, b = offs[k], offs[k + 1]
+        assert out["found"][k] == ref["found"], k
+        assert np.array_equal(out["ransac_mask"][a:b], ref["ransac_mask"]), k
+        assert np.array_equal(out["mask"][a:b], ref["mask"]), k
+        if ref["found"]:
+            n_exact += np.array_equal(out["H"][k], ref["H"])
+            assert np.allclose(out["H"][k], ref["H"], rtol=1e-9, atol=1e-12), k
+            if len(srcs[k]) > 4:
+                assert out["iters"][k] == ref["info"]["iters_run"], k
+    assert n_exact >= 195, n_exact
+
+
+def test_find_homography_large_n(ctx, oracle):
+    """n = 8192 at 30% inliers (BASELINE config 3): parallel refit/LM path; tolerance 1e-5 on H."""
+    rng = np.random.default_rng(3003)
+    src, dst, _ = synth.correspondences(rng, 8192, 0.3)
+    H, mask, rmask = ctx.find_homography(src, dst, want_ransac_mask=True)
+    ref = oracle.find_homography(src, dst)
+    assert np.array_equal(rmask, ref["ransac_mask"])
+    assert np.max(np.abs(H - ref["H"]) / np.maximum(np.abs(ref["H"]), 1e-12)) < 1e-5
+    assert (mask != ref["mask"]).sum() <= 2                  # points within 1e-8 of the threshold may flip
+    corners = np.array([[0, 0, 1], [640, 0, 1], [640, 480, 1], [0, 480, 1]], float)
+    pa = corners @ H.T; pb = corners @ ref["H"].T
+    assert np.max(np.abs(pa[:, :2] / pa[:, 2:] - pb[:, :2] / pb[:, 2:])) < 0.5      # north_star: 0.5 px
+
+
+def test_find_homography_edge_cases(ctx, api):
+    with pytest.raises(api.CvgError) as e:
+        ctx.find_homography(np.zeros((3, 2), np.float32), np.zeros((3, 2), np.float32))
+    assert e.value.code == 3
+    n = 12
+    xs = np.linspace(0, 100, n).astype(np.float32)
+    H, mask = ctx.find_homography(np.c_[xs, 2 * xs], np.c_[xs + 5, 2 * xs + 1])      # all collinear
+    assert H is None and not mask.any()
+    H, mask = ctx.find_homography(np.full((n, 2), 7, np.float32), np.full((n, 2), 9, np.float32))
+    assert H is None and not mask.any()
+
+
+def test_find_homography_no_early_stop_scores_every_hypothesis(ctx, api, oracle):
+    rng = np.random.default_rng(5005)
+    src, dst, _ = synth.correspondences(rng, 512, 0.3)
+    H, mask, rmask = ctx.find_homography(src, dst, max_iters=20000, flags=api.RANSAC_NO_EARLY_STOP | api.RANSAC_NO_REFINE,
+                                         want_ransac_mask=True)
+    tr = oracle.ransac_stage(src, dst, max_iters=2000, want_trace=True)
+    assert mask.sum() >= tr["mask"].sum()                    # more hypotheses can only improve the best count
+
+
+# ---------------------------------------------------------------- fused path on real features
+def test_detect_pairs_real_dataset_vs_cv2_goldens(ctx, api, feats, gpairs):
+    """Golden real pairs (89 views x 10 scene-scales): gate status, counts, inlier masks (through the
+    inlier scene points) and H against cv2 4.13.0."""
+    md = feats["model_desc"].astype(np.float32)
+    models = ctx.upload_models(md, feats["model_kpt"], feats["view_offsets"], feats["view_model"])
+    so = feats["scene_offsets"]; vo = feats["view_offsets"]
+    moff = gpairs["mask_offsets"]
+    V = len(vo) - 1
+    scales = feats["scales"]
+    n_acc = 0
+    for s in range(len(so) - 1):
+        t = feats["scene_desc"][so[s]:so[s + 1]].astype(np.float32)
+        tk = feats["scene_kpt"][so[s]:so[s + 1]]
+        scale = float(scales[s % 5])
+        res, inl, ioff = ctx.detect_pairs(models, t, tk, scale=scale)
+        assert ctx.last_match_path == api.PATH_TENSOR
+        assert np.array_equal(res["status"], gpairs["status"][s].astype(np.int32)), s
+        assert np.array_equal(res["n_good"], gpairs["n_good"][s]), s
+        idx = gpairs["idx"][s].astype(np.int32); acc = gpairs["accept"][s]
+        for v in range(V):
+            st = int(gpairs["status"][s, v])
+            if st in (0, 3, 4):
+                assert res["n_inliers"][v] == gpairs["n_inliers"][s, v], (s, v)
+                G = gpairs["H"][s, v]
+                rel = np.max(np.abs(res["H"][v] - G) / np.maximum(np.abs(G), 1e-12))
+                assert rel < 1e-5, (s, v, rel)
+            if st == 0:
+                n_acc += 1
+                sel = np.nonzero(acc[vo[v]:vo[v + 1]])[0] + vo[v]
+                gmask = gpairs["mask"][moff[s * V + v]:moff[s * V + v + 1]].astype(bool)
+                pts = tk[idx[sel, 0]][gmask]
+                if np.float32(scale) != np.float32(1.0):
+                    pts = pts / np.float32(scale)
+                assert np.array_equal(inl[ioff[v]:ioff[v + 1]], pts.astype(np.float32)), (s, v)
+            else:
+                assert ioff[v + 1] == ioff[v]
+    assert n_acc == int((gpairs["status"] == 0).sum())
+    models.free()
+
+
+def test_detect_scenes_resident_equals_per_scene_calls(ctx, feats, gpairs):
+    md = feats["model_desc"].astype(np.float32)
+    models = ctx.upload_models(md, feats["model_kpt"], feats["view_offsets"], feats["view_model"])
+    so = feats["scene_offsets"]
+    scenes = ctx.upload_scenes(feats["scene_desc"].astype(np.float32), feats["scene_kpt"], so)
+    scales = np.tile(feats["scales"], (len(so) - 1) // 5)
+    res = ctx.detect_scenes(models, scenes, scales=scales)
+    assert np.array_equal(res["status"], gpairs["status"].astype(np.int32))
+    assert np.array_equal(res["n_inliers"][gpairs["status"] == 0], gpairs["n_inliers"][gpairs["status"] == 0])
+    scenes.free(); models.free()

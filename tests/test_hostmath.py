@@ -1,0 +1,76 @@
+"""Host build of csrc/homography_math.cuh (the scalar routines the CUDA verify-stage kernels call)
+against the oracle and the cv2 goldens — catches logic errors on the CPU before a GPU run."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "hostmath", "hostmath.cpp")
+SO = os.path.join(HERE, "hostmath", "libhostmath.so")
+HDR = os.path.join(HERE, "..", "computervision_objectdetection_featurematching_b200", "csrc", "homography_math.cuh")
+
+
+@pytest.fixture(scope="module")
+def hm():
+    if (not os.path.exists(SO)) or max(os.path.getmtime(SRC), os.path.getmtime(HDR)) > os.path.getmtime(SO):
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-shared", "-o", SO, SRC])
+    lib = C.CDLL(SO)
+    lib.hm_reproj_err.restype = C.c_float
+    lib.hm_reproj_err.argtypes = [C.c_void_p] + [C.c_float] * 4
+    lib.hm_det3.restype = C.c_double
+    lib.hm_update_num_iters.argtypes = [C.c_double, C.c_double, C.c_int]
+    return lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_run_kernel_and_lm_match_cv2_goldens(hm, gsynth):
+    for s, d, H in zip(gsynth["dlt_src"], gsynth["dlt_dst"], gsynth["dlt_H"]):
+        out = np.zeros(9)
+        assert hm.hm_run_kernel(_p(s), _p(d), 4, _p(out)) == 1
+        assert np.array_equal(out, H)
+    for s, d, H in zip(gsynth["lm_h_src"], gsynth["lm_h_dst"], gsynth["lm_h_H"]):
+        out = np.zeros(9)
+        s = np.ascontiguousarray(s); d = np.ascontiguousarray(d)
+        assert hm.hm_run_kernel(_p(s), _p(d), len(s), _p(out)) == 1
+        hm.hm_lm_refine(_p(s), _p(d), len(s), _p(out), 10)
+        assert np.array_equal(out, H)       # DLT + 9-parameter LM, bit-exact with cv2
+
+
+def test_pieces_match_oracle(hm, oracle):
+    rng = np.random.default_rng(7)
+    for _ in range(300):
+        n = int(rng.integers(4, 140))
+        s = rng.uniform(0, 640, size=(n, 2)).astype(np.float32)
+        d = (s + rng.normal(0, 15, size=(n, 2))).astype(np.float32)
+        if rng.random() < 0.3:                       # duplicates -> ill-conditioned
+            k = rng.integers(0, n, size=n // 2); s[k] = s[0]; d[k] = d[0]
+        H1 = np.zeros(9)
+        ok = hm.hm_run_kernel(_p(s), _p(d), n, _p(H1))
+        H2 = oracle.run_kernel(s, d)
+        assert bool(ok) == (H2 is not None)
+        if ok:
+            assert np.array_equal(H1, H2.ravel(), equal_nan=True)
+            if np.isfinite(H1).all():
+                Hl = H1.copy(); hm.hm_lm_refine(_p(s), _p(d), n, _p(Hl), 10)
+                Ho, _ = oracle.lm_refine(s, d, H2)
+                assert np.array_equal(Hl, Ho.ravel(), equal_nan=True)
+                err = oracle.compute_error(s, d, H2)
+                mine = np.array([hm.hm_reproj_err(_p(H1), *map(float, (s[i, 0], s[i, 1], d[i, 0], d[i, 1]))) for i in range(n)], np.float32)
+                assert np.array_equal(err, mine, equal_nan=True)
+        a = s[:4].copy(); b = d[:4].copy()
+        if rng.random() < 0.3:
+            a[3] = a[1]
+        assert bool(hm.hm_check_subset4(_p(a), _p(b))) == oracle.check_subset(a, b)
+
+
+def test_update_num_iters(hm, oracle):
+    for n in (5, 17, 32, 100, 8192):
+        for good in range(4, n + 1, max(1, n // 97)):
+            ep = (n - good) / n
+            assert hm.hm_update_num_iters(0.995, ep, 2000) == oracle.update_num_iters(0.995, ep, 4, 2000)
