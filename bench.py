@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py — image-pairs/s of the matching-and-verification hot path (BF-L2 kNN k=2 + ratio test +
+RANSAC homography), BASELINE.json metric, on synthetic descriptors of the named shape.
+
+Workload at every N ("c3"): per GPU and per step, ONE resident model view of 8192 SIFT-like 128-D
+descriptors is matched against B scene descriptor sets of 8192 rows each and each of the B pairs is
+verified with a 2000-iteration RANSAC homography — BASELINE config 3 (8k x 8k + 2000-iter RANSAC), batched
+the way the reference batches it (one model view vs. many test images, src/TestsDetector.cpp:58).
+
+  value : pairs/s with the scene sets already resident in HBM (cvg_detect_scenes), whole job over N GPUs
+  e2e   : pairs/s through the public host-buffer API: every step uploads its B scene sets from pinned
+          host memory (cvg_scenes_upload), runs cvg_detect_scenes and reads the per-pair results back
+  roofline : the tcgen05 match kernel, algorithmic flops 2*Nq*Nt*128 per pair over its CUDA-event time
+  cpu_baseline : cv2 4.13.0 (the reference's own arithmetic) on this host's cores, bounded sample
+
+`--impl reference` times the reference's CPU implementation (cv2 BFMatcher.knnMatch + findHomography, all
+host threads; the C oracle port if cv2 is unavailable) on the same workload, metric and unit.
+
+Launch: python bench.py --gpus N --steps K --warmup W      (N > 1: under torchrun, one rank per GPU)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from computervision_objectdetection_featurematching_b200 import synth  # noqa: E402
+
+METRIC = "image-pairs/s (BF-L2 kNN + RANSAC H)"
+UNIT = "pairs/s"
+NQ = NT = 8192
+DIM = 128
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_burst": p.get("bf16_tflops", 1590.0), "bf16_sustained": p.get("bf16_tflops_sustained", 1400.0),
+                "hbm": p.get("hbm_gbs", 6650.0), "source": "measured"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback"}
+
+
+def make_workload(seed, n_scenes, n_batches):
+    """One model view + n_batches batches of n_scenes scene sets (planted matches, 30% geometric inliers)."""
+    rng = np.random.default_rng(seed)
+    q = synth.sift_like(rng, NQ)
+    qk = rng.uniform([0, 0], [640, 480], size=(NQ, 2)).astype(np.float32)
+    batches = []
+    for _ in range(n_batches):
+        descs, kpts = [], []
+        for _ in range(n_scenes):
+            t = synth.sift_like(rng, NT)
+            tk = rng.uniform([0, 0], [640, 480], size=(NT, 2)).astype(np.float32)
+            k = NQ // 2                                           # 50% planted matches
+            rq = rng.permutation(NQ)[:k]; rt = rng.permutation(NT)[:k]
+            t[rt] = np.clip(q[rq] + np.round(rng.normal(0, 12.0, size=(k, DIM))).astype(np.float32), 0, 255)
+            H = synth.random_homography(rng)
+            geo = rng.random(k) < 0.3                             # 30% of the planted matches follow H
+            p = np.c_[qk[rq[geo]], np.ones(int(geo.sum()))] @ H.T
+            tk[rt[geo]] = (p[:, :2] / p[:, 2:3] + rng.normal(0, 0.7, size=(int(geo.sum()), 2))).astype(np.float32)
+            descs.append(t); kpts.append(tk)
+        batches.append((np.concatenate(descs), np.concatenate(kpts), np.arange(n_scenes + 1, dtype=np.int64) * NT))
+    return q, qk, batches
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu = gpu; self.proc = None; self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv"); os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            busy = [v for v in sm if v >= 0.5 * max(sm)]
+            out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def cpu_pairs(q, qk, batch, n_pairs, threads, first=0):
+    """The reference's CPU path on pairs [first, first + n_pairs) of a batch; returns (seconds, kind)."""
+    desc, kpt, off = batch
+    try:
+        import cv2
+        cv2.setNumThreads(threads)
+        bf = cv2.BFMatcher(cv2.NORM_L2)
+        t0 = time.perf_counter()
+        for s in range(first, first + n_pairs):
+            t = desc[off[s]:off[s + 1]]; tk = kpt[off[s]:off[s + 1]]
+            m = bf.knnMatch(q, t, 2)                                               # src/TestsDetector.cpp:60
+            good = [a for a, b in m if a.distance < np.float32(0.9) * b.distance]  # :67
+            src = np.float32([qk[g.queryIdx] for g in good]); dst = np.float32([tk[g.trainIdx] for g in good])
+            if len(good) >= 4:
+                cv2.findHomography(src, dst, cv2.RANSAC, 5.0)                      # :78
+        return time.perf_counter() - t0, "reference"
+    except ImportError:
+        from oracle import cvoracle as o
+        t0 = time.perf_counter()
+        for s in range(first, first + n_pairs):
+            t = desc[off[s]:off[s + 1]]; tk = kpt[off[s]:off[s + 1]]
+            idx, dist = o.knn2(q, t, nthreads=threads)
+            acc = o.ratio(idx, dist).astype(bool)
+            if acc.sum() >= 4:
+                o.find_homography(qk[acc], tk[idx[acc, 0]])
+        return time.perf_counter() - t0, "port"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    pairs_per_step = 2
+    q, qk, batches = make_workload(3000, pairs_per_step, 1)
+    for _ in range(args.warmup):
+        cpu_pairs(q, qk, batches[0], 1, threads)
+    total = 0.0; kind = "reference"
+    for _ in range(args.steps):
+        dt, kind = cpu_pairs(q, qk, batches[0], pairs_per_step, threads)
+        total += dt
+    value = pairs_per_step * args.steps / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "c3: 1 model view x 8192 desc vs scenes of 8192 desc, ratio 0.9, RANSAC 2000 iters",
+                       "pairs_per_step": pairs_per_step},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                             "sample": f"{pairs_per_step} pairs per step, knnMatch on {threads} threads, findHomography serial"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_cvgraft(args):
+    import torch
+    import torch.distributed as dist
+    from computervision_objectdetection_featurematching_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libcvgraft has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B, R = args.pairs, args.batches
+    q, qk, batches = make_workload(3000 + rank, B, R)
+    ctx = api.Context(local)
+    ctx.set_timing(True)
+    models = ctx.upload_models(q, qk, [0, NQ], [0])
+    params = api.detect_params()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize, device time by CUDA events on the context's stream."""
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for k in range(steps):
+            fn(k)
+        e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        barrier()
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- value: scene sets resident in HBM --------------------------------------------------------
+    resident = [ctx.upload_scenes(d, k, o) for d, k, o in batches]
+    match_ms, ransac_ms, accepted = [], [], 0
+
+    def step_resident(k):
+        nonlocal accepted
+        res = ctx.detect_scenes(models, resident[k % R], params=params)
+        t = ctx.last_timing()
+        match_ms.append(t["match_ms"]); ransac_ms.append(t["ransac_ms"])
+        accepted += int((res["status"] == 0).sum())
+
+    for k in range(args.warmup):
+        step_resident(k)
+    match_ms.clear(); ransac_ms.clear(); accepted = 0
+    clocks = ClockSampler(local); clocks.start()
+    l0 = ctx.launch_count
+    ms_total = timed(step_resident, args.steps)
+    launches = ctx.launch_count - l0
+    clk = clocks.stop()
+    value = world * B * args.steps / (ms_total * 1e-3)
+    for sc in resident:
+        sc.free()
+
+    # ---- e2e: host buffers in, results out, every step -------------------------------------------
+    pinned = []
+    for d, k, o in batches:
+        pd = torch.from_numpy(d).pin_memory(); pk = torch.from_numpy(k).pin_memory()
+        pinned.append((pd.numpy(), pk.numpy(), o, pd, pk))
+    h2d = int(batches[0][0].nbytes + batches[0][1].nbytes + batches[0][2].nbytes)
+    d2h = int(B * api.PAIR_DTYPE.itemsize)
+
+    def step_e2e(k):
+        d, kk, o, _, _ = pinned[k % R]
+        sc = ctx.upload_scenes(d, kk, o)
+        ctx.detect_scenes(models, sc, params=params)
+        sc.free()
+
+    for k in range(max(1, args.warmup // 2)):
+        step_e2e(k)
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        peaks = load_peaks()
+        flops = 2.0 * NQ * NT * DIM * B
+        kms = statistics.mean(match_ms)
+        achieved = flops / (kms * 1e-3) / 1e12
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16 operands (exact for u8 descriptors) / f32 accumulate; f64+f32 verify", "data": "synthetic",
+                "config": {"workload": "c3: 1 resident model view x 8192 desc vs B scenes x 8192 desc, ratio 0.9, "
+                                       "RANSAC 2000 iters thr 5.0 conf 0.995", "pairs_per_step_per_gpu": B,
+                           "scene_batches_rotated": R, "parallelism": f"pair-sharded x{world}, no data-path collective",
+                           "l2": f"{R} rotating batches, {R * B * NT * DIM * 2 / 2**20:.0f} MiB of bf16 operands > 126 MB L2"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches),
+                "clocks": clk,
+                "roofline": {"kernel": "match_tc_kernel (tcgen05)", "bound": "tensor", "achieved": achieved,
+                             "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
+                             "peak_burst": peaks["bf16_burst"], "frac_of_burst": achieved / peaks["bf16_burst"],
+                             "peak_source": peaks["source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
+                             "kernel_ms_per_launch": kms, "algorithmic_flops_per_launch": flops, "traffic": None},
+                "stage_ms_per_step": {"match_kernel": kms, "verify": statistics.mean(ransac_ms)},
+                "accepted_pairs": accepted}
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            n = 0; t_cpu = 0.0; kind = "reference"
+            while t_cpu < args.cpu_seconds and n < B:
+                dt, kind = cpu_pairs(q, qk, batches[0], 1, threads, first=n)
+                t_cpu += dt; n += 1
+            line["cpu_baseline"] = {"value": n / t_cpu, "unit": UNIT, "cores": threads, "kind": kind,
+                                    "sample": f"{n} pairs of the same workload (cv2 knnMatch on {threads} threads + findHomography)"}
+        print(json.dumps(line), flush=True)
+    models.free(); ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cvgraft", choices=["cvgraft", "reference"])
+    ap.add_argument("--pairs", type=int, default=32, help="scene sets (= pairs) per step per GPU")
+    ap.add_argument("--batches", type=int, default=4, help="distinct scene batches rotated over the steps")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cvgraft" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cvgraft(args)
+
+
+if __name__ == "__main__":
+    main()

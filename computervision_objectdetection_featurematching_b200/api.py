@@ -162,6 +162,11 @@ class Context:
         return self.lib.cvg_last_match_path(self.handle)
 
     @property
+    def stream(self):
+        """cudaStream_t of the context as an int (all GPU work of this context is issued there)."""
+        return int(self.lib.cvg_stream(self.handle) or 0)
+
+    @property
     def launch_count(self):
         return int(self.lib.cvg_launch_count(self.handle))
 

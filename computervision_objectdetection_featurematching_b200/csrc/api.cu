@@ -86,7 +86,7 @@ struct cvg_ctx {
     uint32_t* d_rng = nullptr; int64_t rng_len = 0;
     int last_match_path = 0; int64_t launches = 0;
     int timing = 0; float t_match = 0, t_ransac = 0, t_total = 0;
-    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
     // scratch
     DevBuf q_f32, q_b, q_aug, q_norm;                  // raw-query path
     DevBuf t_f32, t_b, t_aug, t_kpt, t_kptoff;         // per-call train path
@@ -134,7 +134,7 @@ int cvg_create(cvg_ctx** out, int device, unsigned flags)
     CU_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU_CHECK(cudaMalloc(&c->d_flags, 64 * sizeof(int)));
     CU_CHECK(cudaMemset(c->d_flags, 0, 64 * sizeof(int)));
-    for (int i = 0; i < 4; i++) CU_CHECK(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 6; i++) CU_CHECK(cudaEventCreate(&c->ev[i]));
     char err[256];
     if (tc_init(err, sizeof err)) { delete c; return set_err(CVG_ERR_CUDA, "%s", err); }
     *out = c;
@@ -154,12 +154,13 @@ void cvg_destroy(cvg_ctx* c)
     for (DevBuf* b : bufs) b->release();
     if (c->d_flags) cudaFree(c->d_flags);
     if (c->d_rng) cudaFree(c->d_rng);
-    for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
 int cvg_last_match_path(const cvg_ctx* c) { return c ? c->last_match_path : 0; }
+void* cvg_stream(const cvg_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int64_t cvg_launch_count(const cvg_ctx* c) { return c ? c->launches : 0; }
 int cvg_set_timing(cvg_ctx* c, int enabled) { if (!c) return CVG_ERR_INVALID; c->timing = enabled; return CVG_OK; }
 int cvg_last_timing(const cvg_ctx* c, float* m, float* r, float* t)
@@ -286,6 +287,7 @@ static int launch_match(cvg_ctx* c, const QuerySide& q, const TrainSet& ts, cons
                         int32_t* d_idx, float* d_dist, uint8_t* d_accept)
 {
     const int nq = q.row_end - q.row_begin;
+    if (c->timing) cudaEventRecord(c->ev[3], c->stream);
     if (n_units > 0) {
         if (path_hint != 2) {
             TcOperands op{ q.d_b, q.d_aug, q.d_norm, q.n_pad, ts.d_b, ts.d_aug, (int)ts.rows_pad_total };
@@ -301,6 +303,7 @@ static int launch_match(cvg_ctx* c, const QuerySide& q, const TrainSet& ts, cons
             c->launches++;
         }
     }
+    if (c->timing) cudaEventRecord(c->ev[4], c->stream);
     launch_merge(d_parts, d_dir, ts.n_segs, n_rb, nq, ratio, d_idx, d_dist, d_accept, c->stream);
     c->launches++;
     CU_CHECK(cudaGetLastError());
@@ -462,6 +465,7 @@ static int match_host_train(cvg_ctx* c, QuerySide q, int q_nonint, const float* 
     rc = sync_and_check(c);
     if (rc) return rc;
     c->last_match_path = flag ? 2 : 1;
+    if (c->timing) { cudaEventElapsedTime(&c->t_match, c->ev[3], c->ev[4]); c->t_ransac = 0; c->t_total = c->t_match; }
     return CVG_OK;
 }
 
@@ -645,8 +649,8 @@ static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, Tra
     if (rc) return rc;
     c->last_match_path = path == 0 ? (flag ? 2 : 1) : path;
     if (c->timing) {
-        cudaEventElapsedTime(&c->t_match, c->ev[0], c->ev[1]);
-        cudaEventElapsedTime(&c->t_ransac, c->ev[1], c->ev[2]);
+        cudaEventElapsedTime(&c->t_match, c->ev[3], c->ev[4]);      // the match kernel(s) alone
+        cudaEventElapsedTime(&c->t_ransac, c->ev[1], c->ev[2]);     // sample + hypothesis + select + finish + gates
         cudaEventElapsedTime(&c->t_total, c->ev[0], c->ev[2]);
     }
     return CVG_OK;
@@ -779,8 +783,8 @@ int cvg_dev_match_top2(cvg_ctx* c, void* stream, const float* query_dev, int n_q
     CU_CHECK(cudaSetDevice(c->device));
     cudaStream_t user = (cudaStream_t)stream;
     // order our stream after the caller's and back (the context owns its scratch and its stream)
-    CU_CHECK(cudaEventRecord(c->ev[3], user));
-    CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev[3], 0));
+    CU_CHECK(cudaEventRecord(c->ev[5], user));
+    CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev[5], 0));
     const int n_pad = round_up(n_query, TILE_M);
     CU_CHECK(c->q_b.ensure((size_t)n_pad * DIM * 2)); CU_CHECK(c->q_aug.ensure((size_t)n_pad * KAUG * 2));
     CU_CHECK(c->q_norm.ensure((size_t)n_pad * 4));
@@ -811,8 +815,8 @@ int cvg_dev_match_top2(cvg_ctx* c, void* stream, const float* query_dev, int n_q
     if (rc) return rc;
     launch_shift_index(c->idx.as<int32_t>(), c->dist.as<float>(), n_query, train_index_base, dist_dev, idx_dev, c->stream);
     c->launches++;
-    CU_CHECK(cudaEventRecord(c->ev[3], c->stream));
-    CU_CHECK(cudaStreamWaitEvent(user, c->ev[3], 0));
+    CU_CHECK(cudaEventRecord(c->ev[5], c->stream));
+    CU_CHECK(cudaStreamWaitEvent(user, c->ev[5], 0));
     return CVG_OK;
 }
 

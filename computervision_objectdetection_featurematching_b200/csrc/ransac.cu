@@ -7,12 +7,12 @@
 // OpenCV's loop is serial (one RNG stream with data-dependent consumption, adaptive stop).  The
 // parallel decomposition keeps its results bit for bit (App. D.5):
 //   1. sample kernel   — replays cv::RNG + getSubset + checkSubset.  The raw RNG stream for the fixed
-//                        per-call seed is a constant table in HBM, so an attempt starting at draw
-//                        position p can be evaluated independently; a block evaluates 128 speculative
-//                        attempts at p, p+4, ... in parallel and accepts the regular prefix.
-//   2. hypothesis kernel — one hypothesis per thread: 4-point normalised DLT (9x9 Jacobi, fp64, no FMA),
-//                        then fp32 scoring of all correspondences staged through shared memory
-//                        (each point is read once per 128 hypotheses, broadcast to the warp).
+//                        per-call seed is a constant table in HBM, so the attempt starting at any draw
+//                        position p can be evaluated independently; a block evaluates a window of 512
+//                        positions in parallel, then one thread follows the chain p -> p + consumed(p).
+//   2. hypothesis kernel — one hypothesis per thread: 4-point normalised DLT (9x9 Jacobi in shared memory,
+//                        fp64, no FMA), then fp32 scoring of all correspondences staged through shared
+//                        memory (each point is read once per 64 hypotheses, broadcast to the warp).
 //   3. select kernel   — the sequential "good > max(best,3)" / RANSACUpdateNumIters scan, one warp per
 //                        set, so the winner is the hypothesis the serial loop would have kept.
 //   4. finish kernel   — winner's inlier mask, DLT refit on the inliers, 9-parameter LM (10 iterations),
@@ -48,6 +48,12 @@ __device__ __forceinline__ int draw_subset(const uint32_t* __restrict__ tab, int
 }
 
 // ---- 1. sample kernel ------------------------------------------------------------------------------
+// A window of SW consecutive draw positions is evaluated in parallel: for every position p the attempt
+// that would start there (draws consumed, checkSubset verdict).  One thread then follows the chain
+// p -> p + consumed(p) through shared memory, which is exactly the order in which the serial getSubset
+// consumes the stream, including rejected attempts and the 10000-attempt limit.
+constexpr int SW = 512;
+
 __global__ void __launch_bounds__(RS_THREADS)
 ransac_sample_kernel(RansacWork w)
 {
@@ -60,65 +66,62 @@ ransac_sample_kernel(RansacWork w)
     }
     const float4* __restrict__ pts = w.pts + w.starts[set];
     __shared__ float4 spts[SMEM_PTS];
-    __shared__ int s_first[RS_THREADS / 32];
-    __shared__ int s_cons, s_ok;
+    __shared__ uint16_t info[SW];                   // bit 15: checkSubset ok; bits 0-14: draws consumed (0 = overrun)
+    __shared__ long long s_pos;
+    __shared__ int s_iter, s_attempts, s_done, s_flags;
     const bool staged = n <= SMEM_PTS;
-    if (staged) {
+    if (staged)
         for (int i = threadIdx.x; i < n; i += RS_THREADS) spts[i] = pts[i];
-        __syncthreads();
-    }
-    int64_t pos = 0;
-    int iter = 0, attempts = 0, flags = 0;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    while (iter < w.max_iters) {
-        // speculative attempt starting at pos + 4*t
-        const int64_t p = pos + 4 * (int64_t)threadIdx.x;
-        int idx[4];
-        int cons = draw_subset(w.rng_tab, w.rng_len, p, (uint32_t)n, idx);
-        bool ok = false;
-        if (cons > 0) {
-            float ms1[8], ms2[8];
-            #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const float4 q = staged ? spts[idx[i]] : pts[idx[i]];
-                ms1[2 * i] = q.x; ms1[2 * i + 1] = q.y; ms2[2 * i] = q.z; ms2[2 * i + 1] = q.w;
+    if (threadIdx.x == 0) { s_pos = 0; s_iter = 0; s_attempts = 0; s_done = 0; s_flags = 0; }
+    __syncthreads();
+    for (;;) {
+        const int64_t base = s_pos;
+        #pragma unroll 1
+        for (int k = 0; k < SW / RS_THREADS; k++) {
+            const int o = k * RS_THREADS + threadIdx.x;
+            int idx[4];
+            const int cons = draw_subset(w.rng_tab, w.rng_len, base + o, (uint32_t)n, idx);
+            uint16_t e = 0;
+            if (cons > 0 && cons < 0x7fff) {
+                float ms1[8], ms2[8];
+                #pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float4 q = staged ? spts[idx[i]] : pts[idx[i]];
+                    ms1[2 * i] = q.x; ms1[2 * i + 1] = q.y; ms2[2 * i] = q.z; ms2[2 * i + 1] = q.w;
+                }
+                e = (uint16_t)(cons | (check_subset4(ms1, ms2) ? 0x8000 : 0));
             }
-            ok = check_subset4(ms1, ms2);
+            info[o] = e;
         }
-        const bool regular = ok && cons == 4;
-        const unsigned bal = __ballot_sync(0xffffffffu, !regular);
-        if (lane == 0) s_first[wid] = bal ? (wid * 32 + __ffs(bal) - 1) : RS_THREADS;
         __syncthreads();
-        int first = RS_THREADS;
-        #pragma unroll
-        for (int k = RS_THREADS / 32 - 1; k >= 0; k--) if (s_first[k] < RS_THREADS) first = s_first[k];
-        if ((int)threadIdx.x == first) { s_cons = cons; s_ok = ok ? 1 : 0; }
-        const int m = min(first, w.max_iters - iter);
-        if ((int)threadIdx.x < m) out[iter + threadIdx.x] = (int32_t)p;
-        __syncthreads();
-        iter += m;
-        pos += 4 * (int64_t)m;
-        if (m > 0) attempts = 0;
-        if (first < RS_THREADS && iter < w.max_iters) {
-            const int c = s_cons;
-            if (c < 0) { flags |= 1; break; }                    // RNG table exhausted
-            if (s_ok) {
-                if (threadIdx.x == 0) out[iter] = (int32_t)pos;
-                iter++; attempts = 0;
-            } else {
-                if (++attempts >= 10000) break;                  // getSubset gave up
+        if (threadIdx.x == 0) {
+            int64_t p = base;
+            int iter = s_iter, attempts = s_attempts, done = 0, flags = 0;
+            while (p < base + SW && iter < w.max_iters) {
+                const uint16_t e = info[p - base];
+                const int c = e & 0x7fff;
+                if (c == 0) { flags = 1; done = 1; break; }              // RNG table exhausted
+                if (e & 0x8000) { out[iter++] = (int32_t)p; attempts = 0; }
+                else if (++attempts >= 10000) { done = 1; break; }       // getSubset gave up
+                p += c;
             }
-            pos += c;
+            if (iter >= w.max_iters) done = 1;
+            if (p + SW + 64 >= 0x7fffffffLL) { flags = 1; done = 1; }
+            s_pos = p; s_iter = iter; s_attempts = attempts; s_done = done; s_flags = flags;
         }
-        if (pos + 4 * RS_THREADS + 64 >= 0x7fffffffLL) { flags |= 1; break; }
         __syncthreads();
+        if (s_done) break;
     }
-    if (threadIdx.x == 0) { w.n_samples[set] = iter; w.status_flags[set] = flags; }
+    if (threadIdx.x == 0) { w.n_samples[set] = s_iter; w.status_flags[set] = s_flags; }
 }
 
 // ---- 2. hypothesis kernel: solve + score ------------------------------------------------------------
+// LtL and V (the Jacobi working set, 162 doubles, dynamically indexed) live in shared memory:
+// as thread-local arrays they thrash L1 and every access costs an L2 round trip.
+constexpr int JAC_STRIDE = 163;                     // doubles per thread; odd -> conflict-free when threads agree on the index
+
 __device__ __forceinline__ bool solve_hypothesis(const RansacWork& w, const float4* __restrict__ pts, int n,
-                                                 int32_t pos, float Hf[8], double* Hd)
+                                                 int32_t pos, float Hf[8], double* Hd, double* jac)
 {
     int idx[4];
     draw_subset(w.rng_tab, w.rng_len, pos, (uint32_t)n, idx);
@@ -128,39 +131,46 @@ __device__ __forceinline__ bool solve_hypothesis(const RansacWork& w, const floa
         const float4 q = pts[idx[i]];
         ms1[2 * i] = q.x; ms1[2 * i + 1] = q.y; ms2[2 * i] = q.z; ms2[2 * i + 1] = q.w;
     }
-    double H[9], LtL[81], V[81];
+    double H[9];
     Pts4 P{ ms1, ms2 };
-    if (!run_kernel_seq(P, 4, H, LtL, V)) return false;
+    if (!run_kernel_seq(P, 4, H, jac, jac + 81)) return false;
     #pragma unroll
     for (int i = 0; i < 8; i++) Hf[i] = (float)H[i];
     if (Hd) for (int i = 0; i < 9; i++) Hd[i] = H[i];
     return true;
 }
 
-__global__ void __launch_bounds__(RS_THREADS)
+constexpr int HYP_THREADS = 64;
+constexpr int HYP_PTS = 512;
+constexpr int HYP_SMEM = HYP_THREADS * JAC_STRIDE * 8 + HYP_PTS * 16;
+
+__global__ void __launch_bounds__(HYP_THREADS)
 ransac_hyp_kernel(RansacWork w)
 {
+    extern __shared__ double hyp_smem[];
     const int set = blockIdx.y;
     const int n = w.counts_n[set];
     const int n_samples = w.n_samples[set];
-    const int iter0 = blockIdx.x * RS_THREADS;
+    const int iter0 = blockIdx.x * HYP_THREADS;
     if (iter0 >= n_samples) return;
     const float4* __restrict__ pts = w.pts + w.starts[set];
     const int iter = iter0 + threadIdx.x;
     const bool active = iter < n_samples;
     float Hf[8];
     bool valid = false;
-    if (active) valid = solve_hypothesis(w, pts, n, w.sample_pos[(size_t)set * w.max_iters + iter], Hf, nullptr);
+    if (active)
+        valid = solve_hypothesis(w, pts, n, w.sample_pos[(size_t)set * w.max_iters + iter], Hf, nullptr,
+                                 hyp_smem + threadIdx.x * JAC_STRIDE);
     if (!valid) {
         #pragma unroll
         for (int i = 0; i < 8; i++) Hf[i] = 0.f;
     }
-    __shared__ float4 spts[SMEM_PTS];
+    float4* spts = reinterpret_cast<float4*>(hyp_smem + HYP_THREADS * JAC_STRIDE);
     int good = 0;
-    for (int base = 0; base < n; base += SMEM_PTS) {
-        const int cnt = min(SMEM_PTS, n - base);
+    for (int base = 0; base < n; base += HYP_PTS) {
+        const int cnt = min(HYP_PTS, n - base);
         __syncthreads();
-        for (int i = threadIdx.x; i < cnt; i += RS_THREADS) spts[i] = pts[base + i];
+        for (int i = threadIdx.x; i < cnt; i += HYP_THREADS) spts[i] = pts[base + i];
         __syncthreads();
         #pragma unroll 4
         for (int i = 0; i < cnt; i++) {
@@ -205,7 +215,7 @@ __global__ void ransac_select_kernel(RansacWork w)
         w.best_iter[set] = best_iter;
         w.best_count[set] = best;
         // value of `iter` when the reference loop exits
-        w.iters_run[set] = n <= 4 ? 0 : min(niters, n_samples);
+        w.iters_run[set] = n <= 4 ? 0 : min(max(niters, best_iter + 1), n_samples);
     }
 }
 
@@ -249,6 +259,7 @@ struct FinishShared {
     LmState lm;
     double H[9];
     double scratch_a[81], scratch_v[81];
+    double jac[JAC_STRIDE];
     float Hf[8];
     int flag;
     int warp_cnt[RS_THREADS / 32];
@@ -340,7 +351,7 @@ ransac_finish_kernel(RansacWork w)
     // winner's model again (deterministic) -> its mask, in original order
     if (tid == 0) {
         float Hf[8];
-        solve_hypothesis(w, pts, n, w.sample_pos[(size_t)set * w.max_iters + best_iter], Hf, sh.H);
+        solve_hypothesis(w, pts, n, w.sample_pos[(size_t)set * w.max_iters + best_iter], Hf, sh.H, sh.jac);
         for (int i = 0; i < 8; i++) sh.Hf[i] = Hf[i];
         sh.base_cnt = 0;
     }
@@ -495,8 +506,13 @@ void launch_ransac(const RansacWork& w, cudaStream_t st)
 {
     if (w.n_sets <= 0) return;
     ransac_sample_kernel<<<w.n_sets, RS_THREADS, 0, st>>>(w);
-    dim3 grid((w.max_iters + RS_THREADS - 1) / RS_THREADS, w.n_sets);
-    ransac_hyp_kernel<<<grid, RS_THREADS, 0, st>>>(w);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(ransac_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HYP_SMEM);
+        attr_set = true;
+    }
+    dim3 grid((w.max_iters + HYP_THREADS - 1) / HYP_THREADS, w.n_sets);
+    ransac_hyp_kernel<<<grid, HYP_THREADS, HYP_SMEM, st>>>(w);
     const int warps_per_block = 4;
     ransac_select_kernel<<<(w.n_sets + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(w);
     ransac_finish_kernel<<<w.n_sets, RS_THREADS, 0, st>>>(w);

@@ -184,10 +184,14 @@ int  cvg_dev_merge_top2(cvg_ctx* ctx, void* stream, const float* dist_parts_dev,
 /* Which match kernel served the last match call on this context: 1 = tcgen05 tensor-core kernel,
  * 2 = exact fp32 SIMT kernel (non-integer descriptors), 0 = none yet. */
 int  cvg_last_match_path(const cvg_ctx* ctx);
+/* The context's cudaStream_t (all of its GPU work is issued there); lets a harness record its own
+ * CUDA events around calls. */
+void* cvg_stream(const cvg_ctx* ctx);
 /* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
 int64_t cvg_launch_count(const cvg_ctx* ctx);
-/* Device time in milliseconds of the match kernels / RANSAC kernels of the last fused call,
- * measured with CUDA events on the context's stream (0 if timing disabled). */
+/* Device times in milliseconds of the last call, measured with CUDA events on the context's stream
+ * (0 if timing disabled): match_ms = the match kernel launch alone (tcgen05 or exact), ransac_ms =
+ * verify-stage kernels, total_ms = first match launch to last gate launch. */
 int  cvg_set_timing(cvg_ctx* ctx, int enabled);
 int  cvg_last_timing(const cvg_ctx* ctx, float* match_ms, float* ransac_ms, float* total_ms);
 
