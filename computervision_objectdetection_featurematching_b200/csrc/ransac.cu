@@ -28,16 +28,17 @@ constexpr int EXACT_MAX_INLIERS = 128;
 constexpr int SMEM_PTS = 1024;              // correspondences staged per shared-memory tile
 
 // ---- draw 4 distinct indices starting at table position p (getSubset's inner loop) ----------------
+// `get(pos)` returns uniform(0, n) for draw position pos, i.e. rng_tab[pos] % n, or -1 past the table.
 // returns the number of draws consumed, or -1 when the table would be overrun
-__device__ __forceinline__ int draw_subset(const uint32_t* __restrict__ tab, int64_t tab_len, int64_t p,
-                                           uint32_t n, int idx[4])
+template <class Get>
+__device__ __forceinline__ int draw_subset_g(const Get& get, int64_t p, int idx[4])
 {
     int64_t pos = p;
     #pragma unroll
     for (int i = 0; i < 4; i++) {
         for (;;) {
-            if (pos >= tab_len) return -1;
-            const int v = (int)(tab[pos++] % n);
+            const int v = get(pos++);
+            if (v < 0) return -1;
             bool dup = false;
             #pragma unroll
             for (int k = 0; k < 4; k++) dup |= (k < i) && (idx[k] == v);
@@ -47,12 +48,24 @@ __device__ __forceinline__ int draw_subset(const uint32_t* __restrict__ tab, int
     return (int)(pos - p);
 }
 
+struct TabGet {
+    const uint32_t* __restrict__ tab; int64_t len; uint32_t n;
+    __device__ __forceinline__ int operator()(int64_t pos) const { return pos < len ? (int)(tab[pos] % n) : -1; }
+};
+
+__device__ __forceinline__ int draw_subset(const uint32_t* __restrict__ tab, int64_t tab_len, int64_t p,
+                                           uint32_t n, int idx[4])
+{
+    return draw_subset_g(TabGet{ tab, tab_len, n }, p, idx);
+}
+
 // ---- 1. sample kernel ------------------------------------------------------------------------------
 // A window of SW consecutive draw positions is evaluated in parallel: for every position p the attempt
 // that would start there (draws consumed, checkSubset verdict).  One thread then follows the chain
 // p -> p + consumed(p) through shared memory, which is exactly the order in which the serial getSubset
 // consumes the stream, including rejected attempts and the 10000-attempt limit.
 constexpr int SW = 512;
+constexpr int SW_TAIL = 64;                       // draws staged beyond the window for attempts that start near its end
 
 __global__ void __launch_bounds__(RS_THREADS)
 ransac_sample_kernel(RansacWork w)
@@ -67,6 +80,7 @@ ransac_sample_kernel(RansacWork w)
     const float4* __restrict__ pts = w.pts + w.starts[set];
     __shared__ float4 spts[SMEM_PTS];
     __shared__ uint16_t info[SW];                   // bit 15: checkSubset ok; bits 0-14: draws consumed (0 = overrun)
+    __shared__ int32_t s_draw[SW + SW_TAIL];        // uniform(0,n) of the window's draw positions (-1 past the table)
     __shared__ long long s_pos;
     __shared__ int s_iter, s_attempts, s_done, s_flags;
     const bool staged = n <= SMEM_PTS;
@@ -76,11 +90,21 @@ ransac_sample_kernel(RansacWork w)
     __syncthreads();
     for (;;) {
         const int64_t base = s_pos;
+        for (int j = threadIdx.x; j < SW + SW_TAIL; j += RS_THREADS) {
+            const int64_t pp = base + j;
+            s_draw[j] = pp < w.rng_len ? (int32_t)(w.rng_tab[pp] % (uint32_t)n) : -1;
+        }
+        __syncthreads();
+        const TabGet slow{ w.rng_tab, w.rng_len, (uint32_t)n };
+        auto get = [&](int64_t pos) -> int {
+            const int64_t j = pos - base;
+            return j < SW + SW_TAIL ? s_draw[j] : slow(pos);
+        };
         #pragma unroll 1
         for (int k = 0; k < SW / RS_THREADS; k++) {
             const int o = k * RS_THREADS + threadIdx.x;
             int idx[4];
-            const int cons = draw_subset(w.rng_tab, w.rng_len, base + o, (uint32_t)n, idx);
+            const int cons = draw_subset_g(get, base + o, idx);
             uint16_t e = 0;
             if (cons > 0 && cons < 0x7fff) {
                 float ms1[8], ms2[8];
@@ -116,10 +140,13 @@ ransac_sample_kernel(RansacWork w)
 }
 
 // ---- 2. hypothesis kernel: solve + score ------------------------------------------------------------
-// LtL and V (the Jacobi working set, 162 doubles, dynamically indexed) live in shared memory:
-// as thread-local arrays they thrash L1 and every access costs an L2 round trip.
-constexpr int JAC_STRIDE = 163;                     // doubles per thread; odd -> conflict-free when threads agree on the index
+// LtL and V (the Jacobi working set, 162 doubles, dynamically indexed) live in shared memory: as
+// thread-local arrays they thrash L1 and every access costs an L2 round trip.  The layout is
+// element-major (element e of thread t at e*HYP_THREADS + t): a thread always hits its own banks, so
+// the divergent indices of 32 different Jacobi sweeps never conflict.
+constexpr int JAC_DOUBLES = 162;
 
+template <int S>
 __device__ __forceinline__ bool solve_hypothesis(const RansacWork& w, const float4* __restrict__ pts, int n,
                                                  int32_t pos, float Hf[8], double* Hd, double* jac)
 {
@@ -133,7 +160,7 @@ __device__ __forceinline__ bool solve_hypothesis(const RansacWork& w, const floa
     }
     double H[9];
     Pts4 P{ ms1, ms2 };
-    if (!run_kernel_seq(P, 4, H, jac, jac + 81)) return false;
+    if (!run_kernel_seq<Pts4, S>(P, 4, H, jac, jac + 81 * S)) return false;
     #pragma unroll
     for (int i = 0; i < 8; i++) Hf[i] = (float)H[i];
     if (Hd) for (int i = 0; i < 9; i++) Hd[i] = H[i];
@@ -142,7 +169,7 @@ __device__ __forceinline__ bool solve_hypothesis(const RansacWork& w, const floa
 
 constexpr int HYP_THREADS = 64;
 constexpr int HYP_PTS = 512;
-constexpr int HYP_SMEM = HYP_THREADS * JAC_STRIDE * 8 + HYP_PTS * 16;
+constexpr int HYP_SMEM = HYP_THREADS * JAC_DOUBLES * 8 + HYP_PTS * 16;
 
 __global__ void __launch_bounds__(HYP_THREADS)
 ransac_hyp_kernel(RansacWork w)
@@ -159,13 +186,13 @@ ransac_hyp_kernel(RansacWork w)
     float Hf[8];
     bool valid = false;
     if (active)
-        valid = solve_hypothesis(w, pts, n, w.sample_pos[(size_t)set * w.max_iters + iter], Hf, nullptr,
-                                 hyp_smem + threadIdx.x * JAC_STRIDE);
+        valid = solve_hypothesis<HYP_THREADS>(w, pts, n, w.sample_pos[(size_t)set * w.max_iters + iter], Hf, nullptr,
+                                              hyp_smem + threadIdx.x);
     if (!valid) {
         #pragma unroll
         for (int i = 0; i < 8; i++) Hf[i] = 0.f;
     }
-    float4* spts = reinterpret_cast<float4*>(hyp_smem + HYP_THREADS * JAC_STRIDE);
+    float4* spts = reinterpret_cast<float4*>(hyp_smem + HYP_THREADS * JAC_DOUBLES);
     int good = 0;
     for (int base = 0; base < n; base += HYP_PTS) {
         const int cnt = min(HYP_PTS, n - base);
@@ -259,7 +286,7 @@ struct FinishShared {
     LmState lm;
     double H[9];
     double scratch_a[81], scratch_v[81];
-    double jac[JAC_STRIDE];
+    double jac[JAC_DOUBLES];
     float Hf[8];
     int flag;
     int warp_cnt[RS_THREADS / 32];
@@ -351,7 +378,7 @@ ransac_finish_kernel(RansacWork w)
     // winner's model again (deterministic) -> its mask, in original order
     if (tid == 0) {
         float Hf[8];
-        solve_hypothesis(w, pts, n, w.sample_pos[(size_t)set * w.max_iters + best_iter], Hf, sh.H, sh.jac);
+        solve_hypothesis<1>(w, pts, n, w.sample_pos[(size_t)set * w.max_iters + best_iter], Hf, sh.H, sh.jac);
         for (int i = 0; i < 8; i++) sh.Hf[i] = Hf[i];
         sh.base_cnt = 0;
     }

@@ -15,6 +15,17 @@ int hm_run_kernel(const float* src, const float* dst, int n, double* H)
     return cvg::run_kernel_seq(P, n, H, LtL, V) ? 1 : 0;
 }
 
+// element-major (strided) storage of LtL / V, as the hypothesis kernel uses in shared memory
+int hm_run_kernel_strided(const float* src, const float* dst, int n, double* H)
+{
+    std::vector<float4> p(n);
+    for (int i = 0; i < n; i++) p[i] = float4{ src[2 * i], src[2 * i + 1], dst[2 * i], dst[2 * i + 1] };
+    constexpr int S = 64;
+    std::vector<double> buf(162 * S + 7, -777.0);
+    cvg::PtsStrided P{ p.data(), nullptr };
+    return cvg::run_kernel_seq<cvg::PtsStrided, S>(P, n, H, buf.data() + 5, buf.data() + 5 + 81 * S) ? 1 : 0;
+}
+
 int hm_check_subset4(const float* ms1, const float* ms2) { return cvg::check_subset4(ms1, ms2) ? 1 : 0; }
 
 float hm_reproj_err(const double* H, float Mx, float My, float mx, float my)

@@ -56,6 +56,9 @@ def test_pieces_match_oracle(hm, oracle):
         assert bool(ok) == (H2 is not None)
         if ok:
             assert np.array_equal(H1, H2.ravel(), equal_nan=True)
+            H3 = np.zeros(9)
+            assert hm.hm_run_kernel_strided(_p(s), _p(d), n, _p(H3)) == 1
+            assert np.array_equal(H1, H3, equal_nan=True)
             if np.isfinite(H1).all():
                 Hl = H1.copy(); hm.hm_lm_refine(_p(s), _p(d), n, _p(Hl), 10)
                 Ho, _ = oracle.lm_refine(s, d, H2)
