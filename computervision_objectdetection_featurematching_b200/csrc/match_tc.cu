@@ -119,6 +119,36 @@ __device__ __forceinline__ uint64_t desc_sw32(uint32_t saddr)
 // both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 
+// Running top-2 (largest acc') of one query row over 32 more train columns.  The row's second best b2
+// is a filter: maxima of groups of 4 columns are compared with it first, so a group costs ~2 instructions
+// per lane unless one of the warp's 32 rows really has a new candidate in it (a rare event per row, but
+// common per warp if tested at 32-column granularity).  Strict > keeps the earlier (lower) train index
+// on ties, as cv::batchDistance's insertion does.
+__device__ __forceinline__ void top2_scan32(const uint32_t* r, int c0, float& b1, int& i1, float& b2, int& i2)
+{
+    float g[8];
+    #pragma unroll
+    for (int k = 0; k < 8; k++)
+        g[k] = fmaxf(fmaxf(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1])),
+                     fmaxf(__uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3])));
+    const float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
+    if (m > b2) {
+        #pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (g[k] > b2) {
+                #pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float v = __uint_as_float(r[4 * k + j]);
+                    if (v > b2) {
+                        if (v > b1) { b2 = b1; i2 = i1; b1 = v; i1 = c0 + 4 * k + j; }
+                        else        { b2 = v; i2 = c0 + 4 * k + j; }
+                    }
+                }
+            }
+        }
+    }
+}
+
 struct TcMaps { CUtensorMap q, qaug, t, taug; };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -229,24 +259,13 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TILE_N + half * 128;
                 const int col_base = un.t_local0 + t * TILE_N + half * 128;
                 #pragma unroll 1
-                for (int ch = 0; ch < 4; ch++) {
-                    uint32_t r[32];
-                    tc_ld32(tbase + ch * 32, r);
+                for (int ch = 0; ch < 4; ch += 2) {
+                    uint32_t ra[32], rb[32];
+                    tc_ld32(tbase + ch * 32, ra);                 // two loads in flight before the wait
+                    tc_ld32(tbase + ch * 32 + 32, rb);
                     tc_wait_ld();
-                    float m = __uint_as_float(r[0]);
-                    #pragma unroll
-                    for (int j = 1; j < 32; j++) m = fmaxf(m, __uint_as_float(r[j]));
-                    if (m > b2) {
-                        const int c0 = col_base + ch * 32;
-                        #pragma unroll
-                        for (int j = 0; j < 32; j++) {
-                            const float v = __uint_as_float(r[j]);
-                            if (v > b2) {                               // strict: earlier (lower) index wins ties
-                                if (v > b1) { b2 = b1; i2 = i1; b1 = v; i1 = c0 + j; }
-                                else        { b2 = v; i2 = c0 + j; }
-                            }
-                        }
-                    }
+                    top2_scan32(ra, col_base + ch * 32, b1, i1, b2, i2);
+                    top2_scan32(rb, col_base + ch * 32 + 32, b1, i1, b2, i2);
                 }
                 tc_fence_before();
                 __syncwarp();
