@@ -91,7 +91,7 @@ struct cvg_ctx {
     DevBuf q_f32, q_b, q_aug, q_norm;                  // raw-query path
     DevBuf t_f32, t_b, t_aug, t_kpt, t_kptoff;         // per-call train path
     DevBuf units, dir, parts, idx, dist, accept;
-    DevBuf pts, starts, counts_n, sample_pos, n_samples, counts, best_iter, best_count, iters_run, sel;
+    DevBuf pts, starts, counts_n, sample_pos, n_samples, counts, best_iter, best_count, iters_run, niters_cur, sel;
     DevBuf H, mask, rmask, found, sflags, results, inl_xy, inl_cnt, scales, src, dst;
 };
 
@@ -148,7 +148,7 @@ void cvg_destroy(cvg_ctx* c)
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = { &c->q_f32, &c->q_b, &c->q_aug, &c->q_norm, &c->t_f32, &c->t_b, &c->t_aug, &c->t_kpt, &c->t_kptoff,
                        &c->units, &c->dir, &c->parts, &c->idx, &c->dist, &c->accept, &c->pts, &c->starts, &c->counts_n,
-                       &c->sample_pos, &c->n_samples, &c->counts, &c->best_iter, &c->best_count, &c->iters_run, &c->sel,
+                       &c->sample_pos, &c->n_samples, &c->counts, &c->best_iter, &c->best_count, &c->iters_run, &c->niters_cur, &c->sel,
                        &c->H, &c->mask, &c->rmask, &c->found, &c->sflags, &c->results, &c->inl_xy, &c->inl_cnt,
                        &c->scales, &c->src, &c->dst };
     for (DevBuf* b : bufs) b->release();
@@ -329,6 +329,7 @@ static int run_ransac(cvg_ctx* c, const float4* d_pts, const int64_t* d_starts, 
     CU_CHECK(c->best_iter.ensure((size_t)n_sets * 4));
     CU_CHECK(c->best_count.ensure((size_t)n_sets * 4));
     CU_CHECK(c->iters_run.ensure((size_t)n_sets * 4));
+    CU_CHECK(c->niters_cur.ensure((size_t)n_sets * 4));
     CU_CHECK(c->sflags.ensure((size_t)n_sets * 4));
     CU_CHECK(c->found.ensure((size_t)n_sets * 4));
     CU_CHECK(c->H.ensure((size_t)n_sets * 9 * 8));
@@ -345,11 +346,11 @@ static int run_ransac(cvg_ctx* c, const float4* d_pts, const int64_t* d_starts, 
     w.sample_pos = c->sample_pos.as<int32_t>(); w.n_samples = c->n_samples.as<int32_t>();
     w.counts = c->counts.as<int32_t>(); w.best_iter = c->best_iter.as<int32_t>();
     w.best_count = c->best_count.as<int32_t>(); w.iters_run = c->iters_run.as<int32_t>();
+    w.niters_cur = c->niters_cur.as<int32_t>();
     w.sel = c->sel.as<int32_t>(); w.H = c->H.as<double>(); w.mask = c->mask.as<uint8_t>();
     w.ransac_mask = want_rmask ? c->rmask.as<uint8_t>() : nullptr;
     w.found = c->found.as<int32_t>(); w.status_flags = c->sflags.as<int32_t>();
-    launch_ransac(w, c->stream);
-    c->launches += 4;
+    c->launches += launch_ransac(w, c->stream);
     CU_CHECK(cudaGetLastError());
     return CVG_OK;
 }

@@ -87,6 +87,7 @@ struct RansacWork {
     int32_t* best_iter;         // [P]
     int32_t* best_count;        // [P]
     int32_t* iters_run;         // [P]
+    int32_t* niters_cur;        // [P] adaptive niters after the rounds scanned so far
     int32_t* sel;               // [total] compacted inlier indices
     // outputs
     double* H;                  // [P, 9]
@@ -95,7 +96,7 @@ struct RansacWork {
     int32_t* found;             // [P]
     int32_t* status_flags;      // [P] bit0: rng table exhausted
 };
-void launch_ransac(const RansacWork& w, cudaStream_t st);
+int  launch_ransac(const RansacWork& w, cudaStream_t st);   // returns the number of kernel launches
 
 // detect glue (ransac.cu)
 struct GateWork {

@@ -61,11 +61,14 @@ __device__ __forceinline__ int draw_subset(const uint32_t* __restrict__ tab, int
 
 // ---- 1. sample kernel ------------------------------------------------------------------------------
 // A window of SW consecutive draw positions is evaluated in parallel: for every position p the attempt
-// that would start there (draws consumed, checkSubset verdict).  One thread then follows the chain
-// p -> p + consumed(p) through shared memory, which is exactly the order in which the serial getSubset
-// consumes the stream, including rejected attempts and the 10000-attempt limit.
+// that would start there (draws consumed, checkSubset verdict).  The serial getSubset visits the chain
+// p -> p + consumed(p); the nodes of that chain inside the window are found by pointer jumping
+// (7 doubling rounds: an attempt consumes >= 4 draws, so a 512-wide window holds <= 128 chain nodes),
+// ranked by a block prefix sum, and the accepted ones become the samples of consecutive iterations —
+// the same order, rejected attempts and 10000-attempt limit as the serial loop.
 constexpr int SW = 512;
 constexpr int SW_TAIL = 64;                       // draws staged beyond the window for attempts that start near its end
+constexpr int SW_PER_THREAD = SW / RS_THREADS;    // 4 consecutive window offsets per thread
 
 __global__ void __launch_bounds__(RS_THREADS)
 ransac_sample_kernel(RansacWork w)
@@ -73,6 +76,7 @@ ransac_sample_kernel(RansacWork w)
     const int set = blockIdx.x;
     const int n = w.counts_n[set];
     int32_t* out = w.sample_pos + (size_t)set * w.max_iters;
+    if (threadIdx.x == 0) { w.niters_cur[set] = max(w.max_iters, 1); w.best_iter[set] = -1; w.best_count[set] = 0; }
     if (n <= 4) {                                   // n < 4: nothing; n == 4: handled by finish kernel
         if (threadIdx.x == 0) { w.n_samples[set] = 0; w.status_flags[set] = 0; }
         return;
@@ -81,27 +85,31 @@ ransac_sample_kernel(RansacWork w)
     __shared__ float4 spts[SMEM_PTS];
     __shared__ uint16_t info[SW];                   // bit 15: checkSubset ok; bits 0-14: draws consumed (0 = overrun)
     __shared__ int32_t s_draw[SW + SW_TAIL];        // uniform(0,n) of the window's draw positions (-1 past the table)
-    __shared__ long long s_pos;
-    __shared__ int s_iter, s_attempts, s_done, s_flags;
+    __shared__ uint16_t jump[2][SW];
+    __shared__ uint8_t reach[SW];
+    __shared__ int s_wsum[RS_THREADS / 32][2];
+    __shared__ int s_last, s_first_ok, s_last_ok, s_bad;
     const bool staged = n <= SMEM_PTS;
     if (staged)
         for (int i = threadIdx.x; i < n; i += RS_THREADS) spts[i] = pts[i];
-    if (threadIdx.x == 0) { s_pos = 0; s_iter = 0; s_attempts = 0; s_done = 0; s_flags = 0; }
-    __syncthreads();
+    int64_t base = 0;
+    int iter = 0, attempts = 0, flags = 0;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const TabGet slow{ w.rng_tab, w.rng_len, (uint32_t)n };
     for (;;) {
-        const int64_t base = s_pos;
+        __syncthreads();
         for (int j = threadIdx.x; j < SW + SW_TAIL; j += RS_THREADS) {
             const int64_t pp = base + j;
             s_draw[j] = pp < w.rng_len ? (int32_t)(w.rng_tab[pp] % (uint32_t)n) : -1;
         }
+        if (threadIdx.x == 0) { s_last = 0; s_first_ok = SW; s_last_ok = -1; s_bad = 0; }
         __syncthreads();
-        const TabGet slow{ w.rng_tab, w.rng_len, (uint32_t)n };
         auto get = [&](int64_t pos) -> int {
             const int64_t j = pos - base;
             return j < SW + SW_TAIL ? s_draw[j] : slow(pos);
         };
         #pragma unroll 1
-        for (int k = 0; k < SW / RS_THREADS; k++) {
+        for (int k = 0; k < SW_PER_THREAD; k++) {
             const int o = k * RS_THREADS + threadIdx.x;
             int idx[4];
             const int cons = draw_subset_g(get, base + o, idx);
@@ -116,27 +124,91 @@ ransac_sample_kernel(RansacWork w)
                 e = (uint16_t)(cons | (check_subset4(ms1, ms2) ? 0x8000 : 0));
             }
             info[o] = e;
+            const int c = e & 0x7fff;
+            jump[0][o] = (uint16_t)((c == 0 || o + c >= SW) ? SW : o + c);
+            reach[o] = o == 0 ? 1 : 0;
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int64_t p = base;
-            int iter = s_iter, attempts = s_attempts, done = 0, flags = 0;
-            while (p < base + SW && iter < w.max_iters) {
-                const uint16_t e = info[p - base];
-                const int c = e & 0x7fff;
-                if (c == 0) { flags = 1; done = 1; break; }              // RNG table exhausted
-                if (e & 0x8000) { out[iter++] = (int32_t)p; attempts = 0; }
-                else if (++attempts >= 10000) { done = 1; break; }       // getSubset gave up
-                p += c;
+        int cur = 0;
+        #pragma unroll 1
+        for (int r = 0; r < 7; r++) {                 // reach = { next^i(0) : i < 2^(r+1) }
+            #pragma unroll
+            for (int k = 0; k < SW_PER_THREAD; k++) {
+                const int o = k * RS_THREADS + threadIdx.x;
+                const int j = jump[cur][o];
+                if (reach[o] && j < SW) reach[j] = 1;
+                jump[cur ^ 1][o] = (uint16_t)(j < SW ? jump[cur][j] : SW);
             }
-            if (iter >= w.max_iters) done = 1;
-            if (p + SW + 64 >= 0x7fffffffLL) { flags = 1; done = 1; }
-            s_pos = p; s_iter = iter; s_attempts = attempts; s_done = done; s_flags = flags;
+            __syncthreads();
+            cur ^= 1;
         }
+        // rank the chain nodes (offsets tid*4 .. tid*4+3 per thread, so ranks follow stream order)
+        int n_reach = 0, n_ok = 0, mask_r = 0, mask_ok = 0;
+        #pragma unroll
+        for (int k = 0; k < SW_PER_THREAD; k++) {
+            const int o = threadIdx.x * SW_PER_THREAD + k;
+            if (reach[o]) {
+                const uint16_t e = info[o];
+                mask_r |= 1 << k; n_reach++;
+                if ((e & 0x7fff) == 0) atomicExch(&s_bad, 1);
+                if (e & 0x8000) { mask_ok |= 1 << k; n_ok++; atomicMin(&s_first_ok, o); atomicMax(&s_last_ok, o); }
+                atomicMax(&s_last, o);
+            }
+        }
+        int pre_r = n_reach, pre_ok = n_ok;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int a = __shfl_up_sync(0xffffffffu, pre_r, d), b2 = __shfl_up_sync(0xffffffffu, pre_ok, d);
+            if (lane >= d) { pre_r += a; pre_ok += b2; }
+        }
+        if (lane == 31) { s_wsum[wid][0] = pre_r; s_wsum[wid][1] = pre_ok; }
         __syncthreads();
-        if (s_done) break;
+        int off_r = 0, off_ok = 0, tot_r = 0, tot_ok = 0;
+        #pragma unroll
+        for (int q = 0; q < RS_THREADS / 32; q++) {
+            if (q < wid) { off_r += s_wsum[q][0]; off_ok += s_wsum[q][1]; }
+            tot_r += s_wsum[q][0]; tot_ok += s_wsum[q][1];
+        }
+        const int excl_r = off_r + pre_r - n_reach, excl_ok = off_ok + pre_ok - n_ok;   // exclusive ranks of this thread
+        const int first_ok = s_first_ok, last_ok = s_last_ok, last = s_last;
+        if (s_bad) { flags |= 1; break; }                       // RNG table exhausted
+        // failures before the first accepted attempt of this window extend the running failure count
+        int fails_head = 0, fails_tail = 0;
+        {
+            // nodes before first_ok / after last_ok: count with the same block-wide sums
+            int h = 0, t = 0;
+            #pragma unroll
+            for (int k = 0; k < SW_PER_THREAD; k++) {
+                const int o = threadIdx.x * SW_PER_THREAD + k;
+                if ((mask_r >> k) & 1) { h += o < first_ok; t += o > last_ok; }
+            }
+            #pragma unroll
+            for (int d = 16; d > 0; d >>= 1) { h += __shfl_xor_sync(0xffffffffu, h, d); t += __shfl_xor_sync(0xffffffffu, t, d); }
+            __syncthreads();
+            if (lane == 0) { s_wsum[wid][0] = h; s_wsum[wid][1] = t; }
+            __syncthreads();
+            #pragma unroll
+            for (int q = 0; q < RS_THREADS / 32; q++) { fails_head += s_wsum[q][0]; fails_tail += s_wsum[q][1]; }
+        }
+        if (attempts + fails_head >= 10000) break;              // getSubset gave up before the next success
+        // emit accepted attempts as the samples of iterations iter, iter+1, ...
+        {
+            int r = excl_ok;
+            #pragma unroll
+            for (int k = 0; k < SW_PER_THREAD; k++)
+                if ((mask_ok >> k) & 1) {
+                    if (iter + r < w.max_iters) out[iter + r] = (int32_t)(base + threadIdx.x * SW_PER_THREAD + k);
+                    r++;
+                }
+        }
+        (void)excl_r; (void)tot_r;
+        attempts = tot_ok > 0 ? fails_tail : attempts + fails_head;
+        iter = min(iter + tot_ok, w.max_iters);
+        if (iter >= w.max_iters) break;
+        base = base + last + (info[last] & 0x7fff);
+        if (base + SW + SW_TAIL + 64 >= 0x7fffffffLL) { flags |= 1; break; }
     }
-    if (threadIdx.x == 0) { w.n_samples[set] = s_iter; w.status_flags[set] = s_flags; }
+    if (threadIdx.x == 0) { w.n_samples[set] = iter; w.status_flags[set] = flags; }
 }
 
 // ---- 2. hypothesis kernel: solve + score ------------------------------------------------------------
@@ -172,14 +244,15 @@ constexpr int HYP_PTS = 512;
 constexpr int HYP_SMEM = HYP_THREADS * JAC_DOUBLES * 8 + HYP_PTS * 16;
 
 __global__ void __launch_bounds__(HYP_THREADS)
-ransac_hyp_kernel(RansacWork w)
+ransac_hyp_kernel(RansacWork w, int round_base)
 {
     extern __shared__ double hyp_smem[];
     const int set = blockIdx.y;
     const int n = w.counts_n[set];
     const int n_samples = w.n_samples[set];
-    const int iter0 = blockIdx.x * HYP_THREADS;
-    if (iter0 >= n_samples) return;
+    const int iter0 = round_base + blockIdx.x * HYP_THREADS;
+    // hypotheses at or beyond the adaptive niters (as known after the previous round) are never looked at
+    if (iter0 >= n_samples || iter0 >= w.niters_cur[set]) return;
     const float4* __restrict__ pts = w.pts + w.starts[set];
     const int iter = iter0 + threadIdx.x;
     const bool active = iter < n_samples;
@@ -210,7 +283,7 @@ ransac_hyp_kernel(RansacWork w)
 }
 
 // ---- 3. select kernel: the serial scan of RANSACPointSetRegistrator::run --------------------------
-__global__ void ransac_select_kernel(RansacWork w)
+__global__ void ransac_select_kernel(RansacWork w, int round_base, int round_len)
 {
     const int set = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -218,15 +291,16 @@ __global__ void ransac_select_kernel(RansacWork w)
     const int n = w.counts_n[set];
     const int n_samples = w.n_samples[set];
     const int32_t* __restrict__ counts = w.counts + (size_t)set * w.max_iters;
-    int niters = max(w.max_iters, 1);
-    int best = 0, best_iter = -1;
-    int base = 0;
-    while (base < niters && base < n_samples) {
+    int niters = w.niters_cur[set];
+    int best = w.best_count[set], best_iter = w.best_iter[set];
+    int base = round_base;
+    const int end = min(round_base + round_len, n_samples);
+    while (base < niters && base < end) {
         const int it = base + lane;
-        const int c = (it < n_samples) ? counts[it] : -1;
+        const int c = (it < end) ? counts[it] : -1;
         int start = 0;
         for (;;) {
-            const bool cand = lane >= start && it < niters && it < n_samples && c > max(best, 3);
+            const bool cand = lane >= start && it < niters && it < end && c > max(best, 3);
             const unsigned bal = __ballot_sync(0xffffffffu, cand);
             if (!bal) break;
             const int f = __ffs(bal) - 1;
@@ -241,6 +315,7 @@ __global__ void ransac_select_kernel(RansacWork w)
     if (lane == 0) {
         w.best_iter[set] = best_iter;
         w.best_count[set] = best;
+        w.niters_cur[set] = niters;
         // value of `iter` when the reference loop exits
         w.iters_run[set] = n <= 4 ? 0 : min(max(niters, best_iter + 1), n_samples);
     }
@@ -529,20 +604,34 @@ ransac_finish_kernel(RansacWork w)
     if (tid == 0) w.found[set] = 1;
 }
 
-void launch_ransac(const RansacWork& w, cudaStream_t st)
+int launch_ransac(const RansacWork& w, cudaStream_t st)
 {
-    if (w.n_sets <= 0) return;
+    if (w.n_sets <= 0) return 0;
+    int launches = 2;
     ransac_sample_kernel<<<w.n_sets, RS_THREADS, 0, st>>>(w);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(ransac_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HYP_SMEM);
         attr_set = true;
     }
-    dim3 grid((w.max_iters + HYP_THREADS - 1) / HYP_THREADS, w.n_sets);
-    ransac_hyp_kernel<<<grid, HYP_THREADS, HYP_SMEM, st>>>(w);
+    // hypotheses are solved and scored in rounds; after each round the serial selection scan advances, so
+    // rounds beyond the adaptive stop (RANSACUpdateNumIters) cost one early-exit per block
+    int round_len = w.max_iters;
+    if (!(w.flags & CVG_RANSAC_NO_EARLY_STOP)) {
+        round_len = (w.max_iters + 15) / 16;
+        if (round_len < 256) round_len = 256;
+        round_len = (round_len + HYP_THREADS - 1) / HYP_THREADS * HYP_THREADS;
+    }
     const int warps_per_block = 4;
-    ransac_select_kernel<<<(w.n_sets + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(w);
+    for (int rb = 0; rb < w.max_iters; rb += round_len) {
+        const int len = w.max_iters - rb < round_len ? w.max_iters - rb : round_len;
+        dim3 grid((len + HYP_THREADS - 1) / HYP_THREADS, w.n_sets);
+        ransac_hyp_kernel<<<grid, HYP_THREADS, HYP_SMEM, st>>>(w, rb);
+        ransac_select_kernel<<<(w.n_sets + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(w, rb, len);
+        launches += 2;
+    }
     ransac_finish_kernel<<<w.n_sets, RS_THREADS, 0, st>>>(w);
+    return launches;
 }
 
 // ---- gates + inlier gather: reference src/TestsDetector.cpp:74-94 ---------------------------------
