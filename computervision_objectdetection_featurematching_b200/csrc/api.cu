@@ -47,6 +47,38 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// Freed device buffers are kept for reuse: cudaMalloc/cudaFree cost milliseconds and serialise the
+// device, which would dominate a streaming caller that uploads a scene batch per step.
+struct BufPool {
+    std::vector<DevBuf> free_list;
+    cudaError_t acquire(DevBuf& b, size_t bytes)
+    {
+        if (b.cap >= bytes) return cudaSuccess;
+        if (b.p) { release(b); }
+        int best = -1;
+        for (int i = 0; i < (int)free_list.size(); i++)
+            if (free_list[i].cap >= bytes && (best < 0 || free_list[i].cap < free_list[best].cap)) best = i;
+        if (best >= 0 && free_list[best].cap <= 2 * bytes + (1 << 20)) {
+            b = free_list[best];
+            free_list.erase(free_list.begin() + best);
+            return cudaSuccess;
+        }
+        return b.ensure(bytes);
+    }
+    void release(DevBuf& b)
+    {
+        if (!b.p) return;
+        if (free_list.size() >= 24) {               // bounded: drop the smallest cached buffer
+            int small = 0;
+            for (int i = 1; i < (int)free_list.size(); i++) if (free_list[i].cap < free_list[small].cap) small = i;
+            if (free_list[small].cap < b.cap) { free_list[small].release(); free_list[small] = b; }
+            else b.release();
+        } else free_list.push_back(b);
+        b.p = nullptr; b.cap = 0;
+    }
+    void clear() { for (DevBuf& b : free_list) b.release(); free_list.clear(); }
+};
+
 struct SegInfo { int rows; int64_t f32_row0; int64_t pad_row0; int ct; };
 
 struct TrainSet {                      // a prepared set of train segments on the device
@@ -93,6 +125,7 @@ struct cvg_ctx {
     DevBuf units, dir, parts, idx, dist, accept;
     DevBuf pts, starts, counts_n, sample_pos, n_samples, counts, best_iter, best_count, iters_run, niters_cur, sel;
     DevBuf H, mask, rmask, found, sflags, results, inl_xy, inl_cnt, scales, src, dst;
+    BufPool pool;                                      // recycled buffers of freed scene batches
 };
 
 extern "C" {
@@ -152,6 +185,7 @@ void cvg_destroy(cvg_ctx* c)
                        &c->H, &c->mask, &c->rmask, &c->found, &c->sflags, &c->results, &c->inl_xy, &c->inl_cnt,
                        &c->scales, &c->src, &c->dst };
     for (DevBuf* b : bufs) b->release();
+    c->pool.clear();
     if (c->d_flags) cudaFree(c->d_flags);
     if (c->d_rng) cudaFree(c->d_rng);
     for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -198,10 +232,12 @@ static int ensure_rng(cvg_ctx* c, int max_iters)
 }
 
 // Prepare (convert) a train set that is already in device fp32 memory.
-static int prep_train(cvg_ctx* c, TrainSet& ts, DevBuf& b, DevBuf& aug, int flag_slot)
+static int prep_train(cvg_ctx* c, TrainSet& ts, DevBuf& b, DevBuf& aug, int flag_slot, bool pooled = false)
 {
-    CU_CHECK(b.ensure((size_t)std::max<int64_t>(ts.rows_pad_total, 1) * DIM * 2));
-    CU_CHECK(aug.ensure((size_t)std::max<int64_t>(ts.rows_pad_total, 1) * KAUG * 2));
+    const size_t nb = (size_t)std::max<int64_t>(ts.rows_pad_total, 1) * DIM * 2;
+    const size_t na = (size_t)std::max<int64_t>(ts.rows_pad_total, 1) * KAUG * 2;
+    if (pooled) { CU_CHECK(c->pool.acquire(b, nb)); CU_CHECK(c->pool.acquire(aug, na)); }
+    else { CU_CHECK(b.ensure(nb)); CU_CHECK(aug.ensure(na)); }
     ts.d_b = b.as<__nv_bfloat16>(); ts.d_aug = aug.as<__nv_bfloat16>();
     for (const SegInfo& s : ts.segs) {
         const int n_pad = s.ct * TILE_N;
@@ -587,8 +623,13 @@ static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, Tra
         std::vector<MatchUnit> units; std::vector<MergeEntry> dir;
         build_plan(q, ts, c->n_sms, units, dir, n_rb);
         DevBuf& ub = cache ? cache->units : c->units; DevBuf& db = cache ? cache->dir : c->dir;
-        CU_CHECK(ub.ensure(std::max<size_t>(units.size(), 1) * sizeof(MatchUnit)));
-        CU_CHECK(db.ensure(std::max<size_t>(dir.size(), 1) * sizeof(MergeEntry)));
+        if (cache) {
+            CU_CHECK(c->pool.acquire(ub, std::max<size_t>(units.size(), 1) * sizeof(MatchUnit)));
+            CU_CHECK(c->pool.acquire(db, std::max<size_t>(dir.size(), 1) * sizeof(MergeEntry)));
+        } else {
+            CU_CHECK(ub.ensure(std::max<size_t>(units.size(), 1) * sizeof(MatchUnit)));
+            CU_CHECK(db.ensure(std::max<size_t>(dir.size(), 1) * sizeof(MergeEntry)));
+        }
         if (!units.empty()) CU_CHECK(cudaMemcpyAsync(ub.p, units.data(), units.size() * sizeof(MatchUnit), cudaMemcpyHostToDevice, c->stream));
         if (!dir.empty()) CU_CHECK(cudaMemcpyAsync(db.p, dir.data(), dir.size() * sizeof(MergeEntry), cudaMemcpyHostToDevice, c->stream));
         CU_CHECK(cudaStreamSynchronize(c->stream));       // host vectors go out of scope
@@ -726,16 +767,16 @@ int cvg_scenes_upload(cvg_ctx* c, const float* desc, const float* kpt_xy, const 
     cvg_scenes* sc = new cvg_scenes();
     layout_segments(sc->ts, offsets, n_scenes);
     if (sc->ts.rows_pad_total > 0x7fffff00LL) { delete sc; return set_err(CVG_ERR_LIMIT, "scene batch too large (>2^31 padded rows)"); }
-    CU_CHECK(sc->f32.ensure((size_t)std::max<int64_t>(total, 1) * DIM * 4));
-    CU_CHECK(sc->kpt.ensure((size_t)std::max<int64_t>(total, 1) * 8));
-    CU_CHECK(sc->kptoff.ensure((size_t)(n_scenes + 1) * 8));
+    CU_CHECK(c->pool.acquire(sc->f32, (size_t)std::max<int64_t>(total, 1) * DIM * 4));
+    CU_CHECK(c->pool.acquire(sc->kpt, (size_t)std::max<int64_t>(total, 1) * 8));
+    CU_CHECK(c->pool.acquire(sc->kptoff, (size_t)(n_scenes + 1) * 8));
     sc->ts.d_f32 = sc->f32.as<float>(); sc->ts.d_kpt = sc->kpt.as<float>(); sc->ts.d_kpt_offsets = sc->kptoff.as<int64_t>();
     if (total > 0) CU_CHECK(cudaMemcpyAsync(sc->ts.d_f32, desc, (size_t)total * DIM * 4, cudaMemcpyHostToDevice, c->stream));
     if (total > 0 && kpt_xy) CU_CHECK(cudaMemcpyAsync(sc->ts.d_kpt, kpt_xy, (size_t)total * 8, cudaMemcpyHostToDevice, c->stream));
     else if (total > 0) CU_CHECK(cudaMemsetAsync(sc->ts.d_kpt, 0, (size_t)total * 8, c->stream));
     CU_CHECK(cudaMemcpyAsync(sc->ts.d_kpt_offsets, offsets, (size_t)(n_scenes + 1) * 8, cudaMemcpyHostToDevice, c->stream));
     CU_CHECK(cudaMemsetAsync(c->d_flags, 0, 4, c->stream));
-    int rc = prep_train(c, sc->ts, sc->b, sc->aug, 0);
+    int rc = prep_train(c, sc->ts, sc->b, sc->aug, 0, true);
     if (rc) { delete sc; return rc; }
     int flag = 0;
     CU_CHECK(cudaMemcpyAsync(&flag, c->d_flags, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -748,9 +789,14 @@ int cvg_scenes_upload(cvg_ctx* c, const float* desc, const float* kpt_xy, const 
 void cvg_scenes_free(cvg_ctx* c, cvg_scenes* sc)
 {
     if (!sc) return;
-    if (c) cudaSetDevice(c->device);
-    sc->f32.release(); sc->b.release(); sc->aug.release(); sc->kpt.release(); sc->kptoff.release();
-    sc->units.release(); sc->dir.release();
+    if (c) {
+        cudaSetDevice(c->device);
+        DevBuf* bufs[] = { &sc->f32, &sc->b, &sc->aug, &sc->kpt, &sc->kptoff, &sc->units, &sc->dir };
+        for (DevBuf* b : bufs) c->pool.release(*b);
+    } else {
+        sc->f32.release(); sc->b.release(); sc->aug.release(); sc->kpt.release(); sc->kptoff.release();
+        sc->units.release(); sc->dir.release();
+    }
     delete sc;
 }
 
