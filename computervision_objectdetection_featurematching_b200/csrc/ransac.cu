@@ -20,6 +20,7 @@
 //                        OpenCV's exact summation order (bit-exact H); larger sets use block reductions.
 #include "common.cuh"
 #include "homography_math.cuh"
+#include "jacobi_warp.cuh"
 
 namespace cvg {
 
@@ -282,6 +283,51 @@ ransac_hyp_kernel(RansacWork w, int round_base)
     if (active) w.counts[(size_t)set * w.max_iters + iter] = valid ? good : -1;
 }
 
+// Warp-per-hypothesis variant, used when a round holds too few hypotheses to hide the latency of
+// thread-serial Jacobi sweeps (few image pairs in flight): the warp solves the DLT cooperatively
+// (jacobi_warp.cuh), then its lanes score the correspondences with coalesced float4 reads and a
+// warp-reduced count.  Bit-identical to ransac_hyp_kernel.
+constexpr int HYPW_WARPS = 8;
+constexpr int HYPW_SMEM_D = 81 + 81 + 9 + 72;       // doubles of scratch per warp
+
+__global__ void __launch_bounds__(HYPW_WARPS * 32)
+ransac_hyp_warp_kernel(RansacWork w, int round_base)
+{
+    __shared__ double smem[HYPW_WARPS][HYPW_SMEM_D];
+    const int set = blockIdx.y;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = w.counts_n[set];
+    const int n_samples = w.n_samples[set];
+    const int iter = round_base + blockIdx.x * HYPW_WARPS + wid;
+    if (iter >= n_samples || iter >= w.niters_cur[set]) return;          // warp-uniform
+    const float4* __restrict__ pts = w.pts + w.starts[set];
+    int idx[4];
+    draw_subset(w.rng_tab, w.rng_len, w.sample_pos[(size_t)set * w.max_iters + iter], (uint32_t)n, idx);
+    float ms1[8], ms2[8];
+    #pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float4 q = pts[idx[i]];
+        ms1[2 * i] = q.x; ms1[2 * i + 1] = q.y; ms2[2 * i] = q.z; ms2[2 * i + 1] = q.w;
+    }
+    double H[9];
+    const bool valid = run_kernel4_warp(ms1, ms2, H, smem[wid]);
+    int good = -1;
+    if (valid) {
+        float Hf[8];
+        #pragma unroll
+        for (int i = 0; i < 8; i++) Hf[i] = (float)H[i];
+        int cnt = 0;
+        for (int i = lane; i < n; i += 32) {
+            const float4 q = pts[i];
+            cnt += reproj_err(Hf, q.x, q.y, q.z, q.w) <= w.thr2 ? 1 : 0;
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        good = cnt;
+    }
+    if (lane == 0) w.counts[(size_t)set * w.max_iters + iter] = good;
+}
+
 // ---- 3. select kernel: the serial scan of RANSACPointSetRegistrator::run --------------------------
 __global__ void ransac_select_kernel(RansacWork w, int round_base, int round_len)
 {
@@ -360,8 +406,11 @@ struct FinishShared {
     double out[56];
     LmState lm;
     double H[9];
-    double scratch_a[81], scratch_v[81];
+    double scratch_a[81], scratch_v[81], scratch_w[9];
     double jac[JAC_DOUBLES];
+    double sums[8];
+    double J[2 * EXACT_MAX_INLIERS * 9];        // exact mode: Jacobian rows of the current evaluation
+    double r[2 * EXACT_MAX_INLIERS];            //             residuals
     float Hf[8];
     int flag;
     int warp_cnt[RS_THREADS / 32];
@@ -412,6 +461,117 @@ __device__ double lm_eval_block(const float4* __restrict__ pts, const int32_t* _
     }
     if (rmax) *rmax = rm;
     return acc[55];
+}
+
+// Exact-order evaluation (n_inl <= EXACT_MAX_INLIERS): rows are computed in parallel, then every sum is
+// accumulated by ONE thread in OpenCV's order (mulTransposed: sequential over rows; gemm: 4 interleaved
+// accumulators below 100 rows; norm: the AVX2 pattern) — 56 independent sums on 56 threads.
+__device__ double lm_eval_exact(const float4* __restrict__ pts, const int32_t* __restrict__ sel, int count,
+                                const double* h, bool wantJ, double* A, double* v, double* rmax, FinishShared& sh)
+{
+    const int tid = threadIdx.x;
+    const int rows = 2 * count;
+    for (int i = tid; i < count; i += RS_THREADS) {
+        const float4 q = pts[sel[i]];
+        double r0, r1, J0[9], J1[9];
+        refine_row(h, q.x, q.y, q.z, q.w, r0, r1, wantJ ? J0 : nullptr, wantJ ? J1 : nullptr);
+        sh.r[2 * i] = r0; sh.r[2 * i + 1] = r1;
+        if (wantJ) {
+            #pragma unroll
+            for (int j = 0; j < 9; j++) { sh.J[(2 * i) * 9 + j] = J0[j]; sh.J[(2 * i + 1) * 9 + j] = J1[j]; }
+        }
+    }
+    __syncthreads();
+    if (wantJ && tid < 45) {                              // upper triangle entry (j,k) of J^T J
+        int j = 0, e = tid;
+        while (e >= 9 - j) { e -= 9 - j; j++; }
+        const int k = j + e;
+        double s = 0;
+        for (int row = 0; row < rows; row++) s += sh.J[row * 9 + j] * sh.J[row * 9 + k];
+        sh.out[tid] = s;
+    } else if (wantJ && tid >= 64 && tid < 73) {          // J^T r entry
+        const int j = tid - 64;
+        double s;
+        if (rows < 100) {
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            int k = 0;
+            for (; k <= rows - 4; k += 4) {
+                s0 += sh.J[k * 9 + j] * sh.r[k]; s1 += sh.J[(k + 1) * 9 + j] * sh.r[k + 1];
+                s2 += sh.J[(k + 2) * 9 + j] * sh.r[k + 2]; s3 += sh.J[(k + 3) * 9 + j] * sh.r[k + 3];
+            }
+            for (; k < rows; k++) s0 += sh.J[k * 9 + j] * sh.r[k];
+            s = ((s0 + s1) + s2) + s3;
+        } else {
+            s = 0;
+            for (int k = 0; k < rows; k++) s += sh.J[k * 9 + j] * sh.r[k];
+        }
+        sh.out[45 + j] = s;
+    } else if (tid == 96) {                               // |r|^2 in cv::norm's order
+        NormL2SqrAcc na; na.init();
+        for (int k = 0; k < rows; k++) na.push(sh.r[k]);
+        sh.out[54] = na.finish();
+    } else if (tid == 97) {
+        double rm = 0;
+        for (int k = 0; k < rows; k++) { const double q = fabs(sh.r[k]); if (q > rm) rm = q; }
+        sh.out[55] = rm;
+    }
+    __syncthreads();
+    if (wantJ) {
+        int e = 0;
+        for (int j = 0; j < 9; j++) {
+            for (int k = j; k < 9; k++) { A[j * 9 + k] = sh.out[e]; A[k * 9 + j] = sh.out[e]; e++; }
+            v[j] = sh.out[45 + j];
+        }
+    }
+    if (rmax) *rmax = sh.out[55];
+    const double S = sh.out[54];
+    __syncthreads();
+    return S;
+}
+
+// lm_step / lm_update with the 9x9 eigen-solves run cooperatively by warp 0 (all 32 lanes call)
+__device__ void lm_step_warp(LmState& st, FinishShared& sh)
+{
+    const int lane = threadIdx.x & 31;
+    double* Ap = sh.part;                                  // 81 doubles of scratch
+    for (int e = lane; e < 81; e += 32) Ap[e] = st.A[e] + ((e / 9 == e % 9) ? st.lambda * st.D[e / 9] : 0.0);
+    __syncwarp();
+    solve_eig9_warp(Ap, st.v, st.d, sh.scratch_a, sh.scratch_v, sh.scratch_w);
+    if (lane < 9) st.xd[lane] = st.x[lane] - st.d[lane];
+    __syncwarp();
+}
+
+__device__ bool lm_update_warp(LmState& st, double Sd, FinishShared& sh)
+{
+    const double Rlo = 0.25, Rhi = 0.75;
+    const int lane = threadIdx.x & 31;
+    double temp_d[9];
+    for (int i = 0; i < 9; i++) {
+        const double s = dot4acc(st.A + i * 9, st.d, 9);
+        temp_d[i] = -1 * s + 2 * st.v[i];
+    }
+    const double dS = dot_unrolled(st.d, temp_d, 9);
+    const double R = (st.S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1);
+    double lambda = st.lambda, lc = st.lc;
+    if (R > Rhi) {
+        lambda *= 0.5;
+        if (lambda < lc) lambda = 0;
+    } else if (R < Rlo) {
+        const double t = dot_unrolled(st.d, st.v, 9);
+        double nu = (Sd - st.S) / (fabs(t) > DBL_EPSILON ? t : 1) + 2;
+        nu = nu > 2. ? nu : 2.;
+        nu = nu < 10. ? nu : 10.;
+        if (lambda == 0) {
+            const double maxval = invert_eig_max_diag9_warp(st.A, sh.scratch_a, sh.scratch_v, sh.scratch_w);
+            lambda = lc = 1. / maxval;
+            nu *= 0.5;
+        }
+        lambda *= nu;
+    }
+    __syncwarp();
+    if (lane == 0) { st.lambda = lambda; st.lc = lc; }
+    __syncwarp();
+    return Sd < st.S;
 }
 
 // ---- 4. finish kernel -----------------------------------------------------------------------------
@@ -488,38 +648,70 @@ ransac_finish_kernel(RansacWork w)
         return;
     }
     if (n_inl > 0) {
-        PtsStrided P{ pts, sel };
-        if (n_inl <= EXACT_MAX_INLIERS) {
-            // exact mode: OpenCV's sequential summation order, one thread
-            if (tid == 0) {
-                double Hn[9];
-                if (run_kernel_seq(P, n_inl, Hn, sh.scratch_a, sh.scratch_v))     // B.7 refit
-                    for (int i = 0; i < 9; i++) sh.H[i] = Hn[i];
-                lm_refine_seq(P, n_inl, sh.H, 10, sh.lm, sh.scratch_a, sh.scratch_v);   // B.8
+        const bool exact = n_inl <= EXACT_MAX_INLIERS;
+        // ---- B.7: DLT refit on the inliers ----
+        double cmx, cmy, cMx, cMy, smx, smy, sMx, sMy;
+        if (exact) {
+            // every sum by one thread, sequentially over the inliers (OpenCV's order)
+            if (tid < 4) {
+                double s0 = 0;
+                for (int i = 0; i < n_inl; i++) {
+                    const float4 q = pts[sel[i]];
+                    s0 += tid == 0 ? q.z : tid == 1 ? q.w : tid == 2 ? q.x : q.y;
+                }
+                sh.sums[tid] = s0 / n_inl;
             }
             __syncthreads();
+            cmx = sh.sums[0]; cmy = sh.sums[1]; cMx = sh.sums[2]; cMy = sh.sums[3];
+            if (tid < 4) {
+                const double cc = sh.sums[tid];
+                double s0 = 0;
+                for (int i = 0; i < n_inl; i++) {
+                    const float4 q = pts[sel[i]];
+                    s0 += fabs((tid == 0 ? q.z : tid == 1 ? q.w : tid == 2 ? q.x : q.y) - cc);
+                }
+                sh.sums[4 + tid] = s0;
+            }
+            __syncthreads();
+            smx = sh.sums[4]; smy = sh.sums[5]; sMx = sh.sums[6]; sMy = sh.sums[7];
         } else {
-            // parallel mode: block reductions (deterministic, not OpenCV's order; H agrees to ~1e-8)
-            double s[8];
-            #pragma unroll
-            for (int k = 0; k < 8; k++) s[k] = 0;
+            double s[4] = { 0, 0, 0, 0 };
             for (int i = tid; i < n_inl; i += RS_THREADS) {
                 const float4 q = pts[sel[i]];
                 s[0] += q.z; s[1] += q.w; s[2] += q.x; s[3] += q.y;
             }
             block_sum<4>(s, sh.part, sh.out);
-            const double cmx = s[0] / n_inl, cmy = s[1] / n_inl, cMx = s[2] / n_inl, cMy = s[3] / n_inl;
-            #pragma unroll
-            for (int k = 0; k < 4; k++) s[k] = 0;
+            cmx = s[0] / n_inl; cmy = s[1] / n_inl; cMx = s[2] / n_inl; cMy = s[3] / n_inl;
+            s[0] = s[1] = s[2] = s[3] = 0;
             for (int i = tid; i < n_inl; i += RS_THREADS) {
                 const float4 q = pts[sel[i]];
                 s[0] += fabs(q.z - cmx); s[1] += fabs(q.w - cmy); s[2] += fabs(q.x - cMx); s[3] += fabs(q.y - cMy);
             }
             block_sum<4>(s, sh.part, sh.out);
-            const bool ok = !(fabs(s[0]) < DBL_EPSILON || fabs(s[1]) < DBL_EPSILON ||
-                              fabs(s[2]) < DBL_EPSILON || fabs(s[3]) < DBL_EPSILON);
-            if (ok) {
-                const double smx = n_inl / s[0], smy = n_inl / s[1], sMx = n_inl / s[2], sMy = n_inl / s[3];
+            smx = s[0]; smy = s[1]; sMx = s[2]; sMy = s[3];
+        }
+        const bool dlt_ok = !(fabs(smx) < DBL_EPSILON || fabs(smy) < DBL_EPSILON ||
+                              fabs(sMx) < DBL_EPSILON || fabs(sMy) < DBL_EPSILON);
+        if (dlt_ok) {
+            smx = n_inl / smx; smy = n_inl / smy; sMx = n_inl / sMx; sMy = n_inl / sMy;
+            double* LtL = sh.scratch_a;
+            if (exact) {
+                if (tid < 45) {                               // one upper-triangle entry per thread, sequential over points
+                    int j = 0, e = tid;
+                    while (e >= 9 - j) { e -= 9 - j; j++; }
+                    const int k = j + e;
+                    double acc = 0;
+                    for (int i = 0; i < n_inl; i++) {
+                        const float4 q = pts[sel[i]];
+                        const double x = (q.z - cmx) * smx, y = (q.w - cmy) * smy;
+                        const double X = (q.x - cMx) * sMx, Y = (q.y - cMy) * sMy;
+                        const double Lx[9] = { X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x };
+                        const double Ly[9] = { 0, 0, 0, X, Y, 1, -y * X, -y * Y, -y };
+                        acc += Lx[j] * Lx[k] + Ly[j] * Ly[k];
+                    }
+                    LtL[j * 9 + k] = acc; LtL[k * 9 + j] = acc;
+                }
+            } else {
                 double L[45];
                 #pragma unroll
                 for (int k = 0; k < 45; k++) L[k] = 0;
@@ -537,59 +729,75 @@ ransac_finish_kernel(RansacWork w)
                 }
                 block_sum<45>(L, sh.part, sh.out);
                 if (tid == 0) {
-                    double* LtL = sh.scratch_a;
                     int e = 0;
                     for (int j = 0; j < 9; j++)
                         for (int k = j; k < 9; k++) { LtL[j * 9 + k] = L[e]; LtL[k * 9 + j] = L[e]; e++; }
-                    double Hn[9];
-                    dlt_finish(LtL, sh.scratch_v, cMx, cMy, cmx, cmy, sMx, sMy, smx, smy, Hn);
-                    for (int i = 0; i < 9; i++) sh.H[i] = Hn[i];
                 }
-                __syncthreads();
             }
-            // LM with block-evaluated reductions; thread 0 runs the scalar schedule
-            LmState& st = sh.lm;
-            if (tid < 9) st.x[tid] = sh.H[tid];
             __syncthreads();
-            {
+            if (tid < 32) {
+                jacobi9_warp(LtL, sh.scratch_w, sh.scratch_v);
+                if (tid == 0) {
+                    const double invHnorm[9] = { 1. / smx, 0, cmx, 0, 1. / smy, cmy, 0, 0, 1 };
+                    const double Hnorm2[9] = { sMx, 0, -cMx * sMx, 0, sMy, -cMy * sMy, 0, 0, 1 };
+                    double Vl[9], Htemp[9], H0[9];
+                    for (int i = 0; i < 9; i++) Vl[i] = sh.scratch_v[72 + i];
+                    mat3mul(invHnorm, Vl, Htemp);
+                    mat3mul(Htemp, Hnorm2, H0);
+                    const double sc = 1. / H0[8];
+                    for (int i = 0; i < 9; i++) sh.H[i] = H0[i] * sc;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- B.8: LMSolver (9 parameters, 10 iterations); reductions by the block, eigen-solves by warp 0 ----
+        LmState& st = sh.lm;
+        if (tid < 9) st.x[tid] = sh.H[tid];
+        __syncthreads();
+        {
+            double A[81], v[9], rmax;
+            const double S = exact ? lm_eval_exact(pts, sel, n_inl, st.x, true, A, v, &rmax, sh)
+                                   : lm_eval_block(pts, sel, n_inl, st.x, A, v, &rmax, sh);
+            if (tid == 0) {
+                for (int i = 0; i < 81; i++) st.A[i] = A[i];
+                for (int i = 0; i < 9; i++) st.v[i] = v[i];
+                st.S = S; st.rmax = rmax;
+                lm_begin(st);
+            }
+            __syncthreads();
+        }
+        for (;;) {
+            if (tid < 32) lm_step_warp(st, sh);
+            __syncthreads();
+            const double Sd = exact ? lm_eval_exact(pts, sel, n_inl, st.xd, false, nullptr, nullptr, nullptr, sh)
+                                    : lm_eval_block(pts, sel, n_inl, st.xd, nullptr, nullptr, nullptr, sh);
+            if (tid < 32) {
+                const bool acc = lm_update_warp(st, Sd, sh);
+                if (tid == 0) sh.flag = acc ? 1 : 0;
+            }
+            __syncthreads();
+            if (sh.flag) {
+                if (tid < 9) st.x[tid] = st.xd[tid];
+                __syncthreads();
                 double A[81], v[9], rmax;
-                const double S = lm_eval_block(pts, sel, n_inl, st.x, A, v, &rmax, sh);
+                const double S = exact ? lm_eval_exact(pts, sel, n_inl, st.x, true, A, v, &rmax, sh)
+                                       : lm_eval_block(pts, sel, n_inl, st.x, A, v, &rmax, sh);
                 if (tid == 0) {
                     for (int i = 0; i < 81; i++) st.A[i] = A[i];
                     for (int i = 0; i < 9; i++) st.v[i] = v[i];
                     st.S = S; st.rmax = rmax;
-                    lm_begin(st);
                 }
                 __syncthreads();
             }
-            for (;;) {
-                if (tid == 0) lm_step(st, sh.scratch_a, sh.scratch_v);
-                __syncthreads();
-                const double Sd = lm_eval_block(pts, sel, n_inl, st.xd, nullptr, nullptr, nullptr, sh);
-                if (tid == 0) sh.flag = lm_update(st, Sd, sh.scratch_a, sh.scratch_v) ? 1 : 0;
-                __syncthreads();
-                if (sh.flag) {
-                    if (tid < 9) st.x[tid] = st.xd[tid];
-                    __syncthreads();
-                    double A[81], v[9], rmax;
-                    const double S = lm_eval_block(pts, sel, n_inl, st.x, A, v, &rmax, sh);
-                    if (tid == 0) {
-                        for (int i = 0; i < 81; i++) st.A[i] = A[i];
-                        for (int i = 0; i < 9; i++) st.v[i] = v[i];
-                        st.S = S; st.rmax = rmax;
-                    }
-                    __syncthreads();
-                }
-                if (tid == 0) sh.flag = lm_proceed(st, 10) ? 1 : 0;
-                __syncthreads();
-                if (!sh.flag) break;
-            }
-            if (tid == 0) {
-                const double sc = 1. / st.x[8];
-                for (int i = 0; i < 9; i++) sh.H[i] = st.x[i] * sc;
-            }
+            if (tid == 0) sh.flag = lm_proceed(st, 10) ? 1 : 0;
             __syncthreads();
+            if (!sh.flag) break;
         }
+        if (tid == 0) {
+            const double sc = 1. / st.x[8];
+            for (int i = 0; i < 9; i++) sh.H[i] = st.x[i] * sc;
+        }
+        __syncthreads();
         // B.9: returned mask = err(H_final) <= thr^2 over ALL correspondences
         #pragma unroll
         for (int i = 0; i < 8; i++) Hf[i] = (float)sh.H[i];
@@ -625,8 +833,13 @@ int launch_ransac(const RansacWork& w, cudaStream_t st)
     const int warps_per_block = 4;
     for (int rb = 0; rb < w.max_iters; rb += round_len) {
         const int len = w.max_iters - rb < round_len ? w.max_iters - rb : round_len;
-        dim3 grid((len + HYP_THREADS - 1) / HYP_THREADS, w.n_sets);
-        ransac_hyp_kernel<<<grid, HYP_THREADS, HYP_SMEM, st>>>(w, rb);
+        if ((int64_t)len * w.n_sets <= 400000) {              // latency-bound: one warp per hypothesis
+            dim3 grid((len + HYPW_WARPS - 1) / HYPW_WARPS, w.n_sets);
+            ransac_hyp_warp_kernel<<<grid, HYPW_WARPS * 32, 0, st>>>(w, rb);
+        } else {                                              // throughput-bound: one thread per hypothesis
+            dim3 grid((len + HYP_THREADS - 1) / HYP_THREADS, w.n_sets);
+            ransac_hyp_kernel<<<grid, HYP_THREADS, HYP_SMEM, st>>>(w, rb);
+        }
         ransac_select_kernel<<<(w.n_sets + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(w, rb, len);
         launches += 2;
     }
