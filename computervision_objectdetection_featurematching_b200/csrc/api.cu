@@ -123,7 +123,7 @@ struct cvg_ctx {
     DevBuf q_f32, q_b, q_aug, q_norm;                  // raw-query path
     DevBuf t_f32, t_b, t_aug, t_kpt, t_kptoff;         // per-call train path
     DevBuf units, dir, parts, idx, dist, accept;
-    DevBuf pts, starts, counts_n, sample_pos, n_samples, counts, best_iter, best_count, iters_run, niters_cur, sel;
+    DevBuf pts, starts, counts_n, sample_pos, n_samples, counts, best_iter, best_count, iters_run, niters_cur, smp_state, sel;
     DevBuf H, mask, rmask, found, sflags, results, inl_xy, inl_cnt, scales, src, dst;
     BufPool pool;                                      // recycled buffers of freed scene batches
 };
@@ -181,7 +181,7 @@ void cvg_destroy(cvg_ctx* c)
     cudaStreamSynchronize(c->stream);
     DevBuf* bufs[] = { &c->q_f32, &c->q_b, &c->q_aug, &c->q_norm, &c->t_f32, &c->t_b, &c->t_aug, &c->t_kpt, &c->t_kptoff,
                        &c->units, &c->dir, &c->parts, &c->idx, &c->dist, &c->accept, &c->pts, &c->starts, &c->counts_n,
-                       &c->sample_pos, &c->n_samples, &c->counts, &c->best_iter, &c->best_count, &c->iters_run, &c->niters_cur, &c->sel,
+                       &c->sample_pos, &c->n_samples, &c->counts, &c->best_iter, &c->best_count, &c->iters_run, &c->niters_cur, &c->smp_state, &c->sel,
                        &c->H, &c->mask, &c->rmask, &c->found, &c->sflags, &c->results, &c->inl_xy, &c->inl_cnt,
                        &c->scales, &c->src, &c->dst };
     for (DevBuf* b : bufs) b->release();
@@ -366,6 +366,7 @@ static int run_ransac(cvg_ctx* c, const float4* d_pts, const int64_t* d_starts, 
     CU_CHECK(c->best_count.ensure((size_t)n_sets * 4));
     CU_CHECK(c->iters_run.ensure((size_t)n_sets * 4));
     CU_CHECK(c->niters_cur.ensure((size_t)n_sets * 4));
+    CU_CHECK(c->smp_state.ensure((size_t)n_sets * 16));
     CU_CHECK(c->sflags.ensure((size_t)n_sets * 4));
     CU_CHECK(c->found.ensure((size_t)n_sets * 4));
     CU_CHECK(c->H.ensure((size_t)n_sets * 9 * 8));
@@ -383,6 +384,7 @@ static int run_ransac(cvg_ctx* c, const float4* d_pts, const int64_t* d_starts, 
     w.counts = c->counts.as<int32_t>(); w.best_iter = c->best_iter.as<int32_t>();
     w.best_count = c->best_count.as<int32_t>(); w.iters_run = c->iters_run.as<int32_t>();
     w.niters_cur = c->niters_cur.as<int32_t>();
+    w.smp_state = c->smp_state.as<int64_t>();
     w.sel = c->sel.as<int32_t>(); w.H = c->H.as<double>(); w.mask = c->mask.as<uint8_t>();
     w.ransac_mask = want_rmask ? c->rmask.as<uint8_t>() : nullptr;
     w.found = c->found.as<int32_t>(); w.status_flags = c->sflags.as<int32_t>();

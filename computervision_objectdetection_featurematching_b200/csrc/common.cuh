@@ -88,6 +88,7 @@ struct RansacWork {
     int32_t* best_count;        // [P]
     int32_t* iters_run;         // [P]
     int32_t* niters_cur;        // [P] adaptive niters after the rounds scanned so far
+    int64_t* smp_state;         // [P, 2] sampler state between rounds: next draw position, failure run (-1 = finished)
     int32_t* sel;               // [total] compacted inlier indices
     // outputs
     double* H;                  // [P, 9]

@@ -69,18 +69,28 @@ __device__ __forceinline__ int draw_subset(const uint32_t* __restrict__ tab, int
 // the same order, rejected attempts and 10000-attempt limit as the serial loop.
 constexpr int SW = 512;
 constexpr int SW_TAIL = 64;                       // draws staged beyond the window for attempts that start near its end
-constexpr int SW_PER_THREAD = SW / RS_THREADS;    // 4 consecutive window offsets per thread
+constexpr int SMP_THREADS = 512;                  // one window offset per thread
+constexpr int SW_PER_THREAD = SW / SMP_THREADS;
 
-__global__ void __launch_bounds__(RS_THREADS)
-ransac_sample_kernel(RansacWork w)
+// Samples are produced round by round (iterations [round_base, round_end)); the stream position and the
+// running failure count persist in smp_state between rounds, and a set whose adaptive niters already
+// ended before round_base is skipped.
+__global__ void __launch_bounds__(SMP_THREADS)
+ransac_sample_kernel(RansacWork w, int round_base, int round_end)
 {
     const int set = blockIdx.x;
     const int n = w.counts_n[set];
     int32_t* out = w.sample_pos + (size_t)set * w.max_iters;
-    if (threadIdx.x == 0) { w.niters_cur[set] = max(w.max_iters, 1); w.best_iter[set] = -1; w.best_count[set] = 0; }
-    if (n <= 4) {                                   // n < 4: nothing; n == 4: handled by finish kernel
-        if (threadIdx.x == 0) { w.n_samples[set] = 0; w.status_flags[set] = 0; }
-        return;
+    if (round_base == 0) {
+        if (threadIdx.x == 0) {
+            w.niters_cur[set] = max(w.max_iters, 1); w.best_iter[set] = -1; w.best_count[set] = 0;
+            w.n_samples[set] = 0; w.status_flags[set] = 0;
+            w.smp_state[2 * set] = 0; w.smp_state[2 * set + 1] = 0;
+        }
+        if (n <= 4) return;                         // n < 4: nothing; n == 4: handled by finish kernel
+    } else {
+        // finished earlier (getSubset failure / table exhausted), or the adaptive stop is behind us
+        if (n <= 4 || w.smp_state[2 * set + 1] < 0 || w.n_samples[set] < round_base || round_base >= w.niters_cur[set]) return;
     }
     const float4* __restrict__ pts = w.pts + w.starts[set];
     __shared__ float4 spts[SMEM_PTS];
@@ -88,18 +98,19 @@ ransac_sample_kernel(RansacWork w)
     __shared__ int32_t s_draw[SW + SW_TAIL];        // uniform(0,n) of the window's draw positions (-1 past the table)
     __shared__ uint16_t jump[2][SW];
     __shared__ uint8_t reach[SW];
-    __shared__ int s_wsum[RS_THREADS / 32][2];
+    __shared__ int s_wsum[SMP_THREADS / 32][2];
     __shared__ int s_last, s_first_ok, s_last_ok, s_bad;
     const bool staged = n <= SMEM_PTS;
     if (staged)
-        for (int i = threadIdx.x; i < n; i += RS_THREADS) spts[i] = pts[i];
-    int64_t base = 0;
-    int iter = 0, attempts = 0, flags = 0;
+        for (int i = threadIdx.x; i < n; i += SMP_THREADS) spts[i] = pts[i];
+    int64_t base = round_base == 0 ? 0 : w.smp_state[2 * set];
+    int iter = round_base, attempts = round_base == 0 ? 0 : (int)w.smp_state[2 * set + 1], flags = 0;
+    bool finished = false;                          // no further samples will ever come
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const TabGet slow{ w.rng_tab, w.rng_len, (uint32_t)n };
     for (;;) {
         __syncthreads();
-        for (int j = threadIdx.x; j < SW + SW_TAIL; j += RS_THREADS) {
+        for (int j = threadIdx.x; j < SW + SW_TAIL; j += SMP_THREADS) {
             const int64_t pp = base + j;
             s_draw[j] = pp < w.rng_len ? (int32_t)(w.rng_tab[pp] % (uint32_t)n) : -1;
         }
@@ -111,7 +122,7 @@ ransac_sample_kernel(RansacWork w)
         };
         #pragma unroll 1
         for (int k = 0; k < SW_PER_THREAD; k++) {
-            const int o = k * RS_THREADS + threadIdx.x;
+            const int o = k * SMP_THREADS + threadIdx.x;
             int idx[4];
             const int cons = draw_subset_g(get, base + o, idx);
             uint16_t e = 0;
@@ -135,7 +146,7 @@ ransac_sample_kernel(RansacWork w)
         for (int r = 0; r < 7; r++) {                 // reach = { next^i(0) : i < 2^(r+1) }
             #pragma unroll
             for (int k = 0; k < SW_PER_THREAD; k++) {
-                const int o = k * RS_THREADS + threadIdx.x;
+                const int o = k * SMP_THREADS + threadIdx.x;
                 const int j = jump[cur][o];
                 if (reach[o] && j < SW) reach[j] = 1;
                 jump[cur ^ 1][o] = (uint16_t)(j < SW ? jump[cur][j] : SW);
@@ -166,13 +177,13 @@ ransac_sample_kernel(RansacWork w)
         __syncthreads();
         int off_r = 0, off_ok = 0, tot_r = 0, tot_ok = 0;
         #pragma unroll
-        for (int q = 0; q < RS_THREADS / 32; q++) {
+        for (int q = 0; q < SMP_THREADS / 32; q++) {
             if (q < wid) { off_r += s_wsum[q][0]; off_ok += s_wsum[q][1]; }
             tot_r += s_wsum[q][0]; tot_ok += s_wsum[q][1];
         }
         const int excl_r = off_r + pre_r - n_reach, excl_ok = off_ok + pre_ok - n_ok;   // exclusive ranks of this thread
         const int first_ok = s_first_ok, last_ok = s_last_ok, last = s_last;
-        if (s_bad) { flags |= 1; break; }                       // RNG table exhausted
+        if (s_bad) { flags |= 1; finished = true; break; }      // RNG table exhausted
         // failures before the first accepted attempt of this window extend the running failure count
         int fails_head = 0, fails_tail = 0;
         {
@@ -189,27 +200,48 @@ ransac_sample_kernel(RansacWork w)
             if (lane == 0) { s_wsum[wid][0] = h; s_wsum[wid][1] = t; }
             __syncthreads();
             #pragma unroll
-            for (int q = 0; q < RS_THREADS / 32; q++) { fails_head += s_wsum[q][0]; fails_tail += s_wsum[q][1]; }
+            for (int q = 0; q < SMP_THREADS / 32; q++) { fails_head += s_wsum[q][0]; fails_tail += s_wsum[q][1]; }
         }
-        if (attempts + fails_head >= 10000) break;              // getSubset gave up before the next success
+        if (attempts + fails_head >= 10000) { finished = true; break; }   // getSubset gave up before the next success
         // emit accepted attempts as the samples of iterations iter, iter+1, ...
         {
             int r = excl_ok;
             #pragma unroll
             for (int k = 0; k < SW_PER_THREAD; k++)
                 if ((mask_ok >> k) & 1) {
-                    if (iter + r < w.max_iters) out[iter + r] = (int32_t)(base + threadIdx.x * SW_PER_THREAD + k);
+                    if (iter + r < round_end) out[iter + r] = (int32_t)(base + threadIdx.x * SW_PER_THREAD + k);
                     r++;
                 }
         }
         (void)excl_r; (void)tot_r;
+        if (iter + tot_ok >= round_end) {
+            // the round is complete inside this window: resume right after the attempt that produced its last sample
+            const int need = round_end - iter;                       // >= 1 accepted attempts of this window are used
+            __syncthreads();
+            {
+                int r = excl_ok;
+                #pragma unroll
+                for (int k = 0; k < SW_PER_THREAD; k++)
+                    if ((mask_ok >> k) & 1) { if (r == need - 1) s_last = threadIdx.x * SW_PER_THREAD + k; r++; }
+            }
+            __syncthreads();
+            const int lo = s_last;
+            base = base + lo + (info[lo] & 0x7fff);
+            attempts = 0;
+            iter = round_end;
+            break;
+        }
         attempts = tot_ok > 0 ? fails_tail : attempts + fails_head;
-        iter = min(iter + tot_ok, w.max_iters);
-        if (iter >= w.max_iters) break;
+        iter += tot_ok;
         base = base + last + (info[last] & 0x7fff);
-        if (base + SW + SW_TAIL + 64 >= 0x7fffffffLL) { flags |= 1; break; }
+        if (base + SW + SW_TAIL + 64 >= 0x7fffffffLL) { flags |= 1; finished = true; break; }
     }
-    if (threadIdx.x == 0) { w.n_samples[set] = iter; w.status_flags[set] = flags; }
+    if (threadIdx.x == 0) {
+        w.n_samples[set] = iter;
+        if (flags) w.status_flags[set] = flags;
+        w.smp_state[2 * set] = base;
+        w.smp_state[2 * set + 1] = finished ? -1 : attempts;
+    }
 }
 
 // ---- 2. hypothesis kernel: solve + score ------------------------------------------------------------
@@ -815,8 +847,8 @@ ransac_finish_kernel(RansacWork w)
 int launch_ransac(const RansacWork& w, cudaStream_t st)
 {
     if (w.n_sets <= 0) return 0;
-    int launches = 2;
-    ransac_sample_kernel<<<w.n_sets, RS_THREADS, 0, st>>>(w);
+    int launches = 1;
+
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(ransac_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HYP_SMEM);
@@ -833,6 +865,7 @@ int launch_ransac(const RansacWork& w, cudaStream_t st)
     const int warps_per_block = 4;
     for (int rb = 0; rb < w.max_iters; rb += round_len) {
         const int len = w.max_iters - rb < round_len ? w.max_iters - rb : round_len;
+        ransac_sample_kernel<<<w.n_sets, SMP_THREADS, 0, st>>>(w, rb, rb + len);
         if ((int64_t)len * w.n_sets <= 400000) {              // latency-bound: one warp per hypothesis
             dim3 grid((len + HYPW_WARPS - 1) / HYPW_WARPS, w.n_sets);
             ransac_hyp_warp_kernel<<<grid, HYPW_WARPS * 32, 0, st>>>(w, rb);
@@ -841,7 +874,7 @@ int launch_ransac(const RansacWork& w, cudaStream_t st)
             ransac_hyp_kernel<<<grid, HYP_THREADS, HYP_SMEM, st>>>(w, rb);
         }
         ransac_select_kernel<<<(w.n_sets + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(w, rb, len);
-        launches += 2;
+        launches += 3;
     }
     ransac_finish_kernel<<<w.n_sets, RS_THREADS, 0, st>>>(w);
     return launches;
