@@ -5,37 +5,44 @@
 // The accumulator is  acc' = 2 q.t - ||t||^2  (operands prepared by prep.cu; exact for integer
 // descriptors), so the nearest train row maximises acc' and  d^2 = ||q||^2 - acc'.
 //
-// CTA = 320 threads, one CTA per SM, persistent over a static list of units (128 query rows x a run
+// CTA = 576 threads, one CTA per SM, persistent over a static list of units (128 query rows x a run
 // of 256-wide train tiles):
-//   warp 0      TMA producer   : A tile (queries, resident per unit, double-buffered) and a 2-stage
-//                                ring of B tiles (train rows), SWIZZLE_128B, + the 16-column norm
-//                                augmentation (SWIZZLE_32B)
-//   warp 1      MMA issuer     : 8 x tcgen05.mma (M128 N256 K16, bf16 -> fp32) + 1 augmentation MMA per
-//                                tile into one of two 256-column TMEM accumulators; owns TMEM alloc
-//   warps 2-9   epilogue       : tcgen05.ld 32x32b.x32 (thread = query row, 32 train columns per
-//                                load), running top-2 per row kept in registers across the unit, two
-//                                warps per TMEM lane quarter (column halves), merged at unit end
+//   warp 0      TMA producer   : A tile (queries, resident per unit, double-buffered), a 4-stage ring of
+//                                half-K B stages (256 train rows x 64 K, SWIZZLE_128B) and a 2-stage ring of the
+//                                16-column norm augmentation (SWIZZLE_32B)
+//   warp 1      MMA issuer     : per tile 8 x tcgen05.mma (M128 N256 K16, bf16 -> fp32) + 1 augmentation MMA
+//                                into one of two 256-column TMEM accumulators; owns TMEM alloc
+//   warps 2-17  epilogue       : tcgen05.ld 32x32b.x32 (thread = query row, 32 train columns per
+//                                load), running top-2 per row kept in registers across the unit, four
+//                                warps per TMEM lane quarter (64 columns each), merged at unit end
 // Pipelines: a_full/a_empty, b_full/b_empty (TMA <-> MMA), t_full/t_empty (MMA <-> epilogue).
 #include "common.cuh"
 #include <cuda.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace cvg {
 
-constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_WARPS = 16;                                 // 4 per TMEM lane quarter: 64 columns each per tile
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;                // 320
 constexpr uint32_t A_ATOM_BYTES = TILE_M * 128;                   // 128 rows x 64 bf16          16 KB
 constexpr uint32_t A_AUG_BYTES = TILE_M * KAUG * 2;               // 128 rows x 16 bf16           4 KB
 constexpr uint32_t A_BYTES = 2 * A_ATOM_BYTES + A_AUG_BYTES;      //                             36 KB
-constexpr uint32_t B_ATOM_BYTES = TILE_N * 128;                   //                             32 KB
+// The train operand streams through two rings: 4 stages of [256 rows x 64 K] (one SWIZZLE_128B atom, 32 KB,
+// released after its 4 MMAs) and 2 stages of the 16-column augmentation (8 KB).  Splitting K instead of N keeps
+// the MMA at N=256 — an SS-mode MMA re-reads its A slice from shared memory for every instruction, and 64-row
+// slices (measured) are 1.4x slower because they need 192 B/cycle of shared-memory bandwidth — while refills
+// start twice as early as with whole 72 KB tiles, which hides the L2 latency of the next tile.
+constexpr int B_STAGES = 4;                                       // half-K stages
+constexpr uint32_t B_ATOM_BYTES = TILE_N * 128;                   // 256 rows x 64 bf16          32 KB
 constexpr uint32_t B_AUG_BYTES = TILE_N * KAUG * 2;               //                              8 KB
-constexpr uint32_t B_BYTES = 2 * B_ATOM_BYTES + B_AUG_BYTES;      //                             72 KB
 constexpr uint32_t OFF_A = 0;
 constexpr uint32_t OFF_B = 2 * A_BYTES;                           //  72 KB
-constexpr uint32_t OFF_SCRATCH = OFF_B + 2 * B_BYTES;             // 216 KB
-constexpr uint32_t SCRATCH_BYTES = TILE_M * 16;
+constexpr uint32_t OFF_BAUG = OFF_B + B_STAGES * B_ATOM_BYTES;    // 200 KB
+constexpr uint32_t OFF_SCRATCH = OFF_BAUG + 2 * B_AUG_BYTES;      // 216 KB
+constexpr uint32_t SCRATCH_BYTES = 3 * TILE_M * 16;                 // partial top-2 of column parts 1..3 at unit end
 constexpr uint32_t OFF_BAR = OFF_SCRATCH + SCRATCH_BYTES;
-constexpr uint32_t TC_SMEM_BYTES = OFF_BAR + 256 + 1024;          // + alignment slack
+constexpr uint32_t TC_SMEM_BYTES = OFF_BAR + 512 + 1024;          // + alignment slack
 constexpr float ABSENT_BELOW = -5.0e8f;                           // padded train rows carry -2^30
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -131,18 +138,16 @@ __device__ __forceinline__ void top2_scan32(const uint32_t* r, int c0, float& b1
     for (int k = 0; k < 8; k++)
         g[k] = fmaxf(fmaxf(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1])),
                      fmaxf(__uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3])));
-    const float m = fmaxf(fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])), fmaxf(fmaxf(g[4], g[5]), fmaxf(g[6], g[7])));
-    if (m > b2) {
-        #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (g[k] > b2) {
-                #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float v = __uint_as_float(r[4 * k + j]);
-                    if (v > b2) {
-                        if (v > b1) { b2 = b1; i2 = i1; b1 = v; i1 = c0 + 4 * k + j; }
-                        else        { b2 = v; i2 = c0 + 4 * k + j; }
-                    }
+    // no 32-wide pre-test: with 32 rows per warp some row almost always has a candidate in a 32-column chunk
+    #pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (g[k] > b2) {
+            #pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float v = __uint_as_float(r[4 * k + j]);
+                if (v > b2) {
+                    if (v > b1) { b2 = b1; i2 = i1; b1 = v; i1 = c0 + 4 * k + j; }
+                    else        { b2 = v; i2 = c0 + 4 * k + j; }
                 }
             }
         }
@@ -154,25 +159,29 @@ struct TcMaps { CUtensorMap q, qaug, t, taug; };
 __global__ void __launch_bounds__(TC_THREADS, 1)
 match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ qnorm,
                 const MatchUnit* __restrict__ units, int n_units, Top2* __restrict__ parts,
-                const int* __restrict__ skip_if_flag, int* dbg)
+                const int* __restrict__ skip_if_flag, int* dbg, int exp_mode)
 {
+    // exp_mode (experiments only, set through CVG_TC_EXP): bit 0 = epilogue releases the accumulator without
+    // scanning it, bit 1 = the producer re-arms ring stages without issuing the B loads
     if (skip_if_flag && *skip_if_flag != 0) return;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t bar0 = smem_base + OFF_BAR;
     // barrier slots (8 bytes each)
-    const uint32_t a_full = bar0, a_empty = bar0 + 16, b_full = bar0 + 32, b_empty = bar0 + 48;
-    const uint32_t t_full = bar0 + 64, t_empty = bar0 + 80;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 128);
+    const uint32_t a_full = bar0, a_empty = bar0 + 16, t_full = bar0 + 32, t_empty = bar0 + 48;
+    const uint32_t b_full = bar0 + 64, b_empty = bar0 + 64 + 8 * B_STAGES;
+    const uint32_t g_full = bar0 + 64 + 16 * B_STAGES, g_empty = g_full + 16;      // augmentation ring (2 stages)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 64 + 16 * B_STAGES + 48);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; i++) {
             mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1);
-            mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1);
             mbar_init(t_full + 8 * i, 1); mbar_init(t_empty + 8 * i, TC_EPI_WARPS);
+            mbar_init(g_full + 8 * i, 1); mbar_init(g_empty + 8 * i, 1);
         }
+        for (int i = 0; i < B_STAGES; i++) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -188,7 +197,7 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            uint32_t ua = 0, bs = 0;
+            uint32_t ua = 0, bs = 0, tcnt = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x, ua++) {
                 const MatchUnit un = units[u];
                 const uint32_t ab = ua & 1;
@@ -198,15 +207,20 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                 tma_load_2d(sa, &maps.q, 0, un.q_row0, a_full + 8 * ab);
                 tma_load_2d(sa + A_ATOM_BYTES, &maps.q, 64, un.q_row0, a_full + 8 * ab);
                 tma_load_2d(sa + 2 * A_ATOM_BYTES, &maps.qaug, 0, un.q_row0, a_full + 8 * ab);
-                for (int t = 0; t < un.n_tiles; t++, bs++) {
-                    const uint32_t s = bs & 1;
-                    mbar_wait(b_empty + 8 * s, ((bs >> 1) & 1) ^ 1, dbg, 2);
-                    const uint32_t sb = smem_base + OFF_B + s * B_BYTES;
+                for (int t = 0; t < un.n_tiles; t++, tcnt++) {
                     const int row = un.t_row0 + t * TILE_N;
-                    mbar_expect_tx(b_full + 8 * s, B_BYTES);
-                    tma_load_2d(sb, &maps.t, 0, row, b_full + 8 * s);
-                    tma_load_2d(sb + B_ATOM_BYTES, &maps.t, 64, row, b_full + 8 * s);
-                    tma_load_2d(sb + 2 * B_ATOM_BYTES, &maps.taug, 0, row, b_full + 8 * s);
+                    #pragma unroll 1
+                    for (int h = 0; h < 2; h++, bs++) {
+                        const uint32_t s = bs % B_STAGES;
+                        mbar_wait(b_empty + 8 * s, ((bs / B_STAGES) & 1) ^ 1, dbg, 2);
+                        if ((exp_mode & 2) && bs >= B_STAGES) { mbar_arrive(b_full + 8 * s); continue; }
+                        mbar_expect_tx(b_full + 8 * s, B_ATOM_BYTES);
+                        tma_load_2d(smem_base + OFF_B + s * B_ATOM_BYTES, &maps.t, 64 * h, row, b_full + 8 * s);
+                    }
+                    const uint32_t g = tcnt & 1;
+                    mbar_wait(g_empty + 8 * g, ((tcnt >> 1) & 1) ^ 1, dbg, 7);
+                    mbar_expect_tx(g_full + 8 * g, B_AUG_BYTES);
+                    tma_load_2d(smem_base + OFF_BAUG + g * B_AUG_BYTES, &maps.taug, 0, row, g_full + 8 * g);
                 }
             }
         }
@@ -219,22 +233,33 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                 const uint32_t ab = ua & 1;
                 mbar_wait(a_full + 8 * ab, (ua >> 1) & 1, dbg, 3);
                 const uint32_t sa = smem_base + OFF_A + ab * A_BYTES;
-                for (int t = 0; t < n_tiles; t++, bs++, tc++) {
-                    const uint32_t s = bs & 1, acc = tc & 1;
-                    mbar_wait(b_full + 8 * s, (bs >> 1) & 1, dbg, 4);
+                for (int t = 0; t < n_tiles; t++, tc++) {
+                    const uint32_t acc = tc & 1;
                     mbar_wait(t_empty + 8 * acc, ((tc >> 1) & 1) ^ 1, dbg, 5);
-                    tc_fence_after();
-                    const uint32_t sb = smem_base + OFF_B + s * B_BYTES;
                     const uint32_t d_tmem = tmem_base + acc * TILE_N;
-                    #pragma unroll
-                    for (int k = 0; k < DIM / 16; k++) {
-                        const uint32_t koff = (uint32_t)(k & 3) * 32u;       // 16 bf16 = 32 B inside the swizzle atom
-                        const uint64_t da = desc_sw128(sa + (k >> 2) * A_ATOM_BYTES + koff);
-                        const uint64_t db = desc_sw128(sb + (k >> 2) * B_ATOM_BYTES + koff);
-                        tc_mma_bf16(d_tmem, da, db, TC_IDESC, k > 0 ? 1u : 0u);
+                    #pragma unroll 1
+                    for (int h = 0; h < 2; h++, bs++) {
+                        const uint32_t s = bs % B_STAGES;
+                        mbar_wait(b_full + 8 * s, (bs / B_STAGES) & 1, dbg, 4);
+                        tc_fence_after();
+                        const uint32_t sb = smem_base + OFF_B + s * B_ATOM_BYTES;
+                        #pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const uint32_t koff = (uint32_t)k * 32u;             // 16 bf16 = 32 B inside the swizzle atom
+                            const uint64_t da = desc_sw128(sa + h * A_ATOM_BYTES + koff);
+                            const uint64_t db = desc_sw128(sb + koff);
+                            tc_mma_bf16(d_tmem, da, db, TC_IDESC, (h | k) ? 1u : 0u);
+                        }
+                        tc_commit(b_empty + 8 * s);      // ring stage reusable once these MMAs retire
                     }
-                    tc_mma_bf16(d_tmem, desc_sw32(sa + 2 * A_ATOM_BYTES), desc_sw32(sb + 2 * B_ATOM_BYTES), TC_IDESC, 1u);
-                    tc_commit(b_empty + 8 * s);          // smem stage reusable once these MMAs retire
+                    {
+                        const uint32_t g = tc & 1;
+                        mbar_wait(g_full + 8 * g, (tc >> 1) & 1, dbg, 8);
+                        tc_fence_after();
+                        tc_mma_bf16(d_tmem, desc_sw32(sa + 2 * A_ATOM_BYTES), desc_sw32(smem_base + OFF_BAUG + g * B_AUG_BYTES),
+                                    TC_IDESC, 1u);
+                        tc_commit(g_empty + 8 * g);
+                    }
                     tc_commit(t_full + 8 * acc);         // accumulator ready for the epilogue
                 }
                 tc_commit(a_empty + 8 * ab);
@@ -244,7 +269,7 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
         // ===================== epilogue =====================
         const int ew = warp - 2;
         const int quarter = warp & 3;                    // TMEM lanes this warp may touch: 32*(warp%4)..
-        const int half = ew >> 2;                        // which 128 columns of the 256-wide accumulator
+        const int part = ew >> 2;                        // which 64 columns of the 256-wide accumulator
         const int row_in_tile = quarter * 32 + lane;
         Top2* scratch = reinterpret_cast<Top2*>(smem + OFF_SCRATCH);
         uint32_t tc = 0;
@@ -256,16 +281,15 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                 const uint32_t acc = tc & 1;
                 mbar_wait(t_full + 8 * acc, (tc >> 1) & 1, dbg, 6);
                 tc_fence_after();
-                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TILE_N + half * 128;
-                const int col_base = un.t_local0 + t * TILE_N + half * 128;
-                #pragma unroll 1
-                for (int ch = 0; ch < 4; ch += 2) {
+                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TILE_N + part * 64;
+                const int col_base = un.t_local0 + t * TILE_N + part * 64;
+                if (!(exp_mode & 1)) {
                     uint32_t ra[32], rb[32];
-                    tc_ld32(tbase + ch * 32, ra);                 // two loads in flight before the wait
-                    tc_ld32(tbase + ch * 32 + 32, rb);
+                    tc_ld32(tbase, ra);                           // two loads in flight before the wait
+                    tc_ld32(tbase + 32, rb);
                     tc_wait_ld();
-                    top2_scan32(ra, col_base + ch * 32, b1, i1, b2, i2);
-                    top2_scan32(rb, col_base + ch * 32 + 32, b1, i1, b2, i2);
+                    top2_scan32(ra, col_base, b1, i1, b2, i2);
+                    top2_scan32(rb, col_base + 32, b1, i1, b2, i2);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -274,22 +298,25 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
             // ---- unit flush: merge the two column halves, convert to distances, write the partial ----
             if (b1 < ABSENT_BELOW) { i1 = -1; }
             if (b2 < ABSENT_BELOW) { i2 = -1; }
-            if (half == 1) {
+            if (part > 0) {
                 Top2 o; o.d1 = b1; o.i1 = i1; o.d2 = b2; o.i2 = i2;
-                scratch[row_in_tile] = o;
+                scratch[(part - 1) * TILE_M + row_in_tile] = o;
             }
             asm volatile("bar.sync 1, %0;" :: "n"(32 * TC_EPI_WARPS) : "memory");
-            if (half == 0) {
-                const Top2 o = scratch[row_in_tile];
+            if (part == 0) {
                 // larger acc' first, ties -> lower train index
-                const float cv[2] = { o.d1, o.d2 };
-                const int ci[2] = { o.i1, o.i2 };
                 #pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    const float v = cv[k]; const int i = ci[k];
-                    if (i < 0) continue;
-                    if (i1 < 0 || v > b1 || (v == b1 && i < i1)) { b2 = b1; i2 = i1; b1 = v; i1 = i; }
-                    else if (i2 < 0 || v > b2 || (v == b2 && i < i2)) { b2 = v; i2 = i; }
+                for (int pp = 0; pp < 3; pp++) {
+                    const Top2 o = scratch[pp * TILE_M + row_in_tile];
+                    const float cv[2] = { o.d1, o.d2 };
+                    const int ci[2] = { o.i1, o.i2 };
+                    #pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        const float v = cv[k]; const int i = ci[k];
+                        if (i < 0) continue;
+                        if (i1 < 0 || v > b1 || (v == b1 && i < i1)) { b2 = b1; i2 = i1; b1 = v; i1 = i; }
+                        else if (i2 < 0 || v > b2 || (v == b2 && i < i2)) { b2 = v; i2 = i; }
+                    }
                 }
                 const float qn = qnorm[un.q_row0 + row_in_tile];
                 Top2 out;
@@ -363,7 +390,9 @@ int launch_match_tc(const TcOperands& op, const MatchUnit* units, int n_units, T
     if (make_map(&maps.t, op.Tb, op.nt_pad, DIM, 64, TILE_N, CU_TENSOR_MAP_SWIZZLE_128B, err, errlen)) return 1;
     if (make_map(&maps.taug, op.Taug, op.nt_pad, KAUG, KAUG, TILE_N, CU_TENSOR_MAP_SWIZZLE_32B, err, errlen)) return 1;
     const int grid = n_units < n_sms ? n_units : n_sms;
-    match_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, op.qnorm, units, n_units, parts, skip_if_flag, dbg);
+    static int exp_mode = -1;
+    if (exp_mode < 0) { const char* e = getenv("CVG_TC_EXP"); exp_mode = e ? atoi(e) : 0; }
+    match_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, op.qnorm, units, n_units, parts, skip_if_flag, dbg, exp_mode);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(err, errlen, "match_tc_kernel launch: %s", cudaGetErrorString(e));
