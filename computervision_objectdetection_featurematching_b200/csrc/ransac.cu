@@ -866,6 +866,10 @@ int launch_ransac(const RansacWork& w, cudaStream_t st)
     for (int rb = 0; rb < w.max_iters; rb += round_len) {
         const int len = w.max_iters - rb < round_len ? w.max_iters - rb : round_len;
         ransac_sample_kernel<<<w.n_sets, SMP_THREADS, 0, st>>>(w, rb, rb + len);
+        // Measured on B200 (13 350 real pairs = 3.4 M hypotheses per round): thread-per-hypothesis 75 ms per round,
+        // warp-per-hypothesis 167 ms (it spends 32 lanes on one matrix); with 32 sets in flight (8 192 hypotheses
+        // per round) the warp kernel takes 0.3 ms against 1.1 ms.  The switch sits where the chip runs out of
+        // resident warps.
         if ((int64_t)len * w.n_sets <= 400000) {              // latency-bound: one warp per hypothesis
             dim3 grid((len + HYPW_WARPS - 1) / HYPW_WARPS, w.n_sets);
             ransac_hyp_warp_kernel<<<grid, HYPW_WARPS * 32, 0, st>>>(w, rb);
