@@ -50,6 +50,7 @@ SYMBOLS = {
     "cvg_launch_count": (C.c_int64, [_P]),
     "cvg_set_timing": (C.c_int, [_P, C.c_int]),
     "cvg_last_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "cvg_last_hyp_stats": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_uint64)]),
 }
 
 _lib = None

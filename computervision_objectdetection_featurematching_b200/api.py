@@ -176,7 +176,10 @@ class Context:
     def last_timing(self):
         a, b, c = C.c_float(), C.c_float(), C.c_float()
         self.lib.cvg_last_timing(self.handle, C.byref(a), C.byref(b), C.byref(c))
-        return {"match_ms": a.value, "ransac_ms": b.value, "total_ms": c.value}
+        h, n, p = C.c_float(), C.c_int(), C.c_uint64()
+        self.lib.cvg_last_hyp_stats(self.handle, C.byref(h), C.byref(n), C.byref(p))
+        return {"match_ms": a.value, "ransac_ms": b.value, "total_ms": c.value,
+                "hyp_ms": h.value, "hyp_launches": n.value, "scored_points": p.value}
 
     # ---- verify stage --------------------------------------------------------------------------
     def find_homography(self, src, dst, threshold=5.0, max_iters=2000, confidence=0.995, flags=0,

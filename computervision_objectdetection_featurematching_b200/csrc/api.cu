@@ -119,6 +119,9 @@ struct cvg_ctx {
     int last_match_path = 0; int64_t launches = 0;
     int timing = 0; float t_match = 0, t_ransac = 0, t_total = 0;
     cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t hyp_ev[32] = {};                       // brackets of the hypothesis kernel, per round
+    int hyp_rounds = 0; float t_hyp = 0; int hyp_launches = 0; unsigned long long scored_pts = 0;
+    unsigned long long* d_scored = nullptr;
     // scratch
     DevBuf q_f32, q_b, q_aug, q_norm;                  // raw-query path
     DevBuf t_f32, t_b, t_aug, t_kpt, t_kptoff;         // per-call train path
@@ -168,6 +171,9 @@ int cvg_create(cvg_ctx** out, int device, unsigned flags)
     CU_CHECK(cudaMalloc(&c->d_flags, 64 * sizeof(int)));
     CU_CHECK(cudaMemset(c->d_flags, 0, 64 * sizeof(int)));
     for (int i = 0; i < 6; i++) CU_CHECK(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < 32; i++) CU_CHECK(cudaEventCreate(&c->hyp_ev[i]));
+    CU_CHECK(cudaMalloc(&c->d_scored, 8));
+    CU_CHECK(cudaMemset(c->d_scored, 0, 8));
     char err[256];
     if (tc_init(err, sizeof err)) { delete c; return set_err(CVG_ERR_CUDA, "%s", err); }
     *out = c;
@@ -189,12 +195,21 @@ void cvg_destroy(cvg_ctx* c)
     if (c->d_flags) cudaFree(c->d_flags);
     if (c->d_rng) cudaFree(c->d_rng);
     for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 32; i++) if (c->hyp_ev[i]) cudaEventDestroy(c->hyp_ev[i]);
+    if (c->d_scored) cudaFree(c->d_scored);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
 int cvg_last_match_path(const cvg_ctx* c) { return c ? c->last_match_path : 0; }
 void* cvg_stream(const cvg_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int cvg_last_hyp_stats(const cvg_ctx* c, float* hyp_ms, int* hyp_launches, uint64_t* scored_points)
+{
+    if (!c) return CVG_ERR_INVALID;
+    if (hyp_ms) *hyp_ms = c->t_hyp; if (hyp_launches) *hyp_launches = c->hyp_launches;
+    if (scored_points) *scored_points = c->scored_pts;
+    return CVG_OK;
+}
 int64_t cvg_launch_count(const cvg_ctx* c) { return c ? c->launches : 0; }
 int cvg_set_timing(cvg_ctx* c, int enabled) { if (!c) return CVG_ERR_INVALID; c->timing = enabled; return CVG_OK; }
 int cvg_last_timing(const cvg_ctx* c, float* m, float* r, float* t)
@@ -388,7 +403,9 @@ static int run_ransac(cvg_ctx* c, const float4* d_pts, const int64_t* d_starts, 
     w.sel = c->sel.as<int32_t>(); w.H = c->H.as<double>(); w.mask = c->mask.as<uint8_t>();
     w.ransac_mask = want_rmask ? c->rmask.as<uint8_t>() : nullptr;
     w.found = c->found.as<int32_t>(); w.status_flags = c->sflags.as<int32_t>();
-    c->launches += launch_ransac(w, c->stream);
+    w.scored_pts = c->timing ? c->d_scored : nullptr;
+    if (c->timing) CU_CHECK(cudaMemsetAsync(c->d_scored, 0, 8, c->stream));
+    c->launches += launch_ransac(w, c->stream, c->timing ? c->hyp_ev : nullptr, &c->hyp_rounds);
     CU_CHECK(cudaGetLastError());
     return CVG_OK;
 }
@@ -693,6 +710,10 @@ static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, Tra
     if (rc) return rc;
     c->last_match_path = path == 0 ? (flag ? 2 : 1) : path;
     if (c->timing) {
+        c->t_hyp = 0;
+        for (int r = 0; r < c->hyp_rounds; r++) { float t = 0; cudaEventElapsedTime(&t, c->hyp_ev[2 * r], c->hyp_ev[2 * r + 1]); c->t_hyp += t; }
+        c->hyp_launches = c->hyp_rounds;
+        cudaMemcpy(&c->scored_pts, c->d_scored, 8, cudaMemcpyDeviceToHost);
         cudaEventElapsedTime(&c->t_match, c->ev[3], c->ev[4]);      // the match kernel(s) alone
         cudaEventElapsedTime(&c->t_ransac, c->ev[1], c->ev[2]);     // sample + hypothesis + select + finish + gates
         cudaEventElapsedTime(&c->t_total, c->ev[0], c->ev[2]);

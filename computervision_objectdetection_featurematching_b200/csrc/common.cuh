@@ -89,6 +89,7 @@ struct RansacWork {
     int32_t* iters_run;         // [P]
     int32_t* niters_cur;        // [P] adaptive niters after the rounds scanned so far
     int64_t* smp_state;         // [P, 2] sampler state between rounds: next draw position, failure run (-1 = finished)
+    unsigned long long* scored_pts;   // device counter: sum over scored hypotheses of n (or NULL)
     int32_t* sel;               // [total] compacted inlier indices
     // outputs
     double* H;                  // [P, 9]
@@ -97,7 +98,8 @@ struct RansacWork {
     int32_t* found;             // [P]
     int32_t* status_flags;      // [P] bit0: rng table exhausted
 };
-int  launch_ransac(const RansacWork& w, cudaStream_t st);   // returns the number of kernel launches
+// returns the number of kernel launches; hyp_events (optional, 32 events) bracket the hypothesis kernel of each round
+int  launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events = nullptr, int* n_hyp_rounds = nullptr);
 
 // detect glue (ransac.cu)
 struct GateWork {

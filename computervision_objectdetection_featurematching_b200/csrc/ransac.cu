@@ -313,6 +313,10 @@ ransac_hyp_kernel(RansacWork w, int round_base)
         }
     }
     if (active) w.counts[(size_t)set * w.max_iters + iter] = valid ? good : -1;
+    if (w.scored_pts) {                                  // algorithmic traffic of the scoring: one float4 per (hypothesis, point)
+        const unsigned bal = __ballot_sync(0xffffffffu, active && valid);
+        if ((threadIdx.x & 31) == 0 && bal) atomicAdd(w.scored_pts, (unsigned long long)__popc(bal) * (unsigned long long)n);
+    }
 }
 
 // Warp-per-hypothesis variant, used when a round holds too few hypotheses to hide the latency of
@@ -357,7 +361,10 @@ ransac_hyp_warp_kernel(RansacWork w, int round_base)
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         good = cnt;
     }
-    if (lane == 0) w.counts[(size_t)set * w.max_iters + iter] = good;
+    if (lane == 0) {
+        w.counts[(size_t)set * w.max_iters + iter] = good;
+        if (w.scored_pts && valid) atomicAdd(w.scored_pts, (unsigned long long)n);
+    }
 }
 
 // ---- 3. select kernel: the serial scan of RANSACPointSetRegistrator::run --------------------------
@@ -844,8 +851,9 @@ ransac_finish_kernel(RansacWork w)
     if (tid == 0) w.found[set] = 1;
 }
 
-int launch_ransac(const RansacWork& w, cudaStream_t st)
+int launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events, int* n_hyp_rounds)
 {
+    if (n_hyp_rounds) *n_hyp_rounds = 0;
     if (w.n_sets <= 0) return 0;
     int launches = 1;
 
@@ -866,6 +874,9 @@ int launch_ransac(const RansacWork& w, cudaStream_t st)
     for (int rb = 0; rb < w.max_iters; rb += round_len) {
         const int len = w.max_iters - rb < round_len ? w.max_iters - rb : round_len;
         ransac_sample_kernel<<<w.n_sets, SMP_THREADS, 0, st>>>(w, rb, rb + len);
+        const int round = rb / round_len;
+        const bool timed = hyp_events != nullptr && round < 16;
+        if (timed) cudaEventRecord(hyp_events[2 * round], st);
         // Measured on B200 (13 350 real pairs = 3.4 M hypotheses per round): thread-per-hypothesis 75 ms per round,
         // warp-per-hypothesis 167 ms (it spends 32 lanes on one matrix); with 32 sets in flight (8 192 hypotheses
         // per round) the warp kernel takes 0.3 ms against 1.1 ms.  The switch sits where the chip runs out of
@@ -877,6 +888,7 @@ int launch_ransac(const RansacWork& w, cudaStream_t st)
             dim3 grid((len + HYP_THREADS - 1) / HYP_THREADS, w.n_sets);
             ransac_hyp_kernel<<<grid, HYP_THREADS, HYP_SMEM, st>>>(w, rb);
         }
+        if (timed) { cudaEventRecord(hyp_events[2 * round + 1], st); *n_hyp_rounds = round + 1; }
         ransac_select_kernel<<<(w.n_sets + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(w, rb, len);
         launches += 3;
     }

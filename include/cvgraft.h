@@ -194,6 +194,10 @@ int64_t cvg_launch_count(const cvg_ctx* ctx);
  * verify-stage kernels, total_ms = first match launch to last gate launch. */
 int  cvg_set_timing(cvg_ctx* ctx, int enabled);
 int  cvg_last_timing(const cvg_ctx* ctx, float* match_ms, float* ransac_ms, float* total_ms);
+/* Verify-stage detail of the last fused call (timing enabled): summed device time of the hypothesis
+ * kernel launches, their number, and the number of (hypothesis, correspondence) pairs they scored —
+ * 16 bytes each is the algorithmic traffic of the scoring. */
+int  cvg_last_hyp_stats(const cvg_ctx* ctx, float* hyp_ms, int* hyp_launches, uint64_t* scored_points);
 
 #ifdef __cplusplus
 }

@@ -273,3 +273,29 @@ def test_detect_scenes_resident_equals_per_scene_calls(ctx, feats, gpairs):
     assert np.array_equal(res["status"], gpairs["status"].astype(np.int32))
     assert np.array_equal(res["n_inliers"][gpairs["status"] == 0], gpairs["n_inliers"][gpairs["status"] == 0])
     scenes.free(); models.free()
+
+
+def test_full_dataset_13350_pairs_vs_cv2(ctx):
+    """The reference's whole loop nest (30 images x 5 scales x 89 views, src/TestsDetector.cpp:38,58,99-100) from the
+    feature cache (tools/build_feature_cache.py) against cv2 4.13.0's results for the same pairs
+    (tests/golden/full_dataset_cv2.npz, written by tools/full_dataset_replay.py --cv2)."""
+    import os
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    cache = os.path.join(root, "data_cache", "features_full.npz")
+    if not os.path.exists(cache):
+        pytest.skip("feature cache not built (needs the reference data + cv2: python __graft_entry__.py)")
+    Z = np.load(cache)
+    G = np.load(os.path.join(root, "tests", "golden", "full_dataset_cv2.npz"))
+    so = Z["scene_offsets"]
+    models = ctx.upload_models(Z["model_desc"].astype(np.float32), Z["model_kpt"], Z["view_offsets"], Z["view_model"])
+    scenes = ctx.upload_scenes(Z["scene_desc"].astype(np.float32), Z["scene_kpt"], so)
+    res = ctx.detect_scenes(models, scenes, scales=np.tile(Z["scales"], (len(so) - 1) // 5))
+    assert res.shape == G["status"].shape == (150, 89)
+    assert np.array_equal(res["status"], G["status"].astype(np.int32))           # 13 350 / 13 350 gate decisions
+    assert np.array_equal(res["n_good"], G["n_good"])
+    has_h = np.isin(G["status"], (0, 3, 4))
+    assert np.array_equal(res["n_inliers"][has_h], G["n_inliers"][has_h])
+    rel = np.abs(res["H"][has_h] - G["H"][has_h]) / np.maximum(np.abs(G["H"][has_h]), 1e-12)
+    assert rel.max() < 1e-5
+    assert np.bincount(res["status"].ravel(), minlength=5).tolist() == [1308, 83, 116, 1182, 10661]   # SURVEY section 6
+    scenes.free(); models.free()
