@@ -254,4 +254,195 @@ __device__ __forceinline__ bool run_kernel4_warp(const float* ms1, const float* 
     return true;
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// 8-lane groups: four matrices per warp share one instruction stream.  The scalar chain of a rotation
+// (five divisions, two square roots — ~230 of the ~360 warp instructions of jacobi9_warp) then serves
+// four matrices at once, which is what matters when the chip is full of hypotheses (issue-bound) rather
+// than waiting on one matrix (latency-bound, jacobi9_warp).  Lane = 8*g + j; every group owns its A, W,
+// V in shared memory.  `live` is group-uniform; groups that converged (or never had a matrix) idle
+// through the remaining rotations of their warp.  Bit-identical to jacobi<9>.
+__device__ __forceinline__ void g8_argmax_first(double& val, int& key)
+{
+    #pragma unroll
+    for (int m = 4; m > 0; m >>= 1) {
+        const double ov = shfl_xor_d(val, m);
+        const int ok = __shfl_xor_sync(0xffffffffu, key, m);
+        if (ov > val || (ov == val && ok < key)) { val = ov; key = ok; }
+    }
+}
+
+__device__ __forceinline__ void g8_rot_a(double* A, int i, int k, int l, double c, double s)
+{
+    double* a; double* b;
+    if (i < k)      { a = &A[9 * i + k]; b = &A[9 * i + l]; }
+    else if (i < l) { if (i == k) return; a = &A[9 * k + i]; b = &A[9 * i + l]; }
+    else            { if (i == l) return; a = &A[9 * k + i]; b = &A[9 * l + i]; }
+    const double a0 = *a, b0 = *b;
+    *a = a0 * c - b0 * s;
+    *b = a0 * s + b0 * c;
+}
+
+__device__ __forceinline__ void g8_rot_v(double* V, int i, int k, int l, double c, double s)
+{
+    double* a = &V[9 * k + i]; double* b = &V[9 * l + i];
+    const double a0 = *a, b0 = *b;
+    *a = a0 * c - b0 * s;
+    *b = a0 * s + b0 * c;
+}
+
+__device__ __noinline__ void jacobi9_g8(double* A, double* W, double* V, bool live)
+{
+    const int lane = threadIdx.x & 31, j = lane & 7;
+    const double eps = DBL_EPSILON;
+    int myR = 0, myC = 0;          // lane j holds indR[j] (rows 0..7) and indC[j+1] (columns 1..8)
+    if (live) {
+        for (int e = j; e < 81; e += 8) V[e] = (e / 9 == e % 9) ? 1.0 : 0.0;
+        W[j] = A[10 * j];
+        if (j == 0) W[8] = A[80];
+        {
+            int m = j + 1; double mv = fabs(A[9 * j + m]);
+            for (int i = j + 2; i < 9; i++) { const double val = fabs(A[9 * j + i]); if (mv < val) { mv = val; m = i; } }
+            myR = m;
+        }
+        {
+            const int cc = j + 1; int m = 0; double mv = fabs(A[cc]);
+            for (int i = 1; i < cc; i++) { const double val = fabs(A[9 * i + cc]); if (mv < val) { mv = val; m = i; } }
+            myC = m;
+        }
+    }
+    __syncwarp();
+    bool done = !live;
+    for (int iters = 0; iters < 9 * 9 * 30; iters++) {
+        // ---- pivot: serial scan order = rows 0..7 (order index j), then columns 1..8 (order index 8 + j)
+        double val = -1.0; int key = j;
+        if (!done) {
+            const double va = fabs(A[9 * j + myR]), vb = fabs(A[9 * myC + (j + 1)]);
+            val = va;
+            if (vb > va) { val = vb; key = 8 + j; }
+        }
+        g8_argmax_first(val, key);
+        const int src = (lane & ~7) | (key & 7);
+        const bool is_col = key >= 8;
+        const int k = __shfl_sync(0xffffffffu, is_col ? myC : j, src);
+        const int l = __shfl_sync(0xffffffffu, is_col ? j + 1 : myR, src);
+        double p = 0;
+        if (!done) { p = A[9 * k + l]; if (fabs(p) <= eps) done = true; }
+        if (__all_sync(0xffffffffu, done)) break;
+        double c = 0, s = 0, t = 0;
+        if (!done) {
+            const double y = (W[l] - W[k]) * 0.5;
+            t = fabs(y) + cv_hypot(p, y);
+            s = cv_hypot(p, t);
+            c = t / s;
+            s = p / s; t = (p / t) * p;
+            if (y < 0) { s = -s; t = -t; }
+        }
+        __syncwarp();
+        if (!done) {
+            if (j == 0) { A[9 * k + l] = 0; W[k] -= t; W[l] += t; }
+            g8_rot_a(A, j, k, l, c, s);
+            g8_rot_v(V, j, k, l, c, s);
+            if (j == 0) g8_rot_a(A, 8, k, l, c, s);
+            if (j == 1) g8_rot_v(V, 8, k, l, c, s);
+        }
+        __syncwarp();
+        // ---- refresh indR[k], indR[l], indC[k], indC[l]
+        int r[4];
+        #pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int idx = (q & 1) ? l : k;
+            double v2 = -1.0; int cand = 99;
+            if (!done) {
+                if (q < 2) { const int i = idx + 1 + j; if (i < 9) { v2 = fabs(A[9 * idx + i]); cand = i; } }
+                else       { const int i = j;           if (i < idx) { v2 = fabs(A[9 * i + idx]); cand = i; } }
+            }
+            g8_argmax_first(v2, cand);
+            r[q] = cand;
+        }
+        if (!done) {
+            if (j == k) myR = r[0];                    // k < l <= 8, so row k always has an indR
+            if (j == l && l < 8) myR = r[1];
+            if (k > 0 && j == k - 1) myC = r[2];
+            if (j == l - 1) myC = r[3];                // l >= 1
+        }
+    }
+    __syncwarp();
+    // ---- selection sort, descending, rows of V follow
+    for (int k = 0; k < 8; k++) {
+        double val = -INFINITY; int m = 99;
+        if (live) {
+            if (j >= k) { val = W[j]; m = j; }
+            if (j == 7) { const double w8 = W[8]; if (w8 > val) { val = w8; m = 8; } }
+        }
+        g8_argmax_first(val, m);
+        if (live && m != k) {
+            if (j == 0) { const double tmp = W[m]; W[m] = W[k]; W[k] = tmp; }
+            { const double tmp = V[9 * m + j]; V[9 * m + j] = V[9 * k + j]; V[9 * k + j] = tmp; }
+            if (j == 1) { const double tmp = V[9 * m + 8]; V[9 * m + 8] = V[9 * k + 8]; V[9 * k + 8] = tmp; }
+        }
+        __syncwarp();
+    }
+}
+
+// runKernel for a 4-point sample by one 8-lane group (see run_kernel4_warp).  smem: this group's 243 doubles.
+// Returns the group's verdict; H valid in every lane of a group that returned true.
+__device__ __forceinline__ bool run_kernel4_g8(const float* ms1, const float* ms2, double* H, double* smem, bool live)
+{
+    const int j = threadIdx.x & 7;
+    double* LtL = smem; double* V = smem + 81; double* W = smem + 162; double* L = smem + 171;   // L: [4][2][9]
+    double cMx = 0, cMy = 0, cmx = 0, cmy = 0, sMx = 0, sMy = 0, smx = 0, smy = 0;
+    #pragma unroll
+    for (int i = 0; i < 4; i++) { cmx += ms2[2 * i]; cmy += ms2[2 * i + 1]; cMx += ms1[2 * i]; cMy += ms1[2 * i + 1]; }
+    cmx /= 4; cmy /= 4; cMx /= 4; cMy /= 4;
+    #pragma unroll
+    for (int i = 0; i < 4; i++) {
+        smx += fabs(ms2[2 * i] - cmx); smy += fabs(ms2[2 * i + 1] - cmy);
+        sMx += fabs(ms1[2 * i] - cMx); sMy += fabs(ms1[2 * i + 1] - cMy);
+    }
+    const bool ok = live && !(fabs(smx) < DBL_EPSILON || fabs(smy) < DBL_EPSILON ||
+                              fabs(sMx) < DBL_EPSILON || fabs(sMy) < DBL_EPSILON);
+    if (ok) {
+        smx = 4 / smx; smy = 4 / smy; sMx = 4 / sMx; sMy = 4 / sMy;
+        if (j < 4) {
+            const int i = j;
+            const double x = (ms2[2 * i] - cmx) * smx, y = (ms2[2 * i + 1] - cmy) * smy;
+            const double X = (ms1[2 * i] - cMx) * sMx, Y = (ms1[2 * i + 1] - cMy) * sMy;
+            double* Lx = L + i * 18; double* Ly = Lx + 9;
+            Lx[0] = X; Lx[1] = Y; Lx[2] = 1; Lx[3] = 0; Lx[4] = 0; Lx[5] = 0; Lx[6] = -x * X; Lx[7] = -x * Y; Lx[8] = -x;
+            Ly[0] = 0; Ly[1] = 0; Ly[2] = 0; Ly[3] = X; Ly[4] = Y; Ly[5] = 1; Ly[6] = -y * X; Ly[7] = -y * Y; Ly[8] = -y;
+        }
+    }
+    __syncwarp();
+    if (ok) {
+        for (int e = j; e < 81; e += 8) {
+            int a = e / 9, b = e % 9;
+            if (b < a) { const int tmp = a; a = b; b = tmp; }
+            double s = 0;
+            #pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const double* Lx = L + i * 18; const double* Ly = Lx + 9;
+                s += Lx[a] * Lx[b] + Ly[a] * Ly[b];
+            }
+            LtL[e] = s;
+        }
+    }
+    __syncwarp();
+    jacobi9_g8(LtL, W, V, ok);
+    if (ok) {
+        const double invHnorm[9] = { 1. / smx, 0, cmx, 0, 1. / smy, cmy, 0, 0, 1 };
+        const double Hnorm2[9] = { sMx, 0, -cMx * sMx, 0, sMy, -cMy * sMy, 0, 0, 1 };
+        double Vl[9], Htemp[9], H0[9];
+        #pragma unroll
+        for (int i = 0; i < 9; i++) Vl[i] = V[72 + i];
+        mat3mul(invHnorm, Vl, Htemp);
+        mat3mul(Htemp, Hnorm2, H0);
+        const double sc = 1. / H0[8];
+        #pragma unroll
+        for (int i = 0; i < 9; i++) H[i] = H0[i] * sc;
+    }
+    __syncwarp();
+    return ok;
+}
+
 }  // namespace cvg

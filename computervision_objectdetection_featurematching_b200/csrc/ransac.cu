@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "homography_math.cuh"
 #include "jacobi_warp.cuh"
+#include <stdlib.h>
 
 namespace cvg {
 
@@ -363,6 +364,53 @@ ransac_hyp_warp_kernel(RansacWork w, int round_base)
     }
     if (lane == 0) {
         w.counts[(size_t)set * w.max_iters + iter] = good;
+        if (w.scored_pts && valid) atomicAdd(w.scored_pts, (unsigned long long)n);
+    }
+}
+
+// Four hypotheses per warp (8-lane groups, jacobi9_g8): the variant for rounds that fill the chip, where
+// the hypothesis kernel is bound by instruction issue and the rotation's scalar chain should be shared.
+constexpr int HYPG_WARPS = 8;
+constexpr int HYPG_SMEM = HYPG_WARPS * 4 * HYPW_SMEM_D * 8;      // 62 KB
+
+__global__ void __launch_bounds__(HYPG_WARPS * 32)
+ransac_hyp_g8_kernel(RansacWork w, int round_base)
+{
+    extern __shared__ double g8_smem[];
+    const int set = blockIdx.y;
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, j = lane & 7;
+    const int n = w.counts_n[set];
+    const int n_samples = w.n_samples[set];
+    const int iter = round_base + (blockIdx.x * HYPG_WARPS + wid) * 4 + g;
+    const bool live = iter < n_samples && iter < w.niters_cur[set];
+    if (!__any_sync(0xffffffffu, live)) return;
+    const float4* __restrict__ pts = w.pts + w.starts[set];
+    float ms1[8], ms2[8];
+    #pragma unroll
+    for (int i = 0; i < 8; i++) { ms1[i] = 0.f; ms2[i] = 0.f; }
+    if (live) {
+        int idx[4];
+        draw_subset(w.rng_tab, w.rng_len, w.sample_pos[(size_t)set * w.max_iters + iter], (uint32_t)n, idx);
+        #pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float4 q = pts[idx[i]];
+            ms1[2 * i] = q.x; ms1[2 * i + 1] = q.y; ms2[2 * i] = q.z; ms2[2 * i + 1] = q.w;
+        }
+    }
+    double H[9];
+    const bool valid = run_kernel4_g8(ms1, ms2, H, g8_smem + (size_t)(wid * 4 + g) * HYPW_SMEM_D, live);
+    float Hf[8];
+    #pragma unroll
+    for (int i = 0; i < 8; i++) Hf[i] = valid ? (float)H[i] : 0.f;
+    int cnt = 0;
+    for (int i = j; i < n; i += 8) {                              // the four groups read the same 128 B per step
+        const float4 q = pts[i];
+        cnt += reproj_err(Hf, q.x, q.y, q.z, q.w) <= w.thr2 ? 1 : 0;
+    }
+    #pragma unroll
+    for (int o = 4; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (live && j == 0) {
+        w.counts[(size_t)set * w.max_iters + iter] = valid ? cnt : -1;
         if (w.scored_pts && valid) atomicAdd(w.scored_pts, (unsigned long long)n);
     }
 }
@@ -860,6 +908,7 @@ int launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events,
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(ransac_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HYP_SMEM);
+        cudaFuncSetAttribute(ransac_hyp_g8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HYPG_SMEM);
         attr_set = true;
     }
     // hypotheses are solved and scored in rounds; after each round the serial selection scan advances, so
@@ -881,9 +930,15 @@ int launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events,
         // warp-per-hypothesis 167 ms (it spends 32 lanes on one matrix); with 32 sets in flight (8 192 hypotheses
         // per round) the warp kernel takes 0.3 ms against 1.1 ms.  The switch sits where the chip runs out of
         // resident warps.
-        if ((int64_t)len * w.n_sets <= 400000) {              // latency-bound: one warp per hypothesis
+        static const int hyp_mode = getenv("CVG_HYP_MODE") ? atoi(getenv("CVG_HYP_MODE")) : 0;   // experiments: 1 warp, 2 g8, 3 thread
+        const int64_t hyps = (int64_t)len * w.n_sets;
+        const int mode = hyp_mode ? hyp_mode : (hyps <= 4096 ? 1 : hyps <= 400000 ? 2 : 3);
+        if (mode == 1) {                                       // a handful of sets: latency of one matrix counts
             dim3 grid((len + HYPW_WARPS - 1) / HYPW_WARPS, w.n_sets);
             ransac_hyp_warp_kernel<<<grid, HYPW_WARPS * 32, 0, st>>>(w, rb);
+        } else if (mode == 2) {                                // the chip is full of warps: four matrices per warp
+            dim3 grid((len + HYPG_WARPS * 4 - 1) / (HYPG_WARPS * 4), w.n_sets);
+            ransac_hyp_g8_kernel<<<grid, HYPG_WARPS * 32, HYPG_SMEM, st>>>(w, rb);
         } else {                                              // throughput-bound: one thread per hypothesis
             dim3 grid((len + HYP_THREADS - 1) / HYP_THREADS, w.n_sets);
             ransac_hyp_kernel<<<grid, HYP_THREADS, HYP_SMEM, st>>>(w, rb);
@@ -962,12 +1017,14 @@ void launch_gates(const GateWork& g, cudaStream_t st)
 }
 
 // ---- compaction of ratio-test survivors into correspondences: reference src/TestsDetector.cpp:62-72 --
-// one warp per (segment, view) pair; output order = query order
-__global__ void compact_kernel(CompactWork c)
+// one block per (segment, view) pair; output order = query order (block-wide ordered compaction)
+constexpr int CMP_THREADS = 256;
+
+__global__ void __launch_bounds__(CMP_THREADS)
+compact_kernel(CompactWork c)
 {
-    const int pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (pair >= c.n_segments * c.n_views) return;
+    const int pair = blockIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int seg = pair / c.n_views, view = pair % c.n_views;
     const int r0 = c.view_offsets[view], r1 = c.view_offsets[view + 1];
     const int64_t start = (int64_t)seg * c.n_query + r0;
@@ -976,26 +1033,35 @@ __global__ void compact_kernel(CompactWork c)
     const float2* mk = reinterpret_cast<const float2*>(c.model_kpt);
     const float2* sk = reinterpret_cast<const float2*>(c.scene_kpt) + c.seg_kpt_offsets[seg];
     float4* out = c.pts + start;
-    int written = 0;
-    for (int base = r0; base < r1; base += 32) {
-        const int q = base + lane;
+    __shared__ int s_wcnt[CMP_THREADS / 32];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int base = r0; base < r1; base += CMP_THREADS) {
+        const int q = base + threadIdx.x;
         const bool in = q < r1 && acc[q];
         const unsigned bal = __ballot_sync(0xffffffffu, in);
+        if (lane == 0) s_wcnt[wid] = __popc(bal);
+        __syncthreads();
+        int off = s_base;
+        for (int k = 0; k < wid; k++) off += s_wcnt[k];
         if (in) {
             const float2 a = mk[q];                           // model.keypoints[i][queryIdx].pt   :68
             const float2 b = sk[idx[2 * q]];                  // sceneKP[trainIdx].pt              :69
-            out[written + __popc(bal & ((1u << lane) - 1))] = make_float4(a.x, a.y, b.x, b.y);
+            out[off + __popc(bal & ((1u << lane) - 1))] = make_float4(a.x, a.y, b.x, b.y);
         }
-        written += __popc(bal);
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < CMP_THREADS / 32; k++) t += s_wcnt[k]; s_base += t; }
+        __syncthreads();
     }
-    if (lane == 0) { c.starts[pair] = start; c.n_good[pair] = written; }
+    if (threadIdx.x == 0) { c.starts[pair] = start; c.n_good[pair] = s_base; }
 }
 
 void launch_compact(const CompactWork& c, cudaStream_t st)
 {
     const int n = c.n_segments * c.n_views;
     if (n <= 0) return;
-    compact_kernel<<<(n + 3) / 4, 128, 0, st>>>(c);
+    compact_kernel<<<n, CMP_THREADS, 0, st>>>(c);
 }
 
 }  // namespace cvg
