@@ -926,13 +926,13 @@ int launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events,
         const int round = rb / round_len;
         const bool timed = hyp_events != nullptr && round < 16;
         if (timed) cudaEventRecord(hyp_events[2 * round], st);
-        // Measured on B200 (13 350 real pairs = 3.4 M hypotheses per round): thread-per-hypothesis 75 ms per round,
-        // warp-per-hypothesis 167 ms (it spends 32 lanes on one matrix); with 32 sets in flight (8 192 hypotheses
-        // per round) the warp kernel takes 0.3 ms against 1.1 ms.  The switch sits where the chip runs out of
-        // resident warps.
+        // Measured on B200.  13 350 real pairs (3.4 M hypotheses per round), whole verify stage: thread-per-
+        // hypothesis 612 ms, warp-per-hypothesis 1436 ms, four-per-warp 498 ms.  64 synthetic 8k x 8k pairs
+        // (16 384 hypotheses per round), hypothesis kernels per step: warp 4.15 ms, four-per-warp 2.41 ms.
+        // One set alone (256 hypotheses): warp 0.30 ms, thread 1.1 ms.
         static const int hyp_mode = getenv("CVG_HYP_MODE") ? atoi(getenv("CVG_HYP_MODE")) : 0;   // experiments: 1 warp, 2 g8, 3 thread
         const int64_t hyps = (int64_t)len * w.n_sets;
-        const int mode = hyp_mode ? hyp_mode : (hyps <= 4096 ? 1 : hyps <= 400000 ? 2 : 3);
+        const int mode = hyp_mode ? hyp_mode : (hyps <= 4096 ? 1 : 2);
         if (mode == 1) {                                       // a handful of sets: latency of one matrix counts
             dim3 grid((len + HYPW_WARPS - 1) / HYPW_WARPS, w.n_sets);
             ransac_hyp_warp_kernel<<<grid, HYPW_WARPS * 32, 0, st>>>(w, rb);
