@@ -285,7 +285,7 @@ def run_cvgraft(args):
                 "clocks": clk,
                 # dominant kernel of the step by device time: the RANSAC hypothesis kernel (DLT solve + scoring).
                 # scoring is a streaming scan, 16 B per (hypothesis, correspondence), HBM roofline.
-                "roofline": {"kernel": "ransac_hyp_warp_kernel (4-pt DLT + inlier scoring)", "bound": "hbm",
+                "roofline": {"kernel": "ransac_hyp_g8_kernel (4-pt DLT + inlier scoring; 8 launches per step, rounds past the adaptive stop exit early)", "bound": "hbm",
                              "achieved": 16.0 * sum(scored) / max(sum(hyp_ms) * 1e-3, 1e-12) / 1e9, "peak": peaks["hbm"],
                              "unit": "GB/s",
                              "frac": 16.0 * sum(scored) / max(sum(hyp_ms) * 1e-3, 1e-12) / 1e9 / peaks["hbm"],
