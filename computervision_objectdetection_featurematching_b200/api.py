@@ -80,9 +80,15 @@ class Models:
 
 
 class Scenes:
-    def __init__(self, ctx, handle, offsets):
+    def __init__(self, ctx, handle, offsets, keep=None):
         self.ctx, self.handle = ctx, handle
         self.offsets = np.asarray(offsets, np.int64)
+        self._keep = keep                      # host arrays an asynchronous upload is still reading
+
+    def wait(self):
+        """Block until an asynchronous upload has finished (optional: detect_scenes orders itself after it)."""
+        self.ctx._check(self.ctx.lib.cvg_scenes_wait(self.ctx.handle, self.handle))
+        self._keep = None
 
     @property
     def n_scenes(self):
@@ -136,6 +142,16 @@ class Context:
         h = C.c_void_p()
         self._check(self.lib.cvg_scenes_upload(self.handle, _ptr(d), _ptr(k), _ptr(off), len(off) - 1, C.byref(h)))
         return Scenes(self, h, off)
+
+    def upload_scenes_async(self, descriptors, keypoints_xy, offsets):
+        """Streaming upload on the context's copy stream: returns at once, overlaps a running detect_scenes.
+        Pass pinned arrays for a truly asynchronous copy; they are kept alive by the returned handle."""
+        d = _f32(descriptors, 128)
+        k = _f32(keypoints_xy, 2) if keypoints_xy is not None else None
+        off = np.ascontiguousarray(offsets, np.int64)
+        h = C.c_void_p()
+        self._check(self.lib.cvg_scenes_upload_async(self.handle, _ptr(d), _ptr(k), _ptr(off), len(off) - 1, C.byref(h)))
+        return Scenes(self, h, off, keep=(d, k, off))
 
     # ---- match stage ---------------------------------------------------------------------------
     def match_knn2(self, query, train, ratio=0.9, view=-1):

@@ -105,6 +105,8 @@ struct cvg_models {
 struct cvg_scenes {
     TrainSet ts;
     DevBuf f32, b, aug, kpt, kptoff;
+    int* d_flag = nullptr;             // non-integer flag of this batch (tail of kptoff)
+    cudaEvent_t ready = nullptr;       // set by cvg_scenes_upload_async: upload + conversion finished
     // cached match plan for a given model set
     const cvg_models* plan_models = nullptr;
     int plan_units = 0, plan_slots = 0;
@@ -114,6 +116,7 @@ struct cvg_scenes {
 struct cvg_ctx {
     int device = 0; unsigned flags = 0; int n_sms = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;                // uploads of cvg_scenes_upload_async (overlap with compute)
     int* d_flags = nullptr;            // [0] train nonint, [1] query nonint, [8..16) kernel debug words
     uint32_t* d_rng = nullptr; int64_t rng_len = 0;
     int last_match_path = 0; int64_t launches = 0;
@@ -129,7 +132,35 @@ struct cvg_ctx {
     DevBuf pts, starts, counts_n, sample_pos, n_samples, counts, best_iter, best_count, iters_run, niters_cur, smp_state, sel;
     DevBuf H, mask, rmask, found, sflags, results, inl_xy, inl_cnt, scales, src, dst;
     BufPool pool;                                      // recycled buffers of freed scene batches
+    // Small host->device parameter blocks of the fused path go through a mapped pinned staging area read by a
+    // copy kernel, not through cudaMemcpyAsync: the H2D copy engine may be busy for milliseconds with the next
+    // scene batch (cvg_scenes_upload_async) and would hold the compute stream behind it.
+    uint8_t* stage_h = nullptr; uint8_t* stage_d = nullptr; size_t stage_cap = 0, stage_used = 0; bool stage_fallback = false;
 };
+
+__global__ void stage_copy_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n16)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+// dst must be 16-byte aligned device memory with room for bytes rounded up to 16.
+static cudaError_t h2d_small(cvg_ctx* c, void* dst, const void* src, size_t bytes)
+{
+    const size_t padded = (bytes + 15) & ~(size_t)15;
+    if (!c->stage_h || c->stage_used + padded > c->stage_cap || ((uintptr_t)dst & 15)) {
+        c->stage_fallback = true;                          // caller synchronises before its host source goes away
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream);
+    }
+    uint8_t* h = c->stage_h + c->stage_used;
+    memcpy(h, src, bytes);
+    const uint8_t* d = c->stage_d + c->stage_used;
+    c->stage_used += padded;
+    const size_t n16 = padded / 16;
+    const int blocks = (int)std::min<size_t>((n16 + 255) / 256, 64);
+    stage_copy_kernel<<<blocks, 256, 0, c->stream>>>(reinterpret_cast<uint4*>(dst), reinterpret_cast<const uint4*>(d), n16);
+    c->launches++;
+    return cudaGetLastError();
+}
 
 extern "C" {
 
@@ -168,12 +199,18 @@ int cvg_create(cvg_ctx** out, int device, unsigned flags)
     cvg_ctx* c = new cvg_ctx();
     c->device = device; c->flags = flags; c->n_sms = prop.multiProcessorCount;
     CU_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU_CHECK(cudaMalloc(&c->d_flags, 64 * sizeof(int)));
     CU_CHECK(cudaMemset(c->d_flags, 0, 64 * sizeof(int)));
     for (int i = 0; i < 6; i++) CU_CHECK(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 32; i++) CU_CHECK(cudaEventCreate(&c->hyp_ev[i]));
     CU_CHECK(cudaMalloc(&c->d_scored, 8));
     CU_CHECK(cudaMemset(c->d_scored, 0, 8));
+    c->stage_cap = 4u << 20;
+    if (cudaHostAlloc((void**)&c->stage_h, c->stage_cap, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&c->stage_d, c->stage_h, 0) != cudaSuccess) {
+        cudaGetLastError(); c->stage_h = nullptr; c->stage_cap = 0;       // falls back to cudaMemcpyAsync
+    }
     char err[256];
     if (tc_init(err, sizeof err)) { delete c; return set_err(CVG_ERR_CUDA, "%s", err); }
     *out = c;
@@ -185,6 +222,7 @@ void cvg_destroy(cvg_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     DevBuf* bufs[] = { &c->q_f32, &c->q_b, &c->q_aug, &c->q_norm, &c->t_f32, &c->t_b, &c->t_aug, &c->t_kpt, &c->t_kptoff,
                        &c->units, &c->dir, &c->parts, &c->idx, &c->dist, &c->accept, &c->pts, &c->starts, &c->counts_n,
                        &c->sample_pos, &c->n_samples, &c->counts, &c->best_iter, &c->best_count, &c->iters_run, &c->niters_cur, &c->smp_state, &c->sel,
@@ -197,7 +235,9 @@ void cvg_destroy(cvg_ctx* c)
     for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 32; i++) if (c->hyp_ev[i]) cudaEventDestroy(c->hyp_ev[i]);
     if (c->d_scored) cudaFree(c->d_scored);
+    if (c->stage_h) cudaFreeHost(c->stage_h);
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
 }
 
@@ -247,8 +287,11 @@ static int ensure_rng(cvg_ctx* c, int max_iters)
 }
 
 // Prepare (convert) a train set that is already in device fp32 memory.
-static int prep_train(cvg_ctx* c, TrainSet& ts, DevBuf& b, DevBuf& aug, int flag_slot, bool pooled = false)
+static int prep_train(cvg_ctx* c, TrainSet& ts, DevBuf& b, DevBuf& aug, int flag_slot, bool pooled = false,
+                      cudaStream_t st = nullptr, int* d_flag = nullptr)
 {
+    if (!st) st = c->stream;
+    if (!d_flag) d_flag = c->d_flags + flag_slot;
     const size_t nb = (size_t)std::max<int64_t>(ts.rows_pad_total, 1) * DIM * 2;
     const size_t na = (size_t)std::max<int64_t>(ts.rows_pad_total, 1) * KAUG * 2;
     if (pooled) { CU_CHECK(c->pool.acquire(b, nb)); CU_CHECK(c->pool.acquire(aug, na)); }
@@ -257,7 +300,7 @@ static int prep_train(cvg_ctx* c, TrainSet& ts, DevBuf& b, DevBuf& aug, int flag
     for (const SegInfo& s : ts.segs) {
         const int n_pad = s.ct * TILE_N;
         launch_prep_rows(ts.d_f32 + s.f32_row0 * DIM, s.rows, n_pad, 1, ts.d_b + s.pad_row0 * DIM,
-                         ts.d_aug + s.pad_row0 * KAUG, nullptr, c->d_flags + flag_slot, c->stream);
+                         ts.d_aug + s.pad_row0 * KAUG, nullptr, d_flag, st);
         c->launches++;
     }
     CU_CHECK(cudaGetLastError());
@@ -361,9 +404,9 @@ static int launch_match(cvg_ctx* c, const QuerySide& q, const TrainSet& ts, cons
     return CVG_OK;
 }
 
-__global__ void combine_flags_kernel(int* f, int force_exact)
+__global__ void combine_flags_kernel(int* f, const int* train_flag, int force_exact, int ignore_query_flag = 0)
 {
-    f[2] = (f[0] | f[1] | force_exact) ? 1 : 0;
+    f[2] = (*train_flag | (ignore_query_flag ? 0 : f[1]) | force_exact) ? 1 : 0;
 }
 
 // Verify stage on a device correspondence pool.
@@ -499,7 +542,7 @@ static int match_host_train(cvg_ctx* c, QuerySide q, int q_nonint, const float* 
     int rc = prep_train(c, ts, c->t_b, c->t_aug, 0);
     if (rc) return rc;
     CU_CHECK(cudaMemcpyAsync(c->d_flags + 1, &q_nonint, 4, cudaMemcpyHostToDevice, c->stream));
-    combine_flags_kernel<<<1, 1, 0, c->stream>>>(c->d_flags, (c->flags & CVG_FORCE_EXACT_MATCH) ? 1 : 0);
+    combine_flags_kernel<<<1, 1, 0, c->stream>>>(c->d_flags, c->d_flags, (c->flags & CVG_FORCE_EXACT_MATCH) ? 1 : 0);
     c->launches++;
     std::vector<MatchUnit> units; std::vector<MergeEntry> dir; int n_rb;
     build_plan(q, ts, c->n_sms, units, dir, n_rb);
@@ -643,15 +686,15 @@ static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, Tra
         build_plan(q, ts, c->n_sms, units, dir, n_rb);
         DevBuf& ub = cache ? cache->units : c->units; DevBuf& db = cache ? cache->dir : c->dir;
         if (cache) {
-            CU_CHECK(c->pool.acquire(ub, std::max<size_t>(units.size(), 1) * sizeof(MatchUnit)));
-            CU_CHECK(c->pool.acquire(db, std::max<size_t>(dir.size(), 1) * sizeof(MergeEntry)));
+            CU_CHECK(c->pool.acquire(ub, std::max<size_t>(units.size(), 1) * sizeof(MatchUnit) + 16));
+            CU_CHECK(c->pool.acquire(db, std::max<size_t>(dir.size(), 1) * sizeof(MergeEntry) + 16));
         } else {
-            CU_CHECK(ub.ensure(std::max<size_t>(units.size(), 1) * sizeof(MatchUnit)));
-            CU_CHECK(db.ensure(std::max<size_t>(dir.size(), 1) * sizeof(MergeEntry)));
+            CU_CHECK(ub.ensure(std::max<size_t>(units.size(), 1) * sizeof(MatchUnit) + 16));
+            CU_CHECK(db.ensure(std::max<size_t>(dir.size(), 1) * sizeof(MergeEntry) + 16));
         }
-        if (!units.empty()) CU_CHECK(cudaMemcpyAsync(ub.p, units.data(), units.size() * sizeof(MatchUnit), cudaMemcpyHostToDevice, c->stream));
-        if (!dir.empty()) CU_CHECK(cudaMemcpyAsync(db.p, dir.data(), dir.size() * sizeof(MergeEntry), cudaMemcpyHostToDevice, c->stream));
-        CU_CHECK(cudaStreamSynchronize(c->stream));       // host vectors go out of scope
+        if (!units.empty()) CU_CHECK(h2d_small(c, ub.p, units.data(), units.size() * sizeof(MatchUnit)));
+        if (!dir.empty()) CU_CHECK(h2d_small(c, db.p, dir.data(), dir.size() * sizeof(MergeEntry)));
+        if (c->stage_fallback) CU_CHECK(cudaStreamSynchronize(c->stream));    // memcpy fallback: host vectors go out of scope
         n_units = (int)units.size();
         d_units = ub.as<MatchUnit>(); d_dir = db.as<MergeEntry>();
         if (cache) { cache->plan_models = m; cache->plan_units = n_units; }
@@ -667,9 +710,7 @@ static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, Tra
     if (c->timing) cudaEventRecord(c->ev[0], c->stream);
     const int path = (c->flags & CVG_FORCE_EXACT_MATCH) ? 2 : ((m->nonint || ts.nonint > 0) ? 2 : (ts.nonint == 0 ? 1 : 0));
     if (path == 0) {
-        const int qn = m->nonint;
-        CU_CHECK(cudaMemcpyAsync(c->d_flags + 1, &qn, 4, cudaMemcpyHostToDevice, c->stream));
-        combine_flags_kernel<<<1, 1, 0, c->stream>>>(c->d_flags, 0);
+        combine_flags_kernel<<<1, 1, 0, c->stream>>>(c->d_flags, (cache && cache->d_flag) ? cache->d_flag : c->d_flags, m->nonint, 1);
         c->launches++;
     }
     int rc = launch_match(c, q, ts, d_units, n_units, d_dir, n_rb, p->ratio, path, c->parts.as<Top2>(),
@@ -738,6 +779,7 @@ int cvg_detect_pairs(cvg_ctx* c, const cvg_models* m, const float* scene_desc, c
     if (rc) return rc;
     if (n_train < 0 || (n_train > 0 && (!scene_desc || !scene_kpt_xy))) return set_err(CVG_ERR_INVALID, "bad scene arrays");
     CU_CHECK(cudaSetDevice(c->device));
+    c->stage_used = 0; c->stage_fallback = false;
     const int V = m->n_views;
     TrainSet ts;
     const int64_t offs[2] = { 0, n_train };
@@ -777,8 +819,8 @@ int cvg_detect_pairs(cvg_ctx* c, const cvg_models* m, const float* scene_desc, c
     return CVG_OK;
 }
 
-int cvg_scenes_upload(cvg_ctx* c, const float* desc, const float* kpt_xy, const int64_t* offsets, int n_scenes,
-                      cvg_scenes** out)
+static int scenes_upload_impl(cvg_ctx* c, const float* desc, const float* kpt_xy, const int64_t* offsets, int n_scenes,
+                              cvg_scenes** out, bool async)
 {
     if (!c || !out || !offsets || n_scenes < 0) return set_err(CVG_ERR_INVALID, "cvg_scenes_upload: bad argument");
     *out = nullptr;
@@ -790,28 +832,64 @@ int cvg_scenes_upload(cvg_ctx* c, const float* desc, const float* kpt_xy, const 
     cvg_scenes* sc = new cvg_scenes();
     layout_segments(sc->ts, offsets, n_scenes);
     if (sc->ts.rows_pad_total > 0x7fffff00LL) { delete sc; return set_err(CVG_ERR_LIMIT, "scene batch too large (>2^31 padded rows)"); }
+    cudaStream_t st = async ? c->copy_stream : c->stream;
     CU_CHECK(c->pool.acquire(sc->f32, (size_t)std::max<int64_t>(total, 1) * DIM * 4));
     CU_CHECK(c->pool.acquire(sc->kpt, (size_t)std::max<int64_t>(total, 1) * 8));
-    CU_CHECK(c->pool.acquire(sc->kptoff, (size_t)(n_scenes + 1) * 8));
+    CU_CHECK(c->pool.acquire(sc->kptoff, (size_t)(n_scenes + 1) * 8 + 16));
     sc->ts.d_f32 = sc->f32.as<float>(); sc->ts.d_kpt = sc->kpt.as<float>(); sc->ts.d_kpt_offsets = sc->kptoff.as<int64_t>();
-    if (total > 0) CU_CHECK(cudaMemcpyAsync(sc->ts.d_f32, desc, (size_t)total * DIM * 4, cudaMemcpyHostToDevice, c->stream));
-    if (total > 0 && kpt_xy) CU_CHECK(cudaMemcpyAsync(sc->ts.d_kpt, kpt_xy, (size_t)total * 8, cudaMemcpyHostToDevice, c->stream));
-    else if (total > 0) CU_CHECK(cudaMemsetAsync(sc->ts.d_kpt, 0, (size_t)total * 8, c->stream));
-    CU_CHECK(cudaMemcpyAsync(sc->ts.d_kpt_offsets, offsets, (size_t)(n_scenes + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-    CU_CHECK(cudaMemsetAsync(c->d_flags, 0, 4, c->stream));
-    int rc = prep_train(c, sc->ts, sc->b, sc->aug, 0, true);
-    if (rc) { delete sc; return rc; }
-    int flag = 0;
-    CU_CHECK(cudaMemcpyAsync(&flag, c->d_flags, 4, cudaMemcpyDeviceToHost, c->stream));
-    CU_CHECK(cudaStreamSynchronize(c->stream));
-    sc->ts.nonint = flag;
+    sc->d_flag = reinterpret_cast<int*>(sc->kptoff.as<int64_t>() + (n_scenes + 1));
+    if (total > 0) CU_CHECK(cudaMemcpyAsync(sc->ts.d_f32, desc, (size_t)total * DIM * 4, cudaMemcpyHostToDevice, st));
+    if (total > 0 && kpt_xy) CU_CHECK(cudaMemcpyAsync(sc->ts.d_kpt, kpt_xy, (size_t)total * 8, cudaMemcpyHostToDevice, st));
+    else if (total > 0) CU_CHECK(cudaMemsetAsync(sc->ts.d_kpt, 0, (size_t)total * 8, st));
+    CU_CHECK(cudaMemcpyAsync(sc->ts.d_kpt_offsets, offsets, (size_t)(n_scenes + 1) * 8, cudaMemcpyHostToDevice, st));
+    CU_CHECK(cudaMemsetAsync(sc->d_flag, 0, 8, st));
+    int rc = prep_train(c, sc->ts, sc->b, sc->aug, 0, true, st, sc->d_flag);
+    if (rc) { cvg_scenes_free(c, sc); return rc; }
+    if (async) {
+        // the caller's buffers are read by the copy engine until `ready`; cvg_detect_scenes orders itself after it
+        CU_CHECK(cudaEventCreateWithFlags(&sc->ready, cudaEventDisableTiming));
+        CU_CHECK(cudaEventRecord(sc->ready, st));
+        sc->ts.nonint = -1;                            // the match path is decided on the device from d_flag
+    } else {
+        int flag = 0;
+        CU_CHECK(cudaMemcpyAsync(&flag, sc->d_flag, 4, cudaMemcpyDeviceToHost, st));
+        CU_CHECK(cudaStreamSynchronize(st));
+        sc->ts.nonint = flag;
+    }
     *out = sc;
+    return CVG_OK;
+}
+
+int cvg_scenes_upload(cvg_ctx* c, const float* desc, const float* kpt_xy, const int64_t* offsets, int n_scenes,
+                      cvg_scenes** out)
+{
+    return scenes_upload_impl(c, desc, kpt_xy, offsets, n_scenes, out, false);
+}
+
+int cvg_scenes_upload_async(cvg_ctx* c, const float* desc, const float* kpt_xy, const int64_t* offsets, int n_scenes,
+                            cvg_scenes** out)
+{
+    return scenes_upload_impl(c, desc, kpt_xy, offsets, n_scenes, out, true);
+}
+
+int cvg_scenes_wait(cvg_ctx* c, cvg_scenes* sc)
+{
+    if (!c || !sc) return set_err(CVG_ERR_INVALID, "cvg_scenes_wait: NULL argument");
+    if (!sc->ready) return CVG_OK;
+    CU_CHECK(cudaSetDevice(c->device));
+    CU_CHECK(cudaEventSynchronize(sc->ready));
+    if (sc->ts.nonint < 0) {
+        int flag = 0;
+        CU_CHECK(cudaMemcpy(&flag, sc->d_flag, 4, cudaMemcpyDeviceToHost));
+        sc->ts.nonint = flag;
+    }
     return CVG_OK;
 }
 
 void cvg_scenes_free(cvg_ctx* c, cvg_scenes* sc)
 {
     if (!sc) return;
+    if (sc->ready) { cudaEventSynchronize(sc->ready); cudaEventDestroy(sc->ready); sc->ready = nullptr; }
     if (c) {
         cudaSetDevice(c->device);
         DevBuf* bufs[] = { &sc->f32, &sc->b, &sc->aug, &sc->kpt, &sc->kptoff, &sc->units, &sc->dir };
@@ -832,13 +910,15 @@ int cvg_detect_scenes(cvg_ctx* c, const cvg_models* m, const cvg_scenes* scenes,
     CU_CHECK(cudaSetDevice(c->device));
     cvg_scenes* sc = const_cast<cvg_scenes*>(scenes);
     const int S = sc->ts.n_segs, V = m->n_views;
+    c->stage_used = 0; c->stage_fallback = false;       // previous call has completed (calls are synchronous)
+    if (sc->ready) CU_CHECK(cudaStreamWaitEvent(c->stream, sc->ready, 0));
     const float* d_scales = nullptr;
     if (scales && S * V > 0) {
         std::vector<float> ps((size_t)S * V);
         for (int s = 0; s < S; s++) for (int v = 0; v < V; v++) ps[(size_t)s * V + v] = scales[s];
-        CU_CHECK(c->scales.ensure(ps.size() * 4));
-        CU_CHECK(cudaMemcpyAsync(c->scales.p, ps.data(), ps.size() * 4, cudaMemcpyHostToDevice, c->stream));
-        CU_CHECK(cudaStreamSynchronize(c->stream));
+        CU_CHECK(c->scales.ensure(ps.size() * 4 + 16));
+        CU_CHECK(h2d_small(c, c->scales.p, ps.data(), ps.size() * 4));
+        if (c->stage_fallback) CU_CHECK(cudaStreamSynchronize(c->stream));
         d_scales = c->scales.as<float>();
     }
     return detect_common(c, m, sc, sc->ts, d_scales, p, per_pair, nullptr, nullptr, false);
@@ -868,7 +948,7 @@ int cvg_dev_match_top2(cvg_ctx* c, void* stream, const float* query_dev, int n_q
     ts.d_f32 = const_cast<float*>(train_dev);
     int rc = prep_train(c, ts, c->t_b, c->t_aug, 0);
     if (rc) return rc;
-    combine_flags_kernel<<<1, 1, 0, c->stream>>>(c->d_flags, (c->flags & CVG_FORCE_EXACT_MATCH) ? 1 : 0);
+    combine_flags_kernel<<<1, 1, 0, c->stream>>>(c->d_flags, c->d_flags, (c->flags & CVG_FORCE_EXACT_MATCH) ? 1 : 0);
     c->launches++;
     QuerySide q{ query_dev, c->q_b.as<__nv_bfloat16>(), c->q_aug.as<__nv_bfloat16>(), c->q_norm.as<float>(), 0, n_query, n_pad };
     std::vector<MatchUnit> units; std::vector<MergeEntry> dir; int n_rb;

@@ -162,6 +162,15 @@ int  cvg_detect_pairs(cvg_ctx* ctx, const cvg_models* models,
 int  cvg_scenes_upload(cvg_ctx* ctx, const float* desc, const float* kpt_xy,
                        const int64_t* offsets, int n_scenes, cvg_scenes** out);
 void cvg_scenes_free(cvg_ctx* ctx, cvg_scenes* scenes);
+/* Streaming form for a caller that walks a list of test images (reference src/Output.cpp:27-47):
+ * cvg_scenes_upload_async enqueues the copy and the operand conversion on the context's copy stream
+ * and returns at once, so the upload of batch k+1 overlaps cvg_detect_scenes of batch k.  The host
+ * arrays must stay valid and unchanged until cvg_scenes_wait or the first cvg_detect_scenes on the
+ * handle has returned (use pinned memory for a truly asynchronous copy).  cvg_detect_scenes orders
+ * itself after the upload on the device; cvg_scenes_wait is optional. */
+int  cvg_scenes_upload_async(cvg_ctx* ctx, const float* desc, const float* kpt_xy,
+                             const int64_t* offsets, int n_scenes, cvg_scenes** out);
+int  cvg_scenes_wait(cvg_ctx* ctx, cvg_scenes* scenes);
 int  cvg_detect_scenes(cvg_ctx* ctx, const cvg_models* models, const cvg_scenes* scenes,
                        const float* scales, const cvg_detect_params* p, cvg_pair_result* per_pair);
 

@@ -275,6 +275,34 @@ def test_detect_scenes_resident_equals_per_scene_calls(ctx, feats, gpairs):
     scenes.free(); models.free()
 
 
+def test_async_upload_pipeline_equals_sync(ctx, feats, api):
+    """cvg_scenes_upload_async (copy stream, device-side path decision) + cvg_detect_scenes == the synchronous
+    upload, for integer (tensor path) and non-integer (exact path) scene batches, two batches in flight."""
+    md = feats["model_desc"].astype(np.float32)
+    models = ctx.upload_models(md, feats["model_kpt"], feats["view_offsets"], feats["view_model"])
+    so = feats["scene_offsets"]
+    n_sc = min(10, len(so) - 1)
+    off = np.asarray(so[:n_sc + 1], np.int64)
+    d_int = np.ascontiguousarray(feats["scene_desc"][:off[-1]].astype(np.float32))
+    kp = np.ascontiguousarray(feats["scene_kpt"][:off[-1]].astype(np.float32))
+    d_flt = d_int.copy(); d_flt[::7, 3] += 0.25                          # non-integer rows -> exact kernel
+    want = []
+    for d in (d_int, d_flt):
+        sc = ctx.upload_scenes(d, kp, off)
+        want.append(ctx.detect_scenes(models, sc).copy()); sc.free()
+    a = ctx.upload_scenes_async(d_int, kp, off)
+    b = ctx.upload_scenes_async(d_flt, kp, off)                           # second upload in flight during detect(a)
+    ra = ctx.detect_scenes(models, a).copy(); pa = ctx.last_match_path
+    rb = ctx.detect_scenes(models, b).copy(); pb = ctx.last_match_path
+    b.wait()
+    a.free(); b.free()
+    assert pa == api.PATH_TENSOR and pb == api.PATH_EXACT
+    for got, w in zip((ra, rb), want):
+        assert np.array_equal(got["status"], w["status"]) and np.array_equal(got["n_inliers"], w["n_inliers"])
+        assert np.array_equal(got["H"], w["H"])
+    models.free()
+
+
 def test_full_dataset_13350_pairs_vs_cv2(ctx):
     """The reference's whole loop nest (30 images x 5 scales x 89 views, src/TestsDetector.cpp:38,58,99-100) from the
     feature cache (tools/build_feature_cache.py) against cv2 4.13.0's results for the same pairs
