@@ -41,8 +41,12 @@ constexpr uint32_t OFF_B = 2 * A_BYTES;                           //  72 KB
 constexpr uint32_t OFF_BAUG = OFF_B + B_STAGES * B_ATOM_BYTES;    // 200 KB
 constexpr uint32_t OFF_SCRATCH = OFF_BAUG + 2 * B_AUG_BYTES;      // 216 KB
 constexpr uint32_t SCRATCH_BYTES = 3 * TILE_M * 16;                 // partial top-2 of column parts 1..3 at unit end
-constexpr uint32_t OFF_BAR = OFF_SCRATCH + SCRATCH_BYTES;
-constexpr uint32_t TC_SMEM_BYTES = OFF_BAR + 512 + 1024;          // + alignment slack
+constexpr uint32_t OFF_SHARE = OFF_SCRATCH + SCRATCH_BYTES;         // running (best, second best) of every column part, per row
+constexpr uint32_t SHARE_BYTES = 4 * TILE_M * 8;                    //                              4 KB
+constexpr uint32_t OFF_BAR = OFF_SHARE + SHARE_BYTES;
+constexpr uint32_t TC_SMEM_SLACK = 512;                           // the dynamic window is 1024-aligned in practice; checked in the kernel
+constexpr uint32_t TC_SMEM_BYTES = OFF_BAR + 512 + TC_SMEM_SLACK;
+static_assert(TC_SMEM_BYTES <= 232448, "shared memory budget of one CTA (227 KB)");
 constexpr float ABSENT_BELOW = -5.0e8f;                           // padded train rows carry -2^30
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -126,32 +130,51 @@ __device__ __forceinline__ uint64_t desc_sw32(uint32_t saddr)
 // both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 
-// Running top-2 (largest acc') of one query row over 32 more train columns.  The row's second best b2
-// is a filter: maxima of groups of 4 columns are compared with it first, so a group costs ~2 instructions
-// per lane unless one of the warp's 32 rows really has a new candidate in it (a rare event per row, but
-// common per warp if tested at 32-column granularity).  Strict > keeps the earlier (lower) train index
-// on ties, as cv::batchDistance's insertion does.
-__device__ __forceinline__ void top2_scan32(const uint32_t* r, int c0, float& b1, int& i1, float& b2, int& i2)
+// Running top-2 (largest acc') of one query row over 32 more train columns.  `f` is the row's filter: no
+// column with a value <= f can be one of the row's two best (f >= the warp's own second best b2, and it is
+// raised further by what the other three column parts of the same rows have found, see the epilogue).  Maxima
+// of groups of 4 columns are compared with it first, so a group costs ~2 instructions per lane unless one of
+// the warp's 32 rows really has a candidate in it.  Strict > against the warp's own values keeps the earlier
+// (lower) train index on ties, as cv::batchDistance's insertion does.
+__device__ __forceinline__ void top2_scan32(const uint32_t* r, int c0, float& b1, int& i1, float& b2, int& i2, float& f)
 {
     float g[8];
     #pragma unroll
     for (int k = 0; k < 8; k++)
         g[k] = fmaxf(fmaxf(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1])),
                      fmaxf(__uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3])));
-    // no 32-wide pre-test: with 32 rows per warp some row almost always has a candidate in a 32-column chunk
     #pragma unroll
     for (int k = 0; k < 8; k++) {
-        if (g[k] > b2) {
+        if (g[k] > f) {
             #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const float v = __uint_as_float(r[4 * k + j]);
-                if (v > b2) {
+                if (v > f) {
                     if (v > b1) { b2 = b1; i2 = i1; b1 = v; i1 = c0 + 4 * k + j; }
                     else        { b2 = v; i2 = c0 + 4 * k + j; }
+                    f = fmaxf(f, b2);
                 }
             }
         }
     }
+}
+
+__device__ __forceinline__ void share_store(uint32_t addr, float a, float b)
+{
+    asm volatile("st.volatile.shared.v2.f32 [%0], {%1, %2};" :: "r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void share_load(uint32_t addr, float& a, float& b)
+{
+    asm volatile("ld.volatile.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(addr) : "memory");
+}
+
+// largest float below x (x finite or -inf; -inf stays -inf)
+__device__ __forceinline__ float float_pred(float x)
+{
+    const int b = __float_as_int(x);
+    if (x == -INFINITY) return x;
+    if (x == 0.f) return __int_as_float((int)0x80000001u);
+    return __int_as_float(x > 0.f ? b - 1 : b + 1);
 }
 
 struct TcMaps { CUtensorMap q, qaug, t, taug; };
@@ -167,6 +190,10 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    if (smem_base - smem_u32(smem_raw) > TC_SMEM_SLACK) {          // never seen: the window starts 1024-aligned
+        if (dbg) { dbg[0] = 9; dbg[1] = (int)blockIdx.x; }
+        __trap();
+    }
     const uint32_t bar0 = smem_base + OFF_BAR;
     // barrier slots (8 bytes each)
     const uint32_t a_full = bar0, a_empty = bar0 + 16, t_full = bar0 + 32, t_empty = bar0 + 48;
@@ -272,15 +299,38 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
         const int part = ew >> 2;                        // which 64 columns of the 256-wide accumulator
         const int row_in_tile = quarter * 32 + lane;
         Top2* scratch = reinterpret_cast<Top2*>(smem + OFF_SCRATCH);
+        // Every column part publishes its running (best, second best) per row; before each tile a warp raises its
+        // filter to the second largest value any part has seen for the row.  Unsynchronised on purpose: a stale or
+        // torn pair still consists of values of real columns with "second <= some other column of that part", so
+        // the bound below is always <= the row's true second best.  Values equal to a foreign bound are kept
+        // (float_pred) because the foreign column may have the higher train index.
+        const uint32_t share = smem_base + OFF_SHARE;
+        const uint32_t my_share = share + (uint32_t)(part * TILE_M + row_in_tile) * 8u;
+        share_store(my_share, -INFINITY, -INFINITY);
+        asm volatile("bar.sync 1, %0;" :: "n"(32 * TC_EPI_WARPS) : "memory");
         uint32_t tc = 0;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             const MatchUnit un = units[u];
-            float b1 = -INFINITY, b2 = -INFINITY;
+            float b1 = -INFINITY, b2 = -INFINITY, f = -INFINITY;
             int i1 = -1, i2 = -1;
             for (int t = 0; t < un.n_tiles; t++, tc++) {
                 const uint32_t acc = tc & 1;
                 mbar_wait(t_full + 8 * acc, (tc >> 1) & 1, dbg, 6);
                 tc_fence_after();
+                if (t > 0) {
+                    float o1[3], o2[3];
+                    #pragma unroll
+                    for (int pp = 0; pp < 3; pp++) {
+                        const int op = (part + 1 + pp) & 3;
+                        share_load(share + (uint32_t)(op * TILE_M + row_in_tile) * 8u, o1[pp], o2[pp]);
+                    }
+                    // second largest of the four bests, and the largest of the four seconds
+                    const float m1 = fmaxf(b1, o1[0]), n1 = fminf(b1, o1[0]);
+                    const float m2 = fmaxf(o1[1], o1[2]), n2 = fminf(o1[1], o1[2]);
+                    const float second_best = fmaxf(fminf(m1, m2), fmaxf(n1, n2));
+                    const float foreign = fmaxf(fmaxf(second_best, o2[0]), fmaxf(o2[1], o2[2]));
+                    f = fmaxf(f, float_pred(foreign));
+                }
                 const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TILE_N + part * 64;
                 const int col_base = un.t_local0 + t * TILE_N + part * 64;
                 if (!(exp_mode & 1)) {
@@ -288,14 +338,16 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                     tc_ld32(tbase, ra);                           // two loads in flight before the wait
                     tc_ld32(tbase + 32, rb);
                     tc_wait_ld();
-                    top2_scan32(ra, col_base, b1, i1, b2, i2);
-                    top2_scan32(rb, col_base + 32, b1, i1, b2, i2);
+                    top2_scan32(ra, col_base, b1, i1, b2, i2, f);
+                    top2_scan32(rb, col_base + 32, b1, i1, b2, i2, f);
+                    share_store(my_share, b1, b2);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(t_empty + 8 * acc);
             }
-            // ---- unit flush: merge the two column halves, convert to distances, write the partial ----
+            // ---- unit flush: merge the four column parts, convert to distances, write the partial ----
+            share_store(my_share, -INFINITY, -INFINITY);     // reset before the barriers below
             if (b1 < ABSENT_BELOW) { i1 = -1; }
             if (b2 < ABSENT_BELOW) { i2 = -1; }
             if (part > 0) {

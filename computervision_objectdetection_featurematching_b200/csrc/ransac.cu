@@ -698,11 +698,23 @@ ransac_finish_kernel(RansacWork w)
     if (best_iter < 0) { fail(); return; }
 
     // winner's model again (deterministic) -> its mask, in original order
-    if (tid == 0) {
-        float Hf[8];
-        solve_hypothesis<1>(w, pts, n, w.sample_pos[(size_t)set * w.max_iters + best_iter], Hf, sh.H, sh.jac);
-        for (int i = 0; i < 8; i++) sh.Hf[i] = Hf[i];
-        sh.base_cnt = 0;
+    if (tid < 32) {                                          // warp 0, cooperatively (bit-identical to the hypothesis kernels)
+        int idx[4];
+        draw_subset(w.rng_tab, w.rng_len, w.sample_pos[(size_t)set * w.max_iters + best_iter], (uint32_t)n, idx);
+        float ms1[8], ms2[8];
+        #pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float4 q = pts[idx[i]];
+            ms1[2 * i] = q.x; ms1[2 * i + 1] = q.y; ms2[2 * i] = q.z; ms2[2 * i + 1] = q.w;
+        }
+        double H[9];
+        // scratch_a, scratch_v, scratch_w, jac are contiguous: 333 doubles >= the 243 run_kernel4_warp needs
+        run_kernel4_warp(ms1, ms2, H, sh.scratch_a);
+        if (tid == 0) {
+            for (int i = 0; i < 9; i++) sh.H[i] = H[i];
+            for (int i = 0; i < 8; i++) sh.Hf[i] = (float)H[i];
+            sh.base_cnt = 0;
+        }
     }
     __syncthreads();
     float Hf[8];
