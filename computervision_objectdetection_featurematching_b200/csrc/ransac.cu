@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "homography_math.cuh"
 #include "jacobi_warp.cuh"
+#include "jacobi_thread.cuh"
 #include <stdlib.h>
 
 namespace cvg {
@@ -413,6 +414,64 @@ ransac_hyp_g8_kernel(RansacWork w, int round_base)
         w.counts[(size_t)set * w.max_iters + iter] = valid ? cnt : -1;
         if (w.scored_pts && valid) atomicAdd(w.scored_pts, (unsigned long long)n);
     }
+}
+
+// One hypothesis per THREAD with the register/predication-friendly Jacobi of jacobi_thread.cuh: the variant for
+// rounds that fill the chip (>= a few thousand hypotheses).  A warp retires 32 rotations with ~850 instructions
+// where the 8-lane-group kernel needs ~2900.  224 threads x 126 doubles of matrix state = 220.5 KB of shared
+// memory, one CTA per SM.  Hypotheses are numbered flat over (set, iteration) so CTAs stay full whatever the
+// round length; lanes of one warp almost always share a set, so the scoring loop's float4 loads are warp-uniform
+// (one L1 transaction, broadcast).  Bit-identical to the other hypothesis kernels.
+constexpr int HYPT_THREADS = 224;
+constexpr int HYPT_SMEM = HYPT_THREADS * JT_DOUBLES * 8;
+
+struct WarpAny { __device__ __forceinline__ bool operator()(bool x) const { return __any_sync(0xffffffffu, x); } };
+
+__global__ void __launch_bounds__(HYPT_THREADS, 1)
+ransac_hyp_t_kernel(RansacWork w, int round_base, int round_len)
+{
+    extern __shared__ double jt_smem[];
+    const int64_t h = (int64_t)blockIdx.x * HYPT_THREADS + threadIdx.x;
+    const int set = (int)(h / round_len);
+    const int iter = round_base + (int)(h - (int64_t)set * round_len);
+    bool live = set < w.n_sets;
+    int n = 0;
+    const float4* __restrict__ pts = w.pts;
+    if (live) {
+        n = w.counts_n[set];
+        live = iter < w.n_samples[set] && iter < w.niters_cur[set];
+        pts = w.pts + w.starts[set];
+    }
+    if (!__any_sync(0xffffffffu, live)) return;                 // warp-uniform; the kernel has no block-wide barrier
+    float ms1[8], ms2[8];
+    #pragma unroll
+    for (int i = 0; i < 8; i++) { ms1[i] = 0.f; ms2[i] = 0.f; }
+    if (live) {
+        int idx[4];
+        draw_subset(w.rng_tab, w.rng_len, w.sample_pos[(size_t)set * w.max_iters + iter], (uint32_t)n, idx);
+        #pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float4 q = pts[idx[i]];
+            ms1[2 * i] = q.x; ms1[2 * i + 1] = q.y; ms2[2 * i] = q.z; ms2[2 * i + 1] = q.w;
+        }
+    }
+    double H[9];
+    const bool valid = run_kernel4_thread<HYPT_THREADS>(ms1, ms2, H, jt_smem + threadIdx.x, live, WarpAny());
+    if (!live) return;
+    int cnt = -1;
+    if (valid) {
+        float Hf[8];
+        #pragma unroll
+        for (int i = 0; i < 8; i++) Hf[i] = (float)H[i];
+        cnt = 0;
+        #pragma unroll 4
+        for (int i = 0; i < n; i++) {
+            const float4 q = __ldg(pts + i);
+            cnt += reproj_err(Hf, q.x, q.y, q.z, q.w) <= w.thr2 ? 1 : 0;     // NaN -> not an inlier
+        }
+        if (w.scored_pts) atomicAdd(w.scored_pts, (unsigned long long)n);
+    }
+    w.counts[(size_t)set * w.max_iters + iter] = cnt;
 }
 
 // ---- 3. select kernel: the serial scan of RANSACPointSetRegistrator::run --------------------------
@@ -921,39 +980,49 @@ int launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events,
     if (!attr_set) {
         cudaFuncSetAttribute(ransac_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HYP_SMEM);
         cudaFuncSetAttribute(ransac_hyp_g8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HYPG_SMEM);
+        cudaFuncSetAttribute(ransac_hyp_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HYPT_SMEM);
         attr_set = true;
     }
-    // hypotheses are solved and scored in rounds; after each round the serial selection scan advances, so
-    // rounds beyond the adaptive stop (RANSACUpdateNumIters) cost one early-exit per block
+    // Hypotheses are solved and scored in rounds; after each round the serial selection scan advances, so rounds
+    // beyond the adaptive stop (RANSACUpdateNumIters) cost one early exit per warp.  A round is a latency-bound
+    // launch (~135 dependent rotations per matrix whatever the kernel), so it is made long enough to fill the chip:
+    // at least 256 iterations per set, and n_sets x round_len >= one full wave of the thread-per-hypothesis kernel.
+    static const int hyp_mode = getenv("CVG_HYP_MODE") ? atoi(getenv("CVG_HYP_MODE")) : 0;   // experiments: 1 warp, 2 g8, 3 thread (generic), 4 thread
+    static const int round_env = getenv("CVG_ROUND_LEN") ? atoi(getenv("CVG_ROUND_LEN")) : 0;
+    static int n_sms = 0;
+    if (!n_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev); if (n_sms <= 0) n_sms = 148; }
     int round_len = w.max_iters;
     if (!(w.flags & CVG_RANSAC_NO_EARLY_STOP)) {
-        round_len = (w.max_iters + 15) / 16;
-        if (round_len < 256) round_len = 256;
-        round_len = (round_len + HYP_THREADS - 1) / HYP_THREADS * HYP_THREADS;
+        const int64_t wave = (int64_t)n_sms * HYPT_THREADS;
+        int64_t fill = wave / w.n_sets / 32 * 32;              // rounded down: n_sets x round_len must not spill into a second wave
+        round_len = (int)std::min<int64_t>(std::max<int64_t>(256, fill), w.max_iters);
+        if (round_env > 0) round_len = std::min(round_env, w.max_iters);
     }
     const int warps_per_block = 4;
-    for (int rb = 0; rb < w.max_iters; rb += round_len) {
+    int round = 0;
+    for (int rb = 0; rb < w.max_iters; rb += round_len, round++) {
         const int len = w.max_iters - rb < round_len ? w.max_iters - rb : round_len;
         ransac_sample_kernel<<<w.n_sets, SMP_THREADS, 0, st>>>(w, rb, rb + len);
-        const int round = rb / round_len;
         const bool timed = hyp_events != nullptr && round < 16;
         if (timed) cudaEventRecord(hyp_events[2 * round], st);
-        // Measured on B200.  13 350 real pairs (3.4 M hypotheses per round), whole verify stage: thread-per-
-        // hypothesis 612 ms, warp-per-hypothesis 1436 ms, four-per-warp 498 ms.  64 synthetic 8k x 8k pairs
+        // Measured on B200 (round 1).  13 350 real pairs (3.4 M hypotheses per round), whole verify stage: generic
+        // thread-per-hypothesis 612 ms, warp-per-hypothesis 1436 ms, four-per-warp 498 ms.  64 synthetic 8k x 8k pairs
         // (16 384 hypotheses per round), hypothesis kernels per step: warp 4.15 ms, four-per-warp 2.41 ms.
-        // One set alone (256 hypotheses): warp 0.30 ms, thread 1.1 ms.
-        static const int hyp_mode = getenv("CVG_HYP_MODE") ? atoi(getenv("CVG_HYP_MODE")) : 0;   // experiments: 1 warp, 2 g8, 3 thread
+        // One set alone (256 hypotheses): warp 0.30 ms, generic thread 1.1 ms.
         const int64_t hyps = (int64_t)len * w.n_sets;
-        const int mode = hyp_mode ? hyp_mode : (hyps <= 4096 ? 1 : 2);
-        if (mode == 1) {                                       // a handful of sets: latency of one matrix counts
+        const int mode = hyp_mode ? hyp_mode : (hyps <= 4096 ? 1 : 4);
+        if (mode == 1) {                                       // a handful of hypotheses: latency of one matrix counts
             dim3 grid((len + HYPW_WARPS - 1) / HYPW_WARPS, w.n_sets);
             ransac_hyp_warp_kernel<<<grid, HYPW_WARPS * 32, 0, st>>>(w, rb);
-        } else if (mode == 2) {                                // the chip is full of warps: four matrices per warp
+        } else if (mode == 2) {                                // four matrices per warp
             dim3 grid((len + HYPG_WARPS * 4 - 1) / (HYPG_WARPS * 4), w.n_sets);
             ransac_hyp_g8_kernel<<<grid, HYPG_WARPS * 32, HYPG_SMEM, st>>>(w, rb);
-        } else {                                              // throughput-bound: one thread per hypothesis
+        } else if (mode == 3) {                                // generic serial routine, one thread per hypothesis
             dim3 grid((len + HYP_THREADS - 1) / HYP_THREADS, w.n_sets);
             ransac_hyp_kernel<<<grid, HYP_THREADS, HYP_SMEM, st>>>(w, rb);
+        } else {                                               // the chip is full: one thread per hypothesis
+            const int64_t blocks = (hyps + HYPT_THREADS - 1) / HYPT_THREADS;
+            ransac_hyp_t_kernel<<<(unsigned)blocks, HYPT_THREADS, HYPT_SMEM, st>>>(w, rb, len);
         }
         if (timed) { cudaEventRecord(hyp_events[2 * round + 1], st); *n_hyp_rounds = round + 1; }
         ransac_select_kernel<<<(w.n_sets + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(w, rb, len);

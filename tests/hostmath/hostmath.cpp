@@ -1,6 +1,7 @@
 // Host build of csrc/homography_math.cuh for CPU-side unit tests (tests/test_hostmath.py): the very
 // functions the CUDA kernels call, compiled with g++ -ffp-contract=off, checked against the oracle.
 #include "../../computervision_objectdetection_featurematching_b200/csrc/homography_math.cuh"
+#include "../../computervision_objectdetection_featurematching_b200/csrc/jacobi_thread.cuh"
 #include <vector>
 #include <cstring>
 
@@ -52,6 +53,14 @@ void hm_jacobi9(const double* A, double* W, double* V)
     double a[81];
     memcpy(a, A, sizeof a);
     cvg::jacobi<9>(a, W, V);
+}
+
+// thread-per-hypothesis runKernel (csrc/jacobi_thread.cuh) on a 4-point sample, element-major storage
+int hm_run_kernel4_thread(const float* src, const float* dst, double* H)
+{
+    constexpr int S = 32;
+    std::vector<double> buf((size_t)cvg::JT_DOUBLES * S + 9, -777.0);
+    return cvg::run_kernel4_thread<S>(src, dst, H, buf.data() + 3, true, [](bool x) { return x; }) ? 1 : 0;
 }
 
 double hm_det3(const double* H) { return cvg::det3(H); }

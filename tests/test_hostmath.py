@@ -10,12 +10,14 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "hostmath", "hostmath.cpp")
 SO = os.path.join(HERE, "hostmath", "libhostmath.so")
-HDR = os.path.join(HERE, "..", "computervision_objectdetection_featurematching_b200", "csrc", "homography_math.cuh")
+CSRC = os.path.join(HERE, "..", "computervision_objectdetection_featurematching_b200", "csrc")
+HDR = os.path.join(CSRC, "homography_math.cuh")
+HDR2 = os.path.join(CSRC, "jacobi_thread.cuh")
 
 
 @pytest.fixture(scope="module")
 def hm():
-    if (not os.path.exists(SO)) or max(os.path.getmtime(SRC), os.path.getmtime(HDR)) > os.path.getmtime(SO):
+    if (not os.path.exists(SO)) or max(os.path.getmtime(SRC), os.path.getmtime(HDR), os.path.getmtime(HDR2)) > os.path.getmtime(SO):
         subprocess.check_call(["g++", "-O2", "-fPIC", "-std=c++17", "-ffp-contract=off", "-shared", "-o", SO, SRC])
     lib = C.CDLL(SO)
     lib.hm_reproj_err.restype = C.c_float
@@ -77,3 +79,35 @@ def test_update_num_iters(hm, oracle):
         for good in range(4, n + 1, max(1, n // 97)):
             ep = (n - good) / n
             assert hm.hm_update_num_iters(0.995, ep, 2000) == oracle.update_num_iters(0.995, ep, 4, 2000)
+
+
+def test_thread_per_hypothesis_run_kernel_bit_exact(hm):
+    """csrc/jacobi_thread.cuh (packed indR/indC, predicated static loops, tournament pivot search, strict-upper
+    storage) == the serial runKernel of homography_math.cuh, bit for bit, on 4-point samples incl. degenerate ones."""
+    rng = np.random.default_rng(11)
+    n_ok = 0
+    for case in range(4000):
+        s = rng.uniform(0, 640, size=(4, 2)).astype(np.float32)
+        kind = case % 8
+        if kind == 0:
+            d = rng.uniform(0, 640, size=(4, 2)).astype(np.float32)            # unrelated points
+        elif kind == 1:
+            d = s.copy()                                                       # identity
+        elif kind == 2:
+            d = (s * np.float32(1.3) + np.float32(7)).astype(np.float32)       # similarity
+        elif kind == 3:
+            s = np.round(s); d = np.round(s + rng.normal(0, 20, size=(4, 2))).astype(np.float32)   # integer coordinates
+        elif kind == 4:
+            d = (s + rng.normal(0, 15, size=(4, 2))).astype(np.float32); d[1] = d[0]; s[1] = s[0]  # duplicate point
+        elif kind == 5:
+            s[:, 1] = s[0, 1]; d = (s + rng.normal(0, 5, size=(4, 2))).astype(np.float32)          # zero spread in y
+        else:
+            d = (s + rng.normal(0, 15, size=(4, 2))).astype(np.float32)
+        H1 = np.zeros(9); H2 = np.zeros(9)
+        ok1 = hm.hm_run_kernel(_p(s), _p(d), 4, _p(H1))
+        ok2 = hm.hm_run_kernel4_thread(_p(s), _p(d), _p(H2))
+        assert ok1 == ok2, case
+        if ok1:
+            assert np.array_equal(H1, H2, equal_nan=True), (case, H1, H2)
+            n_ok += 1
+    assert n_ok > 3000
