@@ -20,7 +20,8 @@ namespace cvg {
 constexpr int JT_A = 0;                 // 36 doubles: A[i][j], i < j, at JT_A + tri(i, j)
 constexpr int JT_V = 36;                // 81 doubles: V row-major
 constexpr int JT_W = 117;               //  9 doubles
-constexpr int JT_DOUBLES = 126;
+constexpr int JT_SPARE = 126;            //  1 double: target of the predicated-off rotations
+constexpr int JT_DOUBLES = 127;
 
 // first element of row i in the packed strict upper triangle: 0, 8, 15, 21, 26, 30, 33, 35
 CVG_HD constexpr int jt_off(int i) { return i * (17 - i) / 2; }
@@ -153,6 +154,7 @@ CVG_HD bool run_kernel4_thread(const float* ms1, const float* ms2, double* H, do
             // element (i, x), i < x, sits at mA[jt_offm(i) * S + x * S]; element (x, i), i > x, at mA[(jt_offm(x) + i) * S]:
             // with the four bases below every access is base + compile-time offset, chosen by a predicate
             double* const mA = m + JT_A * S;
+            double* const spare = m + JT_SPARE * S;
             double* const mk_lt = mA + k * S;                     // + jt_offm(i) * S   for i < k
             double* const mk_gt = mA + jt_offm_dyn(k) * S;        // + i * S            for i > k
             double* const ml_lt = mA + l * S;
@@ -165,22 +167,28 @@ CVG_HD bool run_kernel4_thread(const float* ms1, const float* ms2, double* H, do
             int mRk = 0, mCk = 0, mRl = 0, mCl = 0;
             #pragma unroll
             for (int i = 0; i < 9; i++) {
-                double ma, mb;                     // |A| on the line of k resp. l at the other index i
-                if (i != k && i != l) {
-                    double* const pa = (i < k) ? (mk_lt + jt_offm(i < 8 ? i : 0) * S) : (mk_gt + i * S);
-                    double* const pb = (i < l) ? (ml_lt + jt_offm(i < 8 ? i : 0) * S) : (ml_gt + i * S);
-                    const double a0 = *pa, b0 = *pb;
-                    const double na = a0 * c - b0 * s, nb = a0 * s + b0 * c;
-                    *pa = na; *pb = nb;
-                    ma = fabs(na); mb = fabs(nb);
-                } else {
-                    ma = (i == l) ? 0.0 : -1.0;    // A[k][l] = 0 belongs to row k (and to column l); i == k is no element
-                    mb = (i == k) ? 0.0 : -1.0;
-                }
-                // serial scans in ascending i: columns (i < idx) and rows (i > idx); -1 never wins, so excluded
-                // entries and the scan's first element need no special case
-                if (i < k) { if (mvCk < ma) { mvCk = ma; mCk = i; } } else { if (mvRk < ma) { mvRk = ma; mRk = i; } }
-                if (i < l) { if (mvCl < mb) { mvCl = mb; mCl = i; } } else { if (mvRl < mb) { mvRl = mb; mRl = i; } }
+                // branch-free on purpose (one basic block per rotation lets the scheduler overlap the independent
+                // V update with these dependent chains): for i == k and i == l the pair is redirected to the thread's
+                // spare slot, where garbage is rotated and never read back
+                const bool act = (i != k) & (i != l);
+                double* pa = (i < k) ? (mk_lt + jt_offm(i < 8 ? i : 0) * S) : (mk_gt + i * S);
+                double* pb = (i < l) ? (ml_lt + jt_offm(i < 8 ? i : 0) * S) : (ml_gt + i * S);
+                pa = act ? pa : spare; pb = act ? pb : spare;
+                const double a0 = *pa, b0 = *pb;
+                const double na = a0 * c - b0 * s, nb = a0 * s + b0 * c;
+                *pa = na; *pb = nb;
+                // |A| on the line of k resp. l at the other index i; A[k][l] = 0 belongs to row k and to column l;
+                // i == idx is no element (-1 never wins a scan, nor does it need a first-element special case)
+                const double ma = act ? fabs(na) : ((i == l) ? 0.0 : -1.0);
+                const double mb = act ? fabs(nb) : ((i == k) ? 0.0 : -1.0);
+                // serial scans in ascending i: columns (i < idx), then rows (i > idx)
+                const bool ck = i < k, cl = i < l;
+                const bool tCk = ck & (mvCk < ma), tRk = (!ck) & (mvRk < ma);
+                const bool tCl = cl & (mvCl < mb), tRl = (!cl) & (mvRl < mb);
+                mvCk = tCk ? ma : mvCk; mCk = tCk ? i : mCk;
+                mvRk = tRk ? ma : mvRk; mRk = tRk ? i : mRk;
+                mvCl = tCl ? mb : mvCl; mCl = tCl ? i : mCl;
+                mvRl = tRl ? mb : mvRl; mRl = tRl ? i : mRl;
             }
             {
                 double* const vk = m + (JT_V + 9 * k) * S;

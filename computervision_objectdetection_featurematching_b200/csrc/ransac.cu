@@ -431,7 +431,8 @@ __global__ void __launch_bounds__(HYPT_THREADS, 1)
 ransac_hyp_t_kernel(RansacWork w, int round_base, int round_len)
 {
     extern __shared__ double jt_smem[];
-    const int64_t h = (int64_t)blockIdx.x * HYPT_THREADS + threadIdx.x;
+    const int64_t h0 = (int64_t)blockIdx.x * HYPT_THREADS;
+    const int64_t h = h0 + threadIdx.x;
     const int set = (int)(h / round_len);
     const int iter = round_base + (int)(h - (int64_t)set * round_len);
     bool live = set < w.n_sets;
@@ -442,7 +443,7 @@ ransac_hyp_t_kernel(RansacWork w, int round_base, int round_len)
         live = iter < w.n_samples[set] && iter < w.niters_cur[set];
         pts = w.pts + w.starts[set];
     }
-    if (!__any_sync(0xffffffffu, live)) return;                 // warp-uniform; the kernel has no block-wide barrier
+    if (!__syncthreads_or(live)) return;                        // block-uniform
     float ms1[8], ms2[8];
     #pragma unroll
     for (int i = 0; i < 8; i++) { ms1[i] = 0.f; ms2[i] = 0.f; }
@@ -455,23 +456,43 @@ ransac_hyp_t_kernel(RansacWork w, int round_base, int round_len)
             ms1[2 * i] = q.x; ms1[2 * i + 1] = q.y; ms2[2 * i] = q.z; ms2[2 * i + 1] = q.w;
         }
     }
-    double H[9];
-    const bool valid = run_kernel4_thread<HYPT_THREADS>(ms1, ms2, H, jt_smem + threadIdx.x, live, WarpAny());
-    if (!live) return;
-    int cnt = -1;
-    if (valid) {
-        float Hf[8];
+    float Hf[8];
+    bool valid;
+    {
+        double H[9];
+        valid = run_kernel4_thread<HYPT_THREADS>(ms1, ms2, H, jt_smem + threadIdx.x, live, WarpAny());
         #pragma unroll
-        for (int i = 0; i < 8; i++) Hf[i] = (float)H[i];
-        cnt = 0;
-        #pragma unroll 4
-        for (int i = 0; i < n; i++) {
-            const float4 q = __ldg(pts + i);
-            cnt += reproj_err(Hf, q.x, q.y, q.z, q.w) <= w.thr2 ? 1 : 0;     // NaN -> not an inlier
-        }
-        if (w.scored_pts) atomicAdd(w.scored_pts, (unsigned long long)n);
+        for (int i = 0; i < 8; i++) Hf[i] = valid ? (float)H[i] : 0.f;
     }
-    w.counts[(size_t)set * w.max_iters + iter] = cnt;
+    // ---- scoring: the matrix state is dead, the CTA's shared memory becomes a staging buffer for the
+    //      correspondences of the (one or two, rarely more) sets its hypotheses belong to ----
+    constexpr int STAGE_PTS = HYPT_SMEM / 16;                   // 14 112 correspondences
+    float4* stage = reinterpret_cast<float4*>(jt_smem);
+    const int set_first = (int)(h0 / round_len);
+    const int set_last = min((int)((h0 + HYPT_THREADS - 1) / round_len), w.n_sets - 1);
+    int cnt = 0;
+    for (int s = set_first; s <= set_last; s++) {
+        const int ns = w.counts_n[s];
+        const float4* __restrict__ ps = w.pts + w.starts[s];
+        const bool mine = live && valid && set == s;
+        for (int base = 0; base < ns; base += STAGE_PTS) {
+            const int m = min(STAGE_PTS, ns - base);
+            __syncthreads();                                    // previous contents (matrix state or chunk) are consumed
+            for (int i = threadIdx.x; i < m; i += HYPT_THREADS) stage[i] = ps[base + i];
+            __syncthreads();
+            if (mine) {
+                #pragma unroll 4
+                for (int i = 0; i < m; i++) {
+                    const float4 q = stage[i];                  // same address in every lane: broadcast
+                    cnt += reproj_err(Hf, q.x, q.y, q.z, q.w) <= w.thr2 ? 1 : 0;     // NaN -> not an inlier
+                }
+            }
+        }
+    }
+    if (live) {
+        w.counts[(size_t)set * w.max_iters + iter] = valid ? cnt : -1;
+        if (w.scored_pts && valid) atomicAdd(w.scored_pts, (unsigned long long)n);
+    }
 }
 
 // ---- 3. select kernel: the serial scan of RANSACPointSetRegistrator::run --------------------------
