@@ -266,10 +266,16 @@ int cvg_last_timing(const cvg_ctx* c, float* m, float* r, float* t)
 // ---------------------------------------------------------------------------------------------------
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-static int ensure_rng(cvg_ctx* c, int max_iters)
+constexpr int64_t RNG_TABLE_CAP = 1LL << 28;                    // 1 GiB of draws
+
+// The raw cv::RNG stream of the fixed seed as a device table.  An accepted 4-point sample costs 4 draws plus the
+// draws of the attempts checkSubset rejected before it (5-8 attempts on outlier-heavy sets), so the table is sized
+// at 48 draws per iteration; a call that still runs out grows it (min_len) and repeats the verify stage.
+static int ensure_rng(cvg_ctx* c, int max_iters, int64_t min_len = 0)
 {
-    int64_t want = std::max<int64_t>(1 << 20, (int64_t)max_iters * 6 + (1 << 16));
-    if (want > 0x7fff0000LL) want = 0x7fff0000LL;
+    int64_t want = std::max<int64_t>(1 << 20, (int64_t)max_iters * 48 + (1 << 16));
+    want = std::max(want, min_len);
+    if (want > RNG_TABLE_CAP) want = RNG_TABLE_CAP;
     if (c->rng_len >= want) return CVG_OK;
     std::vector<uint32_t> tab((size_t)want);
     uint64_t state = 0xFFFFFFFFFFFFFFFFull;                     // RNG rng((uint64)-1), SURVEY App. B.2
@@ -277,6 +283,7 @@ static int ensure_rng(cvg_ctx* c, int max_iters)
         state = (uint64_t)(uint32_t)state * 4164903690U + (uint32_t)(state >> 32);
         tab[(size_t)i] = (uint32_t)state;
     }
+    CU_CHECK(cudaStreamSynchronize(c->stream));
     if (c->d_rng) cudaFree(c->d_rng);
     c->d_rng = nullptr; c->rng_len = 0;
     CU_CHECK(cudaMalloc(&c->d_rng, (size_t)want * 4));
@@ -446,6 +453,8 @@ static int run_ransac(cvg_ctx* c, const float4* d_pts, const int64_t* d_starts, 
     w.sel = c->sel.as<int32_t>(); w.H = c->H.as<double>(); w.mask = c->mask.as<uint8_t>();
     w.ransac_mask = want_rmask ? c->rmask.as<uint8_t>() : nullptr;
     w.found = c->found.as<int32_t>(); w.status_flags = c->sflags.as<int32_t>();
+    w.err_flag = c->d_flags + 4;
+    CU_CHECK(cudaMemsetAsync(c->d_flags + 4, 0, 4, c->stream));
     w.scored_pts = c->timing ? c->d_scored : nullptr;
     if (c->timing) CU_CHECK(cudaMemsetAsync(c->d_scored, 0, 8, c->stream));
     c->launches += launch_ransac(w, c->stream, c->timing ? c->hyp_ev : nullptr, &c->hyp_rounds);
@@ -634,23 +643,30 @@ int cvg_find_homography_batch(cvg_ctx* c, const float* src_xy, const float* dst_
     CU_CHECK(cudaMemcpyAsync(c->counts_n.p, cnts.data(), (size_t)n_sets * 4, cudaMemcpyHostToDevice, c->stream));
     launch_pack_points(c->src.as<float>(), c->dst.as<float>(), total, c->pts.as<float4>(), c->stream);
     c->launches++;
-    if (c->timing) cudaEventRecord(c->ev[0], c->stream);
-    rc = run_ransac(c, c->pts.as<float4>(), c->starts.as<int64_t>(), c->counts_n.as<int32_t>(), n_sets, max_n, total, p,
-                    ransac_mask != nullptr);
-    if (rc) return rc;
-    if (c->timing) cudaEventRecord(c->ev[1], c->stream);
-    if (H) CU_CHECK(cudaMemcpyAsync(H, c->H.p, (size_t)n_sets * 72, cudaMemcpyDeviceToHost, c->stream));
-    if (mask && total > 0) CU_CHECK(cudaMemcpyAsync(mask, c->mask.p, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
-    if (ransac_mask && total > 0) CU_CHECK(cudaMemcpyAsync(ransac_mask, c->rmask.p, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
-    if (found) CU_CHECK(cudaMemcpyAsync(found, c->found.p, (size_t)n_sets * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (iters) CU_CHECK(cudaMemcpyAsync(iters, c->iters_run.p, (size_t)n_sets * 4, cudaMemcpyDeviceToHost, c->stream));
     std::vector<int32_t> sflags(n_sets);
-    CU_CHECK(cudaMemcpyAsync(sflags.data(), c->sflags.p, (size_t)n_sets * 4, cudaMemcpyDeviceToHost, c->stream));
-    rc = sync_and_check(c);
-    if (rc) return rc;
+    for (int attempt = 0;; attempt++) {
+        if (c->timing) cudaEventRecord(c->ev[0], c->stream);
+        rc = run_ransac(c, c->pts.as<float4>(), c->starts.as<int64_t>(), c->counts_n.as<int32_t>(), n_sets, max_n, total, p,
+                        ransac_mask != nullptr);
+        if (rc) return rc;
+        if (c->timing) cudaEventRecord(c->ev[1], c->stream);
+        if (H) CU_CHECK(cudaMemcpyAsync(H, c->H.p, (size_t)n_sets * 72, cudaMemcpyDeviceToHost, c->stream));
+        if (mask && total > 0) CU_CHECK(cudaMemcpyAsync(mask, c->mask.p, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+        if (ransac_mask && total > 0) CU_CHECK(cudaMemcpyAsync(ransac_mask, c->rmask.p, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+        if (found) CU_CHECK(cudaMemcpyAsync(found, c->found.p, (size_t)n_sets * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (iters) CU_CHECK(cudaMemcpyAsync(iters, c->iters_run.p, (size_t)n_sets * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU_CHECK(cudaMemcpyAsync(sflags.data(), c->sflags.p, (size_t)n_sets * 4, cudaMemcpyDeviceToHost, c->stream));
+        rc = sync_and_check(c);
+        if (rc) return rc;
+        int bad = -1;
+        for (int k = 0; k < n_sets && bad < 0; k++) if (sflags[k] & 1) bad = k;
+        if (bad < 0) break;
+        if (c->rng_len >= RNG_TABLE_CAP || attempt >= 4)
+            return set_err(CVG_ERR_LIMIT, "set %d: RNG draw table exhausted (pathological rejection rate)", bad);
+        rc = ensure_rng(c, p->max_iters, c->rng_len * 4);       // more draws, then the whole verify stage again
+        if (rc) return rc;
+    }
     if (c->timing) { cudaEventElapsedTime(&c->t_ransac, c->ev[0], c->ev[1]); c->t_match = 0; c->t_total = c->t_ransac; }
-    for (int k = 0; k < n_sets; k++)
-        if (sflags[k] & 1) return set_err(CVG_ERR_LIMIT, "set %d: RNG draw table exhausted (pathological rejection rate)", k);
     return CVG_OK;
 }
 
@@ -726,29 +742,38 @@ static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, Tra
     if (c->timing) cudaEventRecord(c->ev[1], c->stream);
     int max_view = 0;
     for (int v = 0; v < V; v++) max_view = std::max(max_view, m->view_offsets[v + 1] - m->view_offsets[v]);
-    rc = run_ransac(c, c->pts.as<float4>(), c->starts.as<int64_t>(), c->counts_n.as<int32_t>(), P, max_view,
-                    (int64_t)rows, &p->ransac, false);
-    if (rc) return rc;
-    GateWork g;
-    g.n_pairs = P; g.pts = c->pts.as<float4>(); g.starts = c->starts.as<int64_t>(); g.counts_n = c->counts_n.as<int32_t>();
-    g.mask = c->mask.as<uint8_t>(); g.found = c->found.as<int32_t>(); g.H = c->H.as<double>();
-    g.iters_run = c->iters_run.as<int32_t>(); g.pair_scale = d_scales;
-    g.min_inliers = p->min_inliers; g.det_lo = p->det_lo; g.det_hi = p->det_hi;
-    g.results = c->results.as<cvg_pair_result>();
-    g.inlier_xy = host_needs_inliers ? c->inl_xy.as<float>() : nullptr; g.inlier_count = c->inl_cnt.as<int32_t>();
-    launch_gates(g, c->stream);
-    c->launches++;
-    if (c->timing) cudaEventRecord(c->ev[2], c->stream);
-    CU_CHECK(cudaGetLastError());
-    CU_CHECK(cudaMemcpyAsync(per_pair, c->results.p, (size_t)P * sizeof(cvg_pair_result), cudaMemcpyDeviceToHost, c->stream));
-    if (host_needs_inliers) {
-        CU_CHECK(cudaMemcpyAsync(inlier_counts, c->inl_cnt.p, (size_t)P * 4, cudaMemcpyDeviceToHost, c->stream));
-        CU_CHECK(cudaMemcpyAsync(inlier_xy, c->inl_xy.p, rows * 8, cudaMemcpyDeviceToHost, c->stream));
-    }
     int flag = 0;
-    if (path == 0) CU_CHECK(cudaMemcpyAsync(&flag, c->d_flags + 2, 4, cudaMemcpyDeviceToHost, c->stream));
-    rc = sync_and_check(c);
-    if (rc) return rc;
+    for (int attempt = 0;; attempt++) {
+        rc = run_ransac(c, c->pts.as<float4>(), c->starts.as<int64_t>(), c->counts_n.as<int32_t>(), P, max_view,
+                        (int64_t)rows, &p->ransac, false);
+        if (rc) return rc;
+        GateWork g;
+        g.n_pairs = P; g.pts = c->pts.as<float4>(); g.starts = c->starts.as<int64_t>(); g.counts_n = c->counts_n.as<int32_t>();
+        g.mask = c->mask.as<uint8_t>(); g.found = c->found.as<int32_t>(); g.H = c->H.as<double>();
+        g.iters_run = c->iters_run.as<int32_t>(); g.pair_scale = d_scales;
+        g.min_inliers = p->min_inliers; g.det_lo = p->det_lo; g.det_hi = p->det_hi;
+        g.results = c->results.as<cvg_pair_result>();
+        g.inlier_xy = host_needs_inliers ? c->inl_xy.as<float>() : nullptr; g.inlier_count = c->inl_cnt.as<int32_t>();
+        launch_gates(g, c->stream);
+        c->launches++;
+        if (c->timing) cudaEventRecord(c->ev[2], c->stream);
+        CU_CHECK(cudaGetLastError());
+        CU_CHECK(cudaMemcpyAsync(per_pair, c->results.p, (size_t)P * sizeof(cvg_pair_result), cudaMemcpyDeviceToHost, c->stream));
+        if (host_needs_inliers) {
+            CU_CHECK(cudaMemcpyAsync(inlier_counts, c->inl_cnt.p, (size_t)P * 4, cudaMemcpyDeviceToHost, c->stream));
+            CU_CHECK(cudaMemcpyAsync(inlier_xy, c->inl_xy.p, rows * 8, cudaMemcpyDeviceToHost, c->stream));
+        }
+        int rng_short = 0;
+        CU_CHECK(cudaMemcpyAsync(&rng_short, c->d_flags + 4, 4, cudaMemcpyDeviceToHost, c->stream));
+        if (path == 0) CU_CHECK(cudaMemcpyAsync(&flag, c->d_flags + 2, 4, cudaMemcpyDeviceToHost, c->stream));
+        rc = sync_and_check(c);
+        if (rc) return rc;
+        if (!(rng_short & 1)) break;
+        if (c->rng_len >= RNG_TABLE_CAP || attempt >= 4)
+            return set_err(CVG_ERR_LIMIT, "RNG draw table exhausted (pathological rejection rate)");
+        rc = ensure_rng(c, p->ransac.max_iters, c->rng_len * 4);   // more draws, then the verify stage again
+        if (rc) return rc;
+    }
     c->last_match_path = path == 0 ? (flag ? 2 : 1) : path;
     if (c->timing) {
         c->t_hyp = 0;

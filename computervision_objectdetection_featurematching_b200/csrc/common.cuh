@@ -97,6 +97,7 @@ struct RansacWork {
     uint8_t* ransac_mask;       // [total] or NULL
     int32_t* found;             // [P]
     int32_t* status_flags;      // [P] bit0: rng table exhausted
+    int* err_flag;              // one word, OR of all status_flags (or NULL)
 };
 // returns the number of kernel launches; hyp_events (optional, 32 events) bracket the hypothesis kernel of each round
 int  launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events = nullptr, int* n_hyp_rounds = nullptr);

@@ -240,7 +240,7 @@ ransac_sample_kernel(RansacWork w, int round_base, int round_end)
     }
     if (threadIdx.x == 0) {
         w.n_samples[set] = iter;
-        if (flags) w.status_flags[set] = flags;
+        if (flags) { w.status_flags[set] = flags; if (w.err_flag) atomicOr(w.err_flag, flags); }
         w.smp_state[2 * set] = base;
         w.smp_state[2 * set + 1] = finished ? -1 : attempts;
     }

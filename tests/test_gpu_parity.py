@@ -222,6 +222,84 @@ def test_find_homography_no_early_stop_scores_every_hypothesis(ctx, api, oracle)
     assert mask.sum() >= tr["mask"].sum()                    # more hypotheses can only improve the best count
 
 
+def test_find_homography_batch_shapes_thread_kernel(ctx, api, oracle):
+    """Shapes that exercise the thread-per-hypothesis kernel's block layout: tiny rounds (many sets per CTA), sets far
+    larger than the shared-memory staging buffer (chunked scoring), and wildly mixed set sizes in one batch — RANSAC-stage
+    masks bit-exact against the oracle, iteration counts equal."""
+    rng = np.random.default_rng(7007)
+    cases = [
+        dict(sizes=[int(v) for v in rng.integers(5, 60, size=700)], max_iters=10),      # round_len 10: ~22 sets per CTA
+        dict(sizes=[20000, 15000, 30001, 14112, 14113, 9, 4, 250], max_iters=600),      # > 14 112 points: staged in chunks
+        dict(sizes=[4, 5, 6, 3000, 7, 64, 1, 0, 2, 800] * 3, max_iters=2000),           # mixed, incl. < 4 points
+    ]
+    for case in cases:
+        srcs, dsts, offs = [], [], [0]
+        for n in case["sizes"]:
+            if n >= 4:
+                s, d, _ = synth.correspondences(rng, n, float(rng.uniform(0.25, 0.9)))
+            else:
+                s = rng.uniform(0, 600, size=(n, 2)).astype(np.float32); d = s + np.float32(3)
+            srcs.append(s); dsts.append(d); offs.append(offs[-1] + n)
+        out = ctx.find_homography_batch(np.concatenate(srcs), np.concatenate(dsts), offs, max_iters=case["max_iters"],
+                                        want_ransac_mask=True)
+        for k, n in enumerate(case["sizes"]):
+            a, b = offs[k], offs[k + 1]
+            if n < 4:
+                assert not out["found"][k]
+                continue
+            ref = oracle.find_homography(srcs[k], dsts[k], max_iters=case["max_iters"])
+            assert out["found"][k] == ref["found"], (case["max_iters"], k, n)
+            assert np.array_equal(out["ransac_mask"][a:b], ref["ransac_mask"]), (case["max_iters"], k, n)
+            if n > 4:
+                assert out["iters"][k] == ref["info"]["iters_run"], (case["max_iters"], k, n)
+            if ref["found"] and n < 100:
+                assert np.array_equal(out["mask"][a:b], ref["mask"]), (case["max_iters"], k, n)
+                assert np.allclose(out["H"][k], ref["H"], rtol=1e-9, atol=1e-12), (case["max_iters"], k, n)
+
+
+def test_rng_table_grows_on_high_rejection_rate(api, oracle):
+    """85 % of the points on one line: ~95 % of the 4-point attempts fail checkSubset, so an iteration consumes ~80
+    draws of the cv::RNG stream instead of ~5.  The draw table (48 per iteration) runs out, is regrown, and the verify
+    stage repeats — the result must still be the oracle's."""
+    rng = np.random.default_rng(8008)
+    n = 200
+    src, dst, _ = synth.correspondences(rng, n, 0.5)
+    line = rng.random(n) < 0.85
+    t = rng.uniform(0, 600, size=int(line.sum())).astype(np.float32)
+    src[line] = np.c_[t, 0.5 * t + 20]                                    # collinear in src only: never inliers
+    ref = oracle.find_homography(src, dst, max_iters=30000, conf=0.9999999)
+    assert ref["info"]["draws"] > 30000 * 48 + (1 << 16)                 # really beyond the initial table
+    with api.Context(0) as c:
+        H, mask, rmask = c.find_homography(src, dst, max_iters=30000, confidence=0.9999999, want_ransac_mask=True)
+    assert (H is not None) == ref["found"]
+    assert np.array_equal(rmask, ref["ransac_mask"]) and np.array_equal(mask, ref["mask"])
+
+
+def test_hypothesis_kernel_variants_agree(api):
+    """CVG_HYP_MODE selects the kernel (1 warp, 2 eight-lane groups, 4 thread per hypothesis): identical counts ->
+    identical winners, masks and H, checked through a subprocess per mode."""
+    import json, os, subprocess, sys
+    code = (
+        "import sys, json, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from computervision_objectdetection_featurematching_b200 import api, synth\n"
+        "rng = np.random.default_rng(9009); srcs=[]; dsts=[]; offs=[0]\n"
+        "for _ in range(40):\n"
+        "    n = int(rng.integers(4, 400)); s, d, _ = synth.correspondences(rng, n, float(rng.uniform(0.2, 0.9)), dup=float(rng.choice([0, 0.4])))\n"
+        "    srcs.append(s); dsts.append(d); offs.append(offs[-1] + n)\n"
+        "c = api.Context(0); o = c.find_homography_batch(np.concatenate(srcs), np.concatenate(dsts), offs, want_ransac_mask=True)\n"
+        "import hashlib\n"
+        "print(json.dumps({k: hashlib.sha256(np.ascontiguousarray(o[k]).tobytes()).hexdigest() for k in ('H','mask','ransac_mask','iters','found')}))\n"
+    ) % os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    digests = []
+    for mode in ("1", "2", "4"):
+        env = dict(os.environ, CVG_HYP_MODE=mode)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert digests[0] == digests[1] == digests[2]
+
+
 # ---------------------------------------------------------------- fused path on real features
 def test_detect_pairs_real_dataset_vs_cv2_goldens(ctx, api, feats, gpairs):
     """Golden real pairs (89 views x 10 scene-scales): gate status, counts, inlier masks (through the
