@@ -20,7 +20,7 @@ ACCEPT, LT4_MATCHES, H_EMPTY, LT4_INLIERS, DET_REJECT = range(5)
 RANSAC_NO_EARLY_STOP = 1
 RANSAC_NO_REFINE = 2
 FORCE_EXACT_MATCH = 1
-PATH_TENSOR, PATH_EXACT = 1, 2
+PATH_TENSOR, PATH_EXACT, PATH_TENSOR_RERANK = 1, 2, 3   # cvg_last_match_path
 
 PAIR_DTYPE = np.dtype([("status", "<i4"), ("n_good", "<i4"), ("n_inliers", "<i4"), ("ransac_iters", "<i4"),
                        ("H", "<f8", (9,)), ("det", "<f8")])
@@ -176,6 +176,11 @@ class Context:
     @property
     def last_match_path(self):
         return self.lib.cvg_last_match_path(self.handle)
+
+    @property
+    def last_match_fallback_rows(self):
+        """Rows of the last candidate-path call that were redone by the exact fallback kernel."""
+        return int(self.lib.cvg_last_match_fallback_rows(self.handle))
 
     @property
     def stream(self):

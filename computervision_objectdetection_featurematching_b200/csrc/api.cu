@@ -88,23 +88,25 @@ struct TrainSet {                      // a prepared set of train segments on th
     int max_rows = 0;
     float* d_f32 = nullptr;            // [rows_total, 128]
     __nv_bfloat16* d_b = nullptr;      // [rows_pad_total, 128]
+    __nv_bfloat16* d_blo = nullptr;    // [rows_pad_total, 128] lo half of the split operand (zero for integer rows)
     __nv_bfloat16* d_aug = nullptr;    // [rows_pad_total, 16]
     float* d_kpt = nullptr;            // [rows_total, 2] or null
     int64_t* d_kpt_offsets = nullptr;  // [S+1]
-    int nonint = -1;                   // host-known flag (-1 unknown)
+    int nonint = -1;                   // host-known row-kind bits of prep_rows_kernel (-1 unknown: decided on the device)
+    int* d_tnmax = nullptr;            // device word: max ||t||^2 as float bits (error bound of the candidate path)
 };
 
 struct cvg_models {
     int n_rows = 0, n_pad = 0, n_views = 0;
     std::vector<int32_t> view_offsets, view_model;
-    float* d_f32 = nullptr; __nv_bfloat16* d_b = nullptr; __nv_bfloat16* d_aug = nullptr;
+    float* d_f32 = nullptr; __nv_bfloat16* d_b = nullptr; __nv_bfloat16* d_blo = nullptr; __nv_bfloat16* d_aug = nullptr;
     float* d_norm = nullptr; float* d_kpt = nullptr; int32_t* d_view_offsets = nullptr;
     int nonint = 0;
 };
 
 struct cvg_scenes {
     TrainSet ts;
-    DevBuf f32, b, aug, kpt, kptoff;
+    DevBuf f32, b, blo, aug, kpt, kptoff;
     int* d_flag = nullptr;             // non-integer flag of this batch (tail of kptoff)
     cudaEvent_t ready = nullptr;       // set by cvg_scenes_upload_async: upload + conversion finished
     // cached match plan for a given model set
@@ -117,7 +119,9 @@ struct cvg_ctx {
     int device = 0; unsigned flags = 0; int n_sms = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;                // uploads of cvg_scenes_upload_async (overlap with compute)
-    int* d_flags = nullptr;            // [0] train nonint, [1] query nonint, [8..16) kernel debug words
+    int* d_flags = nullptr;            // [0] train row kinds, [1] query row kinds, [2] match path (0 tensor exact, 1 tensor
+                                       // candidates + re-rank, 2 exact SIMT), [3] raw-query kinds, [4] RNG table short,
+                                       // [5] max ||t||^2 bits, [6] fallback row count, [8..16) kernel debug words
     uint32_t* d_rng = nullptr; int64_t rng_len = 0;
     int last_match_path = 0; int64_t launches = 0;
     int timing = 0; float t_match = 0, t_ransac = 0, t_total = 0;
@@ -126,9 +130,10 @@ struct cvg_ctx {
     int hyp_rounds = 0; float t_hyp = 0; int hyp_launches = 0; unsigned long long scored_pts = 0;
     unsigned long long* d_scored = nullptr;
     // scratch
-    DevBuf q_f32, q_b, q_aug, q_norm;                  // raw-query path
-    DevBuf t_f32, t_b, t_aug, t_kpt, t_kptoff;         // per-call train path
+    DevBuf q_f32, q_b, q_blo, q_aug, q_norm;           // raw-query path
+    DevBuf t_f32, t_b, t_blo, t_aug, t_kpt, t_kptoff;  // per-call train path
     DevBuf units, dir, parts, idx, dist, accept;
+    DevBuf parts4, segdev, fb;                         // candidate path: Top4 records, segment table, unproven rows
     DevBuf pts, starts, counts_n, sample_pos, n_samples, counts, best_iter, best_count, iters_run, niters_cur, smp_state, sel;
     DevBuf H, mask, rmask, found, sflags, results, inl_xy, inl_cnt, scales, src, dst;
     BufPool pool;                                      // recycled buffers of freed scene batches
@@ -223,8 +228,8 @@ void cvg_destroy(cvg_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
-    DevBuf* bufs[] = { &c->q_f32, &c->q_b, &c->q_aug, &c->q_norm, &c->t_f32, &c->t_b, &c->t_aug, &c->t_kpt, &c->t_kptoff,
-                       &c->units, &c->dir, &c->parts, &c->idx, &c->dist, &c->accept, &c->pts, &c->starts, &c->counts_n,
+    DevBuf* bufs[] = { &c->q_f32, &c->q_b, &c->q_blo, &c->q_aug, &c->q_norm, &c->t_f32, &c->t_b, &c->t_blo, &c->t_aug, &c->t_kpt, &c->t_kptoff,
+                       &c->units, &c->dir, &c->parts, &c->parts4, &c->segdev, &c->fb, &c->idx, &c->dist, &c->accept, &c->pts, &c->starts, &c->counts_n,
                        &c->sample_pos, &c->n_samples, &c->counts, &c->best_iter, &c->best_count, &c->iters_run, &c->niters_cur, &c->smp_state, &c->sel,
                        &c->H, &c->mask, &c->rmask, &c->found, &c->sflags, &c->results, &c->inl_xy, &c->inl_cnt,
                        &c->scales, &c->src, &c->dst };
@@ -242,6 +247,14 @@ void cvg_destroy(cvg_ctx* c)
 }
 
 int cvg_last_match_path(const cvg_ctx* c) { return c ? c->last_match_path : 0; }
+int cvg_last_match_fallback_rows(const cvg_ctx* c)
+{
+    if (!c || c->last_match_path != 3) return 0;
+    int n = 0;
+    cudaSetDevice(c->device);
+    cudaMemcpy(&n, c->d_flags + 6, 4, cudaMemcpyDeviceToHost);
+    return n;
+}
 void* cvg_stream(const cvg_ctx* c) { return c ? (void*)c->stream : nullptr; }
 int cvg_last_hyp_stats(const cvg_ctx* c, float* hyp_ms, int* hyp_launches, uint64_t* scored_points)
 {
@@ -294,20 +307,22 @@ static int ensure_rng(cvg_ctx* c, int max_iters, int64_t min_len = 0)
 }
 
 // Prepare (convert) a train set that is already in device fp32 memory.
-static int prep_train(cvg_ctx* c, TrainSet& ts, DevBuf& b, DevBuf& aug, int flag_slot, bool pooled = false,
+static int prep_train(cvg_ctx* c, TrainSet& ts, DevBuf& b, DevBuf& blo, DevBuf& aug, int flag_slot, bool pooled = false,
                       cudaStream_t st = nullptr, int* d_flag = nullptr)
 {
     if (!st) st = c->stream;
     if (!d_flag) d_flag = c->d_flags + flag_slot;
+    if (!ts.d_tnmax) ts.d_tnmax = c->d_flags + 5;
+    CU_CHECK(cudaMemsetAsync(ts.d_tnmax, 0, 4, st));
     const size_t nb = (size_t)std::max<int64_t>(ts.rows_pad_total, 1) * DIM * 2;
     const size_t na = (size_t)std::max<int64_t>(ts.rows_pad_total, 1) * KAUG * 2;
-    if (pooled) { CU_CHECK(c->pool.acquire(b, nb)); CU_CHECK(c->pool.acquire(aug, na)); }
-    else { CU_CHECK(b.ensure(nb)); CU_CHECK(aug.ensure(na)); }
-    ts.d_b = b.as<__nv_bfloat16>(); ts.d_aug = aug.as<__nv_bfloat16>();
+    if (pooled) { CU_CHECK(c->pool.acquire(b, nb)); CU_CHECK(c->pool.acquire(blo, nb)); CU_CHECK(c->pool.acquire(aug, na)); }
+    else { CU_CHECK(b.ensure(nb)); CU_CHECK(blo.ensure(nb)); CU_CHECK(aug.ensure(na)); }
+    ts.d_b = b.as<__nv_bfloat16>(); ts.d_blo = blo.as<__nv_bfloat16>(); ts.d_aug = aug.as<__nv_bfloat16>();
     for (const SegInfo& s : ts.segs) {
         const int n_pad = s.ct * TILE_N;
         launch_prep_rows(ts.d_f32 + s.f32_row0 * DIM, s.rows, n_pad, 1, ts.d_b + s.pad_row0 * DIM,
-                         ts.d_aug + s.pad_row0 * KAUG, nullptr, d_flag, st);
+                         ts.d_blo + s.pad_row0 * DIM, ts.d_aug + s.pad_row0 * KAUG, nullptr, d_flag, ts.d_tnmax, st);
         c->launches++;
     }
     CU_CHECK(cudaGetLastError());
@@ -331,7 +346,7 @@ static void layout_segments(TrainSet& ts, const int64_t* offsets, int n)
 }
 
 struct QuerySide {
-    const float* d_f32; const __nv_bfloat16* d_b; const __nv_bfloat16* d_aug; const float* d_norm;
+    const float* d_f32; const __nv_bfloat16* d_b; const __nv_bfloat16* d_blo; const __nv_bfloat16* d_aug; const float* d_norm;
     int row_begin, row_end;        // absolute rows matched
     int n_pad;                     // rows of the padded operand matrices
 };
@@ -381,39 +396,78 @@ static void build_plan(const QuerySide& q, const TrainSet& ts, int n_sms, std::v
     std::stable_sort(units.begin(), units.end(), [](const MatchUnit& a, const MatchUnit& b) { return a.n_tiles > b.n_tiles; });
 }
 
-// Launch the match kernels for a plan already on the device.  path_hint: 1 = tensor-core only,
-// 2 = exact only, 0 = decide on the device from d_flags[0] | d_flags[1].
+// Match paths.  Host-side hints / cvg_last_match_path: 1 = tensor cores, exact (integer descriptors), 2 = exact fp32
+// SIMT kernel, 3 = tensor cores, candidates + fp32 re-rank (non-integer descriptors), 0 = decided on the device.
+// The device word d_flags[2] holds 0 / 1 / 2 for tensor-exact / tensor-candidates / SIMT.
+static int path_from_kinds(unsigned ctx_flags, int q_kinds, int t_kinds)
+{
+    if (ctx_flags & CVG_FORCE_EXACT_MATCH) return 2;
+    if (t_kinds < 0 || q_kinds < 0) return 0;
+    const int k = q_kinds | t_kinds;
+    return (k & 2) ? 2 : ((k & 1) ? 3 : 1);
+}
+static int path_from_device_word(int w) { return w == 0 ? 1 : (w == 1 ? 3 : 2); }
+
+// Launch the match kernels for a plan already on the device.  With path_hint 0 all three variants are enqueued and
+// gate themselves on d_flags[2]; no host round trip.
 static int launch_match(cvg_ctx* c, const QuerySide& q, const TrainSet& ts, const MatchUnit* d_units, int n_units,
                         const MergeEntry* d_dir, int n_rb, float ratio, int path_hint, Top2* d_parts,
                         int32_t* d_idx, float* d_dist, uint8_t* d_accept)
 {
     const int nq = q.row_end - q.row_begin;
+    const int* gate = path_hint == 0 ? c->d_flags + 2 : nullptr;
+    const bool want_int = path_hint == 0 || path_hint == 1, want_cand = path_hint == 0 || path_hint == 3;
+    const bool want_simt = path_hint == 0 || path_hint == 2;
+    if (want_cand && n_units > 0) {
+        CU_CHECK(c->parts4.ensure((size_t)n_units * 4 * TILE_M * sizeof(Top4)));
+        CU_CHECK(c->segdev.ensure((size_t)ts.n_segs * sizeof(SegDev) + 16));
+        CU_CHECK(c->fb.ensure((size_t)ts.n_segs * std::max(nq, 1) * (sizeof(int2) + 16)));   // row list + two key arrays
+        std::vector<SegDev> sd((size_t)ts.n_segs);
+        for (int s = 0; s < ts.n_segs; s++) sd[(size_t)s] = SegDev{ ts.segs[(size_t)s].f32_row0, ts.segs[(size_t)s].rows, 0 };
+        CU_CHECK(h2d_small(c, c->segdev.p, sd.data(), sd.size() * sizeof(SegDev)));
+    }
     if (c->timing) cudaEventRecord(c->ev[3], c->stream);
     if (n_units > 0) {
-        if (path_hint != 2) {
-            TcOperands op{ q.d_b, q.d_aug, q.d_norm, q.n_pad, ts.d_b, ts.d_aug, (int)ts.rows_pad_total };
-            char err[256];
-            if (launch_match_tc(op, d_units, n_units, d_parts, path_hint == 0 ? c->d_flags + 2 : nullptr,
-                                c->d_flags + 8, c->n_sms, c->stream, err, sizeof err))
+        TcOperands op{ q.d_b, q.d_aug, q.d_norm, q.n_pad, ts.d_b, ts.d_aug, (int)ts.rows_pad_total, q.d_blo, ts.d_blo };
+        char err[256];
+        if (want_int) {
+            if (launch_match_tc(op, d_units, n_units, d_parts, 2, gate, 0, c->d_flags + 8, c->n_sms, c->stream, err, sizeof err))
                 return set_err(CVG_ERR_CUDA, "%s", err);
             c->launches++;
         }
-        if (path_hint != 1) {
-            launch_match_exact(q.d_f32, q.row_end, ts.d_f32, d_units, n_units, d_parts,
-                               path_hint == 0 ? c->d_flags + 2 : nullptr, c->stream);
+        if (want_cand) {
+            if (launch_match_tc(op, d_units, n_units, c->parts4.p, 4, gate, 1, c->d_flags + 8, c->n_sms, c->stream, err, sizeof err))
+                return set_err(CVG_ERR_CUDA, "%s", err);
+            c->launches++;
+        }
+        if (want_simt) {
+            launch_match_exact(q.d_f32, q.row_end, ts.d_f32, d_units, n_units, d_parts, gate, 2, c->stream);
             c->launches++;
         }
     }
     if (c->timing) cudaEventRecord(c->ev[4], c->stream);
-    launch_merge(d_parts, d_dir, ts.n_segs, n_rb, nq, ratio, d_idx, d_dist, d_accept, c->stream);
-    c->launches++;
+    if (want_int || want_simt || n_units == 0) {
+        launch_merge(d_parts, d_dir, ts.n_segs, n_rb, nq, ratio, d_idx, d_dist, d_accept, gate, 1, c->stream);
+        c->launches++;
+    }
+    if (want_cand && n_units > 0) {
+        const size_t n_rows_all = (size_t)ts.n_segs * std::max(nq, 1);
+        launch_merge4_rerank(c->parts4.as<Top4>(), d_dir, c->segdev.as<SegDev>(), ts.n_segs, n_rb, nq, ts.max_rows, ratio, q.d_f32,
+                             q.row_begin, ts.d_f32, q.d_norm, ts.d_tnmax ? ts.d_tnmax : c->d_flags + 5, d_idx, d_dist, d_accept,
+                             c->d_flags + 6, c->fb.as<int2>(),
+                             reinterpret_cast<unsigned long long*>(c->fb.as<int2>() + n_rows_all), gate, 1, c->n_sms, c->stream);
+        c->launches += 5;
+    }
     CU_CHECK(cudaGetLastError());
     return CVG_OK;
 }
 
-__global__ void combine_flags_kernel(int* f, const int* train_flag, int force_exact, int ignore_query_flag = 0)
+// d_flags[2] = match path word from the row kinds of both sides
+__global__ void combine_flags_kernel(int* f, const int* train_flag, int extra_kinds_or_force, int ignore_query_flag = 0)
 {
-    f[2] = (*train_flag | (ignore_query_flag ? 0 : f[1]) | force_exact) ? 1 : 0;
+    // extra_kinds_or_force: host-known kinds of the query side (bits 0-1) or 4 = force the SIMT kernel
+    const int k = *train_flag | (ignore_query_flag ? 0 : f[1]) | extra_kinds_or_force;
+    f[2] = (k & 6) ? 2 : ((k & 1) ? 1 : 0);
 }
 
 // Verify stage on a device correspondence pool.
@@ -500,6 +554,7 @@ int cvg_models_upload(cvg_ctx* c, const float* desc, const float* kpt_xy, const 
     if (view_model) m->view_model.assign(view_model, view_model + n_views);
     CU_CHECK(cudaMalloc(&m->d_f32, (size_t)m->n_pad * DIM * 4));
     CU_CHECK(cudaMalloc(&m->d_b, (size_t)m->n_pad * DIM * 2));
+    CU_CHECK(cudaMalloc(&m->d_blo, (size_t)m->n_pad * DIM * 2));
     CU_CHECK(cudaMalloc(&m->d_aug, (size_t)m->n_pad * KAUG * 2));
     CU_CHECK(cudaMalloc(&m->d_norm, (size_t)m->n_pad * 4));
     CU_CHECK(cudaMalloc(&m->d_kpt, (size_t)std::max(n, 1) * 8));
@@ -509,7 +564,7 @@ int cvg_models_upload(cvg_ctx* c, const float* desc, const float* kpt_xy, const 
     if (n > 0 && kpt_xy) CU_CHECK(cudaMemcpyAsync(m->d_kpt, kpt_xy, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
     CU_CHECK(cudaMemcpyAsync(m->d_view_offsets, view_offsets, (size_t)(n_views + 1) * 4, cudaMemcpyHostToDevice, c->stream));
     CU_CHECK(cudaMemsetAsync(c->d_flags + 1, 0, 4, c->stream));
-    launch_prep_rows(m->d_f32, n, m->n_pad, 0, m->d_b, m->d_aug, m->d_norm, c->d_flags + 1, c->stream);
+    launch_prep_rows(m->d_f32, n, m->n_pad, 0, m->d_b, m->d_blo, m->d_aug, m->d_norm, c->d_flags + 1, nullptr, c->stream);
     c->launches++;
     int flag = 0;
     CU_CHECK(cudaMemcpyAsync(&flag, c->d_flags + 1, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -523,7 +578,7 @@ void cvg_models_free(cvg_ctx* c, cvg_models* m)
 {
     if (!m) return;
     if (c) cudaSetDevice(c->device);
-    cudaFree(m->d_f32); cudaFree(m->d_b); cudaFree(m->d_aug); cudaFree(m->d_norm); cudaFree(m->d_kpt);
+    cudaFree(m->d_f32); cudaFree(m->d_b); cudaFree(m->d_blo); cudaFree(m->d_aug); cudaFree(m->d_norm); cudaFree(m->d_kpt);
     cudaFree(m->d_view_offsets);
     delete m;
 }
@@ -548,10 +603,10 @@ static int match_host_train(cvg_ctx* c, QuerySide q, int q_nonint, const float* 
     ts.d_f32 = c->t_f32.as<float>();
     if (n_train > 0) CU_CHECK(cudaMemcpyAsync(ts.d_f32, train, (size_t)n_train * DIM * 4, cudaMemcpyHostToDevice, c->stream));
     CU_CHECK(cudaMemsetAsync(c->d_flags, 0, 4, c->stream));
-    int rc = prep_train(c, ts, c->t_b, c->t_aug, 0);
+    int rc = prep_train(c, ts, c->t_b, c->t_blo, c->t_aug, 0);
     if (rc) return rc;
     CU_CHECK(cudaMemcpyAsync(c->d_flags + 1, &q_nonint, 4, cudaMemcpyHostToDevice, c->stream));
-    combine_flags_kernel<<<1, 1, 0, c->stream>>>(c->d_flags, c->d_flags, (c->flags & CVG_FORCE_EXACT_MATCH) ? 1 : 0);
+    combine_flags_kernel<<<1, 1, 0, c->stream>>>(c->d_flags, c->d_flags, (c->flags & CVG_FORCE_EXACT_MATCH) ? 4 : 0);
     c->launches++;
     std::vector<MatchUnit> units; std::vector<MergeEntry> dir; int n_rb;
     build_plan(q, ts, c->n_sms, units, dir, n_rb);
@@ -572,7 +627,7 @@ static int match_host_train(cvg_ctx* c, QuerySide q, int q_nonint, const float* 
     CU_CHECK(cudaMemcpyAsync(&flag, c->d_flags + 2, 4, cudaMemcpyDeviceToHost, c->stream));
     rc = sync_and_check(c);
     if (rc) return rc;
-    c->last_match_path = flag ? 2 : 1;
+    c->last_match_path = path_from_device_word(flag);
     if (c->timing) { cudaEventElapsedTime(&c->t_match, c->ev[3], c->ev[4]); c->t_ransac = 0; c->t_total = c->t_match; }
     return CVG_OK;
 }
@@ -585,7 +640,7 @@ int cvg_match_knn2(cvg_ctx* c, const cvg_models* m, int view, const float* train
     if (!c || !m) return set_err(CVG_ERR_INVALID, "cvg_match_knn2: NULL context/models");
     if (view < -1 || view >= m->n_views) return set_err(CVG_ERR_INVALID, "cvg_match_knn2: view %d of %d", view, m->n_views);
     CU_CHECK(cudaSetDevice(c->device));
-    QuerySide q{ m->d_f32, m->d_b, m->d_aug, m->d_norm, 0, m->n_rows, m->n_pad };
+    QuerySide q{ m->d_f32, m->d_b, m->d_blo, m->d_aug, m->d_norm, 0, m->n_rows, m->n_pad };
     if (view >= 0) { q.row_begin = m->view_offsets[view]; q.row_end = m->view_offsets[view + 1]; }
     return match_host_train(c, q, m->nonint, train, n_train, ratio, idx, dist, accept);
 }
@@ -599,17 +654,18 @@ int cvg_match_knn2_raw(cvg_ctx* c, const float* query, int n_query, const float*
     CU_CHECK(cudaSetDevice(c->device));
     const int n_pad = round_up(n_query, TILE_M);
     CU_CHECK(c->q_f32.ensure((size_t)n_pad * DIM * 4)); CU_CHECK(c->q_b.ensure((size_t)n_pad * DIM * 2));
+    CU_CHECK(c->q_blo.ensure((size_t)n_pad * DIM * 2));
     CU_CHECK(c->q_aug.ensure((size_t)n_pad * KAUG * 2)); CU_CHECK(c->q_norm.ensure((size_t)n_pad * 4));
     CU_CHECK(cudaMemcpyAsync(c->q_f32.p, query, (size_t)n_query * DIM * 4, cudaMemcpyHostToDevice, c->stream));
     CU_CHECK(cudaMemsetAsync(c->d_flags + 3, 0, 4, c->stream));
-    launch_prep_rows(c->q_f32.as<float>(), n_query, n_pad, 0, c->q_b.as<__nv_bfloat16>(), c->q_aug.as<__nv_bfloat16>(),
-                     c->q_norm.as<float>(), c->d_flags + 3, c->stream);
+    launch_prep_rows(c->q_f32.as<float>(), n_query, n_pad, 0, c->q_b.as<__nv_bfloat16>(), c->q_blo.as<__nv_bfloat16>(),
+                     c->q_aug.as<__nv_bfloat16>(), c->q_norm.as<float>(), c->d_flags + 3, nullptr, c->stream);
     c->launches++;
     int qflag = 0;
     CU_CHECK(cudaMemcpyAsync(&qflag, c->d_flags + 3, 4, cudaMemcpyDeviceToHost, c->stream));
     CU_CHECK(cudaStreamSynchronize(c->stream));
-    QuerySide q{ c->q_f32.as<float>(), c->q_b.as<__nv_bfloat16>(), c->q_aug.as<__nv_bfloat16>(), c->q_norm.as<float>(),
-                 0, n_query, n_pad };
+    QuerySide q{ c->q_f32.as<float>(), c->q_b.as<__nv_bfloat16>(), c->q_blo.as<__nv_bfloat16>(), c->q_aug.as<__nv_bfloat16>(),
+                 c->q_norm.as<float>(), 0, n_query, n_pad };
     return match_host_train(c, q, qflag, train, n_train, ratio, idx, dist, accept);
 }
 
@@ -691,7 +747,7 @@ static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, Tra
     const int S = ts.n_segs, V = m->n_views, nq = m->n_rows;
     const int P = S * V;
     if (P == 0) return CVG_OK;
-    QuerySide q{ m->d_f32, m->d_b, m->d_aug, m->d_norm, 0, nq, m->n_pad };
+    QuerySide q{ m->d_f32, m->d_b, m->d_blo, m->d_aug, m->d_norm, 0, nq, m->n_pad };
     int n_units = 0, n_rb = 0;
     const MatchUnit* d_units; const MergeEntry* d_dir;
     if (cache && cache->plan_models == m) {
@@ -724,7 +780,7 @@ static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, Tra
     if (host_needs_inliers) CU_CHECK(c->inl_xy.ensure(rows * 8));
 
     if (c->timing) cudaEventRecord(c->ev[0], c->stream);
-    const int path = (c->flags & CVG_FORCE_EXACT_MATCH) ? 2 : ((m->nonint || ts.nonint > 0) ? 2 : (ts.nonint == 0 ? 1 : 0));
+    const int path = path_from_kinds(c->flags, m->nonint, ts.nonint);
     if (path == 0) {
         combine_flags_kernel<<<1, 1, 0, c->stream>>>(c->d_flags, (cache && cache->d_flag) ? cache->d_flag : c->d_flags, m->nonint, 1);
         c->launches++;
@@ -774,7 +830,7 @@ static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, Tra
         rc = ensure_rng(c, p->ransac.max_iters, c->rng_len * 4);   // more draws, then the verify stage again
         if (rc) return rc;
     }
-    c->last_match_path = path == 0 ? (flag ? 2 : 1) : path;
+    c->last_match_path = path == 0 ? path_from_device_word(flag) : path;
     if (c->timing) {
         c->t_hyp = 0;
         for (int r = 0; r < c->hyp_rounds; r++) { float t = 0; cudaEventElapsedTime(&t, c->hyp_ev[2 * r], c->hyp_ev[2 * r + 1]); c->t_hyp += t; }
@@ -822,7 +878,7 @@ int cvg_detect_pairs(cvg_ctx* c, const cvg_models* m, const float* scene_desc, c
     std::vector<float> scales(std::max(V, 1), scale);
     CU_CHECK(cudaMemcpyAsync(c->scales.p, scales.data(), scales.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CU_CHECK(cudaMemsetAsync(c->d_flags, 0, 4, c->stream));
-    rc = prep_train(c, ts, c->t_b, c->t_aug, 0);
+    rc = prep_train(c, ts, c->t_b, c->t_blo, c->t_aug, 0);
     if (rc) return rc;
     ts.nonint = -1;                                    // decided on the device
     const bool want_inl = inlier_scene_xy != nullptr && inlier_offsets != nullptr;
@@ -863,12 +919,13 @@ static int scenes_upload_impl(cvg_ctx* c, const float* desc, const float* kpt_xy
     CU_CHECK(c->pool.acquire(sc->kptoff, (size_t)(n_scenes + 1) * 8 + 16));
     sc->ts.d_f32 = sc->f32.as<float>(); sc->ts.d_kpt = sc->kpt.as<float>(); sc->ts.d_kpt_offsets = sc->kptoff.as<int64_t>();
     sc->d_flag = reinterpret_cast<int*>(sc->kptoff.as<int64_t>() + (n_scenes + 1));
+    sc->ts.d_tnmax = sc->d_flag + 1;
     if (total > 0) CU_CHECK(cudaMemcpyAsync(sc->ts.d_f32, desc, (size_t)total * DIM * 4, cudaMemcpyHostToDevice, st));
     if (total > 0 && kpt_xy) CU_CHECK(cudaMemcpyAsync(sc->ts.d_kpt, kpt_xy, (size_t)total * 8, cudaMemcpyHostToDevice, st));
     else if (total > 0) CU_CHECK(cudaMemsetAsync(sc->ts.d_kpt, 0, (size_t)total * 8, st));
     CU_CHECK(cudaMemcpyAsync(sc->ts.d_kpt_offsets, offsets, (size_t)(n_scenes + 1) * 8, cudaMemcpyHostToDevice, st));
     CU_CHECK(cudaMemsetAsync(sc->d_flag, 0, 8, st));
-    int rc = prep_train(c, sc->ts, sc->b, sc->aug, 0, true, st, sc->d_flag);
+    int rc = prep_train(c, sc->ts, sc->b, sc->blo, sc->aug, 0, true, st, sc->d_flag);
     if (rc) { cvg_scenes_free(c, sc); return rc; }
     if (async) {
         // the caller's buffers are read by the copy engine until `ready`; cvg_detect_scenes orders itself after it
@@ -917,10 +974,10 @@ void cvg_scenes_free(cvg_ctx* c, cvg_scenes* sc)
     if (sc->ready) { cudaEventSynchronize(sc->ready); cudaEventDestroy(sc->ready); sc->ready = nullptr; }
     if (c) {
         cudaSetDevice(c->device);
-        DevBuf* bufs[] = { &sc->f32, &sc->b, &sc->aug, &sc->kpt, &sc->kptoff, &sc->units, &sc->dir };
+        DevBuf* bufs[] = { &sc->f32, &sc->b, &sc->blo, &sc->aug, &sc->kpt, &sc->kptoff, &sc->units, &sc->dir };
         for (DevBuf* b : bufs) c->pool.release(*b);
     } else {
-        sc->f32.release(); sc->b.release(); sc->aug.release(); sc->kpt.release(); sc->kptoff.release();
+        sc->f32.release(); sc->b.release(); sc->blo.release(); sc->aug.release(); sc->kpt.release(); sc->kptoff.release();
         sc->units.release(); sc->dir.release();
     }
     delete sc;
@@ -962,20 +1019,21 @@ int cvg_dev_match_top2(cvg_ctx* c, void* stream, const float* query_dev, int n_q
     CU_CHECK(cudaStreamWaitEvent(c->stream, c->ev[5], 0));
     const int n_pad = round_up(n_query, TILE_M);
     CU_CHECK(c->q_b.ensure((size_t)n_pad * DIM * 2)); CU_CHECK(c->q_aug.ensure((size_t)n_pad * KAUG * 2));
+    CU_CHECK(c->q_blo.ensure((size_t)n_pad * DIM * 2));
     CU_CHECK(c->q_norm.ensure((size_t)n_pad * 4));
     CU_CHECK(cudaMemsetAsync(c->d_flags, 0, 16, c->stream));
-    launch_prep_rows(query_dev, n_query, n_pad, 0, c->q_b.as<__nv_bfloat16>(), c->q_aug.as<__nv_bfloat16>(),
-                     c->q_norm.as<float>(), c->d_flags + 1, c->stream);
+    launch_prep_rows(query_dev, n_query, n_pad, 0, c->q_b.as<__nv_bfloat16>(), c->q_blo.as<__nv_bfloat16>(),
+                     c->q_aug.as<__nv_bfloat16>(), c->q_norm.as<float>(), c->d_flags + 1, nullptr, c->stream);
     c->launches++;
     TrainSet ts;
     const int64_t offs[2] = { 0, n_train };
     layout_segments(ts, offs, 1);
     ts.d_f32 = const_cast<float*>(train_dev);
-    int rc = prep_train(c, ts, c->t_b, c->t_aug, 0);
+    int rc = prep_train(c, ts, c->t_b, c->t_blo, c->t_aug, 0);
     if (rc) return rc;
-    combine_flags_kernel<<<1, 1, 0, c->stream>>>(c->d_flags, c->d_flags, (c->flags & CVG_FORCE_EXACT_MATCH) ? 1 : 0);
+    combine_flags_kernel<<<1, 1, 0, c->stream>>>(c->d_flags, c->d_flags, (c->flags & CVG_FORCE_EXACT_MATCH) ? 4 : 0);
     c->launches++;
-    QuerySide q{ query_dev, c->q_b.as<__nv_bfloat16>(), c->q_aug.as<__nv_bfloat16>(), c->q_norm.as<float>(), 0, n_query, n_pad };
+    QuerySide q{ query_dev, c->q_b.as<__nv_bfloat16>(), c->q_blo.as<__nv_bfloat16>(), c->q_aug.as<__nv_bfloat16>(), c->q_norm.as<float>(), 0, n_query, n_pad };
     std::vector<MatchUnit> units; std::vector<MergeEntry> dir; int n_rb;
     build_plan(q, ts, c->n_sms, units, dir, n_rb);
     CU_CHECK(c->units.ensure(std::max<size_t>(units.size(), 1) * sizeof(MatchUnit)));

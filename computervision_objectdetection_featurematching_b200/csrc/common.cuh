@@ -32,6 +32,19 @@ struct __align__(16) Top2 {
     float d1; int32_t i1; float d2; int32_t i2;
 };
 
+// Candidate record of one query row and one column part of a unit (non-integer descriptors): raw accumulator
+// values 2 q.t - ||t||^2 (approximate), largest first, and their train indices (-1 = absent).
+struct __align__(16) Top4 {
+    float v[4]; int32_t i[4];
+};
+
+// A train segment as the re-rank kernels see it.
+struct SegDev {
+    int64_t f32_row0;        // first row in the unpadded fp32 train matrix
+    int32_t rows;            // valid train rows
+    int32_t pad;
+};
+
 // Per (segment, row-block) directory entry for the merge kernel.
 struct MergeEntry {
     int32_t first_slot;      // first partial slot
@@ -41,27 +54,38 @@ struct MergeEntry {
 // ---- launchers (defined in the .cu files) --------------------------------------------------------
 // prep.cu
 void launch_prep_rows(const float* X, int n_rows, int n_pad, int is_train, __nv_bfloat16* Xb,
-                      __nv_bfloat16* Xaug, float* norms, int* nonint_flag, cudaStream_t st);
+                      __nv_bfloat16* Xlo /*lo half: bf16(x - hi), zero for integer rows; or NULL*/, __nv_bfloat16* Xaug, float* norms, int* nonint_flag /*bit0 non-integer, bit1 non-finite*/,
+                      int* tnmax_bits /*train side: max ||t||^2 as float bits, or NULL*/, cudaStream_t st);
 void launch_pack_points(const float* src_xy, const float* dst_xy, int64_t n, float4* pts, cudaStream_t st);
 
 // match_exact.cu — fp32 SIMT kernel in cv::batchDistance's summation order
 void launch_match_exact(const float* Q, int n_query, const float* T, const MatchUnit* units, int n_units,
-                        Top2* parts, const int* run_if_flag /*device flag: run only if *flag != 0, or NULL*/,
-                        cudaStream_t st);
+                        Top2* parts, const int* gate_flag /*device flag: run only if *flag == gate_want, or NULL*/,
+                        int gate_want, cudaStream_t st);
 
 // match_tc.cu — tcgen05 / TMEM / TMA kernel
 struct TcOperands {
     const __nv_bfloat16* Qb; const __nv_bfloat16* Qaug; const float* qnorm; int nq_pad;
     const __nv_bfloat16* Tb; const __nv_bfloat16* Taug; int nt_pad;
+    const __nv_bfloat16* Qlo; const __nv_bfloat16* Tlo;      // lo halves of the split operands (candidate path), or NULL
 };
 int  tc_init(char* err, size_t errlen);     // resolves cuTensorMapEncodeTiled; 0 = ok
-int  launch_match_tc(const TcOperands& op, const MatchUnit* units, int n_units, Top2* parts,
-                     const int* skip_if_flag /*device flag: skip if *flag != 0*/, int* dbg, int n_sms,
+// candidates = 2: exact top-2 (Top2 parts[n_units][128]); 4: candidate records (Top4 parts[n_units][4][128]).
+// gate_flag (device, may be NULL): the kernel runs only if *gate_flag == gate_want.
+int  launch_match_tc(const TcOperands& op, const MatchUnit* units, int n_units, void* parts, int candidates,
+                     const int* gate_flag, int gate_want, int* dbg, int n_sms,
                      cudaStream_t st, char* err, size_t errlen);
 
 // merge.cu (in match_exact.cu)
 void launch_merge(const Top2* parts, const MergeEntry* dir, int n_segments, int n_rowblocks, int n_query,
-                  float ratio, int32_t* idx, float* dist, uint8_t* accept, cudaStream_t st);
+                  float ratio, int32_t* idx, float* dist, uint8_t* accept,
+                  const int* gate_flag /*skipped if *flag == gate_skip, or NULL*/, int gate_skip, cudaStream_t st);
+// candidate path: merge of Top4 records, fp32 re-rank with proof, exact fallback for the unproven rows
+void launch_merge4_rerank(const Top4* parts4, const MergeEntry* dir, const SegDev* segs, int n_segments, int n_rowblocks,
+                          int n_query, int max_seg_rows, float ratio, const float* Q, int q_row_begin, const float* T,
+                          const float* qnorm, const int* tnmax_bits, int32_t* idx, float* dist, uint8_t* accept, int* fb_count,
+                          int2* fb_list, unsigned long long* fb_keys /*[2][n_segments * n_query]*/,
+                          const int* gate_flag, int gate_want, int n_sms, cudaStream_t st);
 void launch_merge_parts(const float* dist_parts, const int32_t* idx_parts, int n_parts, int n_query, float ratio,
                         int32_t* idx, float* dist, uint8_t* accept, cudaStream_t st);
 void launch_shift_index(const int32_t* idx_in, const float* dist_in, int n_query, int32_t idx_base,

@@ -16,9 +16,9 @@ constexpr int EX_TROWS = 16;          // train rows staged per smem tile
 __global__ void __launch_bounds__(EX_THREADS)
 match_exact_kernel(const float* __restrict__ Q, int n_query, const float* __restrict__ T,
                    const MatchUnit* __restrict__ units, Top2* __restrict__ parts,
-                   const int* __restrict__ run_if_flag)
+                   const int* __restrict__ gate_flag, int gate_want)
 {
-    if (run_if_flag && *run_if_flag == 0) return;
+    if (gate_flag && *gate_flag != gate_want) return;
     __shared__ float4 tile[EX_TROWS][DIM / 4];
     const MatchUnit u = units[blockIdx.x];
     const int qrow = u.q_row0 + threadIdx.x;
@@ -77,10 +77,10 @@ match_exact_kernel(const float* __restrict__ Q, int n_query, const float* __rest
 }
 
 void launch_match_exact(const float* Q, int n_query, const float* T, const MatchUnit* units, int n_units,
-                        Top2* parts, const int* run_if_flag, cudaStream_t st)
+                        Top2* parts, const int* gate_flag, int gate_want, cudaStream_t st)
 {
     if (n_units <= 0) return;
-    match_exact_kernel<<<n_units, EX_THREADS, 0, st>>>(Q, n_query, T, units, parts, run_if_flag);
+    match_exact_kernel<<<n_units, EX_THREADS, 0, st>>>(Q, n_query, T, units, parts, gate_flag, gate_want);
 }
 
 // ---- merge: lexicographic (distance, train index), the order that reproduces OpenCV's tie rule ----
@@ -111,8 +111,10 @@ __device__ __forceinline__ void top2_emit(float d1, int i1, float d2, int i2, fl
 // one thread per (segment, query row)
 __global__ void merge_kernel(const Top2* __restrict__ parts, const MergeEntry* __restrict__ dir,
                              int n_segments, int n_rowblocks, int n_query, float ratio,
-                             int32_t* __restrict__ idx, float* __restrict__ dist, uint8_t* __restrict__ accept)
+                             int32_t* __restrict__ idx, float* __restrict__ dist, uint8_t* __restrict__ accept,
+                             const int* __restrict__ gate_flag, int gate_skip)
 {
+    if (gate_flag && *gate_flag == gate_skip) return;          // the candidate path writes the results instead
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (int64_t)n_segments * n_query) return;
     const int seg = (int)(gid / n_query), row = (int)(gid % n_query);
@@ -128,13 +130,222 @@ __global__ void merge_kernel(const Top2* __restrict__ parts, const MergeEntry* _
 }
 
 void launch_merge(const Top2* parts, const MergeEntry* dir, int n_segments, int n_rowblocks, int n_query,
-                  float ratio, int32_t* idx, float* dist, uint8_t* accept, cudaStream_t st)
+                  float ratio, int32_t* idx, float* dist, uint8_t* accept, const int* gate_flag, int gate_skip,
+                  cudaStream_t st)
 {
     const int64_t n = (int64_t)n_segments * n_query;
     if (n <= 0) return;
     merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(parts, dir, n_segments, n_rowblocks, n_query,
-                                                              ratio, idx, dist, accept);
+                                                              ratio, idx, dist, accept, gate_flag, gate_skip);
 }
+
+// ---- candidate path (non-integer descriptors): fp32 re-rank with a proof, exact fallback ------------
+// cv::batchDistance's squared L2 distance of two 128-float rows, bit for bit
+__device__ __forceinline__ float l2sqr_cv(const float4* __restrict__ q, const float4* __restrict__ t)
+{
+    float acc[4][4];
+    #pragma unroll
+    for (int a = 0; a < 4; a++)
+        #pragma unroll
+        for (int l = 0; l < 4; l++) acc[a][l] = 0.f;
+    #pragma unroll 8
+    for (int j4 = 0; j4 < DIM / 4; j4++) {
+        const float4 x = q[j4], y = t[j4];
+        const int a = j4 & 3;
+        float d;
+        d = __fsub_rn(x.x, y.x); acc[a][0] = __fadd_rn(acc[a][0], __fmul_rn(d, d));
+        d = __fsub_rn(x.y, y.y); acc[a][1] = __fadd_rn(acc[a][1], __fmul_rn(d, d));
+        d = __fsub_rn(x.z, y.z); acc[a][2] = __fadd_rn(acc[a][2], __fmul_rn(d, d));
+        d = __fsub_rn(x.w, y.w); acc[a][3] = __fadd_rn(acc[a][3], __fmul_rn(d, d));
+    }
+    float v[4];
+    #pragma unroll
+    for (int l = 0; l < 4; l++)
+        v[l] = __fadd_rn(__fadd_rn(__fadd_rn(acc[0][l], acc[1][l]), acc[2][l]), acc[3][l]);
+    return __fadd_rn(__fadd_rn(v[0], v[2]), __fadd_rn(v[1], v[3]));
+}
+
+// One thread per (segment, query row).  The tensor-core kernel left, per unit and column part, the four columns
+// with the largest APPROXIMATE value a = 2 q.t - ||t||^2 (bf16 hi/lo split operands, three products).  Here:
+//   1. the records are merged into the row's four best candidates; every other column has a <= a4;
+//   2. the candidates' distances are recomputed exactly as OpenCV does (fp32, its summation order) and ordered by
+//      (distance, train index);
+//   3. the answer is PROVEN: with eps >= |a - (2 q.t - ||t||^2)| for every column (bf16 rounding of both operands,
+//      fp32 accumulation, the fp32 norms), any other column has a true squared distance >= qn - a4 - eps; if the
+//      second best candidate's squared distance is below that bound (with a relative margin that also covers
+//      OpenCV's own fp32 rounding and the rounding of sqrtf), no other column can enter or tie the top two.
+//      Rows that cannot be proven go to the exact fallback kernel (list `fb`).
+__global__ void merge4_rerank_kernel(const Top4* __restrict__ parts4, const MergeEntry* __restrict__ dir,
+                                     const SegDev* __restrict__ segs, int n_segments, int n_rowblocks, int n_query,
+                                     float ratio, const float* __restrict__ Q, int q_row_begin,
+                                     const float* __restrict__ T, const float* __restrict__ qnorm,
+                                     const int* __restrict__ tnmax_bits,
+                                     int32_t* __restrict__ idx, float* __restrict__ dist, uint8_t* __restrict__ accept,
+                                     int* __restrict__ fb_count, int2* __restrict__ fb_list,
+                                     const int* __restrict__ gate_flag, int gate_want)
+{
+    if (gate_flag && *gate_flag != gate_want) return;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (int64_t)n_segments * n_query) return;
+    const int seg = (int)(gid / n_query), row = (int)(gid % n_query);
+    const MergeEntry e = dir[seg * n_rowblocks + row / TILE_M];
+    const SegDev sd = segs[seg];
+    float b[4] = { -INFINITY, -INFINITY, -INFINITY, -INFINITY };
+    int ix[4] = { -1, -1, -1, -1 };
+    for (int s = 0; s < e.n_slots * 4; s++) {
+        const Top4 p = parts4[((size_t)e.first_slot * 4 + s) * TILE_M + (row % TILE_M)];
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float v = p.v[k]; const int id = p.i[k];
+            if (id < 0 || !(v > b[3])) continue;
+            if (v > b[2]) {
+                b[3] = b[2]; ix[3] = ix[2];
+                if (v > b[1]) {
+                    b[2] = b[1]; ix[2] = ix[1];
+                    if (v > b[0]) { b[1] = b[0]; ix[1] = ix[0]; b[0] = v; ix[0] = id; }
+                    else          { b[1] = v; ix[1] = id; }
+                } else { b[2] = v; ix[2] = id; }
+            } else { b[3] = v; ix[3] = id; }
+        }
+    }
+    const float4* q = reinterpret_cast<const float4*>(Q + (size_t)(q_row_begin + row) * DIM);
+    float d1 = INFINITY, d2 = INFINITY, s2 = INFINITY;      // s2: squared distance of the current second best
+    int i1 = -1, i2 = -1;
+    float s1 = INFINITY;
+    bool bad = false;
+    #pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (ix[k] < 0) continue;
+        const float4* t = reinterpret_cast<const float4*>(T + (size_t)(sd.f32_row0 + ix[k]) * DIM);
+        const float s = l2sqr_cv(q, t);
+        const float d = sqrtf(s);
+        if (!(d < FLT_MAX)) { bad = true; continue; }        // NaN / inf: let the exact kernel apply OpenCV's rule
+        if (i1 < 0 || lex_less(d, ix[k], d1, i1)) { d2 = d1; i2 = i1; s2 = s1; d1 = d; i1 = ix[k]; s1 = s; }
+        else if (i2 < 0 || lex_less(d, ix[k], d2, i2)) { d2 = d; i2 = ix[k]; s2 = s; }
+    }
+    bool proven;
+    if (sd.rows <= 4) proven = !bad;                          // every column was a candidate
+    else if (bad || i2 < 0 || ix[3] < 0) proven = false;
+    else {
+        const float qn = qnorm[q_row_begin + row];
+        const float tnmax = __int_as_float(*tnmax_bits);
+        // |a - exact| is bounded by: the split operands (2q = hi + lo + O(2^-18 |2q|), same for t, the lo.lo product is
+        // dropped): 3 * 2^-17 ||q|| ||t||; the fp32 accumulation of 400 products, truncating adder assumed:
+        // 400 * 2^-23 (2 ||q|| ||t|| + ||t||^2); the fp32 norms: 2^-17 (||q||^2 + ||t||^2).  Each doubled for slack.
+        const float qt = sqrtf(qn) * sqrtf(tnmax);
+        const float eps = 2.f * (2.2888184e-5f * qt + 4.7683716e-5f * (2.f * qt + tnmax) + 7.6293945e-6f * (qn + tnmax));
+        const float lower = (qn - b[3]) - eps;                // squared distance of any non-candidate is >= lower
+        proven = s2 < lower * (1.f - 6.103515625e-5f);        // 2^-14: OpenCV's own fp32 sum and sqrtf rounding
+    }
+    if (proven) {
+        top2_emit(d1, i1, d2, i2, ratio, (size_t)gid, idx, dist, accept);
+    } else {
+        const int slot = atomicAdd(fb_count, 1);
+        fb_list[slot] = make_int2(seg, row);
+    }
+}
+
+// Exact top-2 of the rows the re-rank could not prove.  A work item = (unproven row, chunk of FB_CHUNK train rows),
+// one CTA each, looped over a fixed grid because the number of rows is only known on the device.  (distance, index)
+// pairs are packed into 64-bit keys whose unsigned order is the lexicographic order OpenCV's insertion produces
+// (distances are >= 0), so the merge across chunks is an atomicMin: pass 1 finds every row's nearest column, pass 2
+// the nearest one that is not it.
+constexpr int FB_THREADS = 256;
+constexpr int FB_CHUNK = 512;
+constexpr unsigned long long FB_ABSENT = ~0ull;
+
+__device__ __forceinline__ unsigned long long fb_key(float d, int i)
+{
+    return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)i;
+}
+
+__global__ void fallback_init_kernel(const int* __restrict__ fb_count, unsigned long long* __restrict__ g1,
+                                     unsigned long long* __restrict__ g2, const int* __restrict__ gate_flag, int gate_want)
+{
+    if (gate_flag && *gate_flag != gate_want) return;
+    const int n = *fb_count;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) { g1[e] = FB_ABSENT; g2[e] = FB_ABSENT; }
+}
+
+__global__ void __launch_bounds__(FB_THREADS)
+fallback_scan_kernel(const int* __restrict__ fb_count, const int2* __restrict__ fb_list, const SegDev* __restrict__ segs,
+                     int chunks, const float* __restrict__ Q, int q_row_begin, const float* __restrict__ T,
+                     unsigned long long* __restrict__ g1, unsigned long long* __restrict__ g2, int pass,
+                     const int* __restrict__ gate_flag, int gate_want)
+{
+    if (gate_flag && *gate_flag != gate_want) return;
+    __shared__ unsigned long long s_min[FB_THREADS / 32];
+    const int n = *fb_count;
+    const long long total = (long long)n * chunks;
+    for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+        const int e = (int)(w / chunks), c = (int)(w % chunks);
+        const int2 sr = fb_list[e];
+        const SegDev sd = segs[sr.x];
+        const int r0 = c * FB_CHUNK, r1 = min(r0 + FB_CHUNK, sd.rows);
+        if (r0 >= r1) continue;                               // block-uniform
+        const float4* q = reinterpret_cast<const float4*>(Q + (size_t)(q_row_begin + sr.y) * DIM);
+        const unsigned long long skip = pass == 2 ? g1[e] : FB_ABSENT;
+        unsigned long long best = FB_ABSENT;
+        for (int r = r0 + (int)threadIdx.x; r < r1; r += FB_THREADS) {
+            const float d = sqrtf(l2sqr_cv(q, reinterpret_cast<const float4*>(T + (size_t)(sd.f32_row0 + r) * DIM)));
+            if (d < FLT_MAX) {                                // NaN / inf / >= FLT_MAX never enter (App. A.1)
+                const unsigned long long k = fb_key(d, r);
+                if (k != skip && k < best) best = k;
+            }
+        }
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+            if (ob < best) best = ob;
+        }
+        __syncthreads();                                      // s_min of the previous work item consumed
+        if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            #pragma unroll
+            for (int k = 1; k < FB_THREADS / 32; k++) if (s_min[k] < best) best = s_min[k];
+            if (best != FB_ABSENT) atomicMin(pass == 1 ? &g1[e] : &g2[e], best);
+        }
+    }
+}
+
+__global__ void fallback_emit_kernel(const int* __restrict__ fb_count, const int2* __restrict__ fb_list, int n_query, float ratio,
+                                     const unsigned long long* __restrict__ g1, const unsigned long long* __restrict__ g2,
+                                     int32_t* __restrict__ idx, float* __restrict__ dist, uint8_t* __restrict__ accept,
+                                     const int* __restrict__ gate_flag, int gate_want)
+{
+    if (gate_flag && *gate_flag != gate_want) return;
+    const int n = *fb_count;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int2 sr = fb_list[e];
+        const unsigned long long a = g1[e], b = g2[e];
+        const int i1 = a == FB_ABSENT ? -1 : (int)(unsigned int)a, i2 = b == FB_ABSENT ? -1 : (int)(unsigned int)b;
+        const float d1 = __uint_as_float((unsigned int)(a >> 32)), d2 = __uint_as_float((unsigned int)(b >> 32));
+        top2_emit(d1, i1, d2, i2, ratio, (size_t)sr.x * n_query + sr.y, idx, dist, accept);
+    }
+}
+
+void launch_merge4_rerank(const Top4* parts4, const MergeEntry* dir, const SegDev* segs, int n_segments, int n_rowblocks,
+                          int n_query, int max_seg_rows, float ratio, const float* Q, int q_row_begin, const float* T,
+                          const float* qnorm, const int* tnmax_bits, int32_t* idx, float* dist, uint8_t* accept, int* fb_count,
+                          int2* fb_list, unsigned long long* fb_keys /*[2][n_segments * n_query]*/,
+                          const int* gate_flag, int gate_want, int n_sms, cudaStream_t st)
+{
+    const int64_t n = (int64_t)n_segments * n_query;
+    if (n <= 0) return;
+    cudaMemsetAsync(fb_count, 0, 4, st);
+    merge4_rerank_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(parts4, dir, segs, n_segments, n_rowblocks, n_query, ratio,
+                                                                      Q, q_row_begin, T, qnorm, tnmax_bits, idx, dist, accept,
+                                                                      fb_count, fb_list, gate_flag, gate_want);
+    unsigned long long* g1 = fb_keys; unsigned long long* g2 = fb_keys + n;
+    const int chunks = (max_seg_rows + FB_CHUNK - 1) / FB_CHUNK;
+    fallback_init_kernel<<<n_sms, 256, 0, st>>>(fb_count, g1, g2, gate_flag, gate_want);
+    for (int pass = 1; pass <= 2; pass++)
+        fallback_scan_kernel<<<n_sms * 8, FB_THREADS, 0, st>>>(fb_count, fb_list, segs, chunks, Q, q_row_begin, T, g1, g2, pass,
+                                                              gate_flag, gate_want);
+    fallback_emit_kernel<<<n_sms, 256, 0, st>>>(fb_count, fb_list, n_query, ratio, g1, g2, idx, dist, accept, gate_flag, gate_want);
+}
+
 
 // merge of n_parts partial results laid out [n_parts][n_query][2] (multi-GPU train-tile shards)
 __global__ void merge_parts_kernel(const float* __restrict__ dparts, const int32_t* __restrict__ iparts,

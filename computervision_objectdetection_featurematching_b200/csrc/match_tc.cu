@@ -177,16 +177,56 @@ __device__ __forceinline__ float float_pred(float x)
     return __int_as_float(x > 0.f ? b - 1 : b + 1);
 }
 
-struct TcMaps { CUtensorMap q, qaug, t, taug; };
+// Candidate form for non-integer descriptors (the accumulator is then an approximation of 2 q.t - ||t||^2): the four
+// largest values per row are kept; the fp32 re-rank (match_exact.cu) decides among them and proves, with an error
+// bound, that no other column can belong to the two nearest.  Ties need no care here: a column that is dropped has
+// a value <= the fourth kept one, which is all the bound uses.
+__device__ __forceinline__ void top4_scan32(const uint32_t* r, int c0, float (&b)[4], int (&ix)[4], float& f)
+{
+    float g[8];
+    #pragma unroll
+    for (int k = 0; k < 8; k++)
+        g[k] = fmaxf(fmaxf(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1])),
+                     fmaxf(__uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3])));
+    #pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (g[k] > f) {
+            #pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float v = __uint_as_float(r[4 * k + j]);
+                if (v > f) {
+                    const int id = c0 + 4 * k + j;
+                    if (v > b[2]) {
+                        b[3] = b[2]; ix[3] = ix[2];
+                        if (v > b[1]) {
+                            b[2] = b[1]; ix[2] = ix[1];
+                            if (v > b[0]) { b[1] = b[0]; ix[1] = ix[0]; b[0] = v; ix[0] = id; }
+                            else          { b[1] = v; ix[1] = id; }
+                        } else { b[2] = v; ix[2] = id; }
+                    } else { b[3] = v; ix[3] = id; }
+                    f = fmaxf(f, b[3]);
+                }
+            }
+        }
+    }
+}
 
+struct TcMaps { CUtensorMap q, qaug, t, taug, qlo, tlo; };
+
+// KP = 2: exact top-2 per row (integer descriptors), partial records Top2 with distances.
+// KP = 4: four candidates per row and column part (non-integer descriptors), partial records Top4 with raw
+//         accumulator values, slot (part_slot * 4 + column part).
+template <int KP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ qnorm,
-                const MatchUnit* __restrict__ units, int n_units, Top2* __restrict__ parts,
-                const int* __restrict__ skip_if_flag, int* dbg, int exp_mode)
+                const MatchUnit* __restrict__ units, int n_units, void* __restrict__ parts_out,
+                const int* __restrict__ gate_flag, int gate_want, int* dbg, int exp_mode)
 {
     // exp_mode (experiments only, set through CVG_TC_EXP): bit 0 = epilogue releases the accumulator without
     // scanning it, bit 1 = the producer re-arms ring stages without issuing the B loads
-    if (skip_if_flag && *skip_if_flag != 0) return;
+    if (gate_flag && *gate_flag != gate_want) return;
+    constexpr bool SPLIT = KP == 4;                  // hi/lo split operands (non-integer descriptors)
+    constexpr int N_STAGES_PER_TILE = SPLIT ? 4 : 2;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -227,22 +267,36 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
             uint32_t ua = 0, bs = 0, tcnt = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x, ua++) {
                 const MatchUnit un = units[u];
-                const uint32_t ab = ua & 1;
-                mbar_wait(a_empty + 8 * ab, ((ua >> 1) & 1) ^ 1, dbg, 1);
+                // KP == 2: A tile (queries) double-buffered.  KP == 4 (split operands): one buffer holding the hi and lo
+                // halves of 2q — [hi k 0-63][hi k 64-127][lo k 0-63][lo k 64-127][aug] = 68 KB in the same 72 KB region.
+                const uint32_t ab = SPLIT ? 0u : (ua & 1);
+                mbar_wait(a_empty + 8 * ab, (SPLIT ? (ua & 1) : ((ua >> 1) & 1)) ^ 1, dbg, 1);
                 const uint32_t sa = smem_base + OFF_A + ab * A_BYTES;
-                mbar_expect_tx(a_full + 8 * ab, A_BYTES);
-                tma_load_2d(sa, &maps.q, 0, un.q_row0, a_full + 8 * ab);
-                tma_load_2d(sa + A_ATOM_BYTES, &maps.q, 64, un.q_row0, a_full + 8 * ab);
-                tma_load_2d(sa + 2 * A_ATOM_BYTES, &maps.qaug, 0, un.q_row0, a_full + 8 * ab);
+                if constexpr (SPLIT) {
+                    mbar_expect_tx(a_full, 4 * A_ATOM_BYTES + A_AUG_BYTES);
+                    tma_load_2d(sa, &maps.q, 0, un.q_row0, a_full);
+                    tma_load_2d(sa + A_ATOM_BYTES, &maps.q, 64, un.q_row0, a_full);
+                    tma_load_2d(sa + 2 * A_ATOM_BYTES, &maps.qlo, 0, un.q_row0, a_full);
+                    tma_load_2d(sa + 3 * A_ATOM_BYTES, &maps.qlo, 64, un.q_row0, a_full);
+                    tma_load_2d(sa + 4 * A_ATOM_BYTES, &maps.qaug, 0, un.q_row0, a_full);
+                } else {
+                    mbar_expect_tx(a_full + 8 * ab, A_BYTES);
+                    tma_load_2d(sa, &maps.q, 0, un.q_row0, a_full + 8 * ab);
+                    tma_load_2d(sa + A_ATOM_BYTES, &maps.q, 64, un.q_row0, a_full + 8 * ab);
+                    tma_load_2d(sa + 2 * A_ATOM_BYTES, &maps.qaug, 0, un.q_row0, a_full + 8 * ab);
+                }
                 for (int t = 0; t < un.n_tiles; t++, tcnt++) {
                     const int row = un.t_row0 + t * TILE_N;
+                    // ring stages of a tile: the two K halves of the train operand; split operands add the two K halves
+                    // of its lo part (stages 2, 3)
                     #pragma unroll 1
-                    for (int h = 0; h < 2; h++, bs++) {
+                    for (int h = 0; h < N_STAGES_PER_TILE; h++, bs++) {
                         const uint32_t s = bs % B_STAGES;
                         mbar_wait(b_empty + 8 * s, ((bs / B_STAGES) & 1) ^ 1, dbg, 2);
-                        if ((exp_mode & 2) && bs >= B_STAGES) { mbar_arrive(b_full + 8 * s); continue; }
+                        if (!SPLIT && (exp_mode & 2) && bs >= B_STAGES) { mbar_arrive(b_full + 8 * s); continue; }
                         mbar_expect_tx(b_full + 8 * s, B_ATOM_BYTES);
-                        tma_load_2d(smem_base + OFF_B + s * B_ATOM_BYTES, &maps.t, 64 * h, row, b_full + 8 * s);
+                        tma_load_2d(smem_base + OFF_B + s * B_ATOM_BYTES, (SPLIT && h >= 2) ? &maps.tlo : &maps.t, 64 * (h & 1), row,
+                                    b_full + 8 * s);
                     }
                     const uint32_t g = tcnt & 1;
                     mbar_wait(g_empty + 8 * g, ((tcnt >> 1) & 1) ^ 1, dbg, 7);
@@ -257,15 +311,15 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
             uint32_t ua = 0, bs = 0, tc = 0;
             for (int u = blockIdx.x; u < n_units; u += gridDim.x, ua++) {
                 const int n_tiles = units[u].n_tiles;
-                const uint32_t ab = ua & 1;
-                mbar_wait(a_full + 8 * ab, (ua >> 1) & 1, dbg, 3);
+                const uint32_t ab = SPLIT ? 0u : (ua & 1);
+                mbar_wait(a_full + 8 * ab, SPLIT ? (ua & 1) : ((ua >> 1) & 1), dbg, 3);
                 const uint32_t sa = smem_base + OFF_A + ab * A_BYTES;
                 for (int t = 0; t < n_tiles; t++, tc++) {
                     const uint32_t acc = tc & 1;
                     mbar_wait(t_empty + 8 * acc, ((tc >> 1) & 1) ^ 1, dbg, 5);
                     const uint32_t d_tmem = tmem_base + acc * TILE_N;
                     #pragma unroll 1
-                    for (int h = 0; h < 2; h++, bs++) {
+                    for (int h = 0; h < N_STAGES_PER_TILE; h++, bs++) {
                         const uint32_t s = bs % B_STAGES;
                         mbar_wait(b_full + 8 * s, (bs / B_STAGES) & 1, dbg, 4);
                         tc_fence_after();
@@ -273,9 +327,15 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                         #pragma unroll
                         for (int k = 0; k < 4; k++) {
                             const uint32_t koff = (uint32_t)k * 32u;             // 16 bf16 = 32 B inside the swizzle atom
-                            const uint64_t da = desc_sw128(sa + h * A_ATOM_BYTES + koff);
                             const uint64_t db = desc_sw128(sb + koff);
-                            tc_mma_bf16(d_tmem, da, db, TC_IDESC, (h | k) ? 1u : 0u);
+                            if constexpr (SPLIT) {
+                                // 2q.t ~ hi.hi + lo.hi (stages 0, 1: train hi) + hi.lo (stages 2, 3: train lo)
+                                const uint32_t kh = (uint32_t)(h & 1);
+                                tc_mma_bf16(d_tmem, desc_sw128(sa + kh * A_ATOM_BYTES + koff), db, TC_IDESC, (h | k) ? 1u : 0u);
+                                if (h < 2) tc_mma_bf16(d_tmem, desc_sw128(sa + (2 + kh) * A_ATOM_BYTES + koff), db, TC_IDESC, 1u);
+                            } else {
+                                tc_mma_bf16(d_tmem, desc_sw128(sa + h * A_ATOM_BYTES + koff), db, TC_IDESC, (h | k) ? 1u : 0u);
+                            }
                         }
                         tc_commit(b_empty + 8 * s);      // ring stage reusable once these MMAs retire
                     }
@@ -283,8 +343,8 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                         const uint32_t g = tc & 1;
                         mbar_wait(g_full + 8 * g, (tc >> 1) & 1, dbg, 8);
                         tc_fence_after();
-                        tc_mma_bf16(d_tmem, desc_sw32(sa + 2 * A_ATOM_BYTES), desc_sw32(smem_base + OFF_BAUG + g * B_AUG_BYTES),
-                                    TC_IDESC, 1u);
+                        tc_mma_bf16(d_tmem, desc_sw32(sa + (SPLIT ? 4 : 2) * A_ATOM_BYTES),
+                                    desc_sw32(smem_base + OFF_BAUG + g * B_AUG_BYTES), TC_IDESC, 1u);
                         tc_commit(g_empty + 8 * g);
                     }
                     tc_commit(t_full + 8 * acc);         // accumulator ready for the epilogue
@@ -308,76 +368,123 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
         const uint32_t my_share = share + (uint32_t)(part * TILE_M + row_in_tile) * 8u;
         share_store(my_share, -INFINITY, -INFINITY);
         asm volatile("bar.sync 1, %0;" :: "n"(32 * TC_EPI_WARPS) : "memory");
-        uint32_t tc = 0;
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const MatchUnit un = units[u];
-            float b1 = -INFINITY, b2 = -INFINITY, f = -INFINITY;
-            int i1 = -1, i2 = -1;
-            for (int t = 0; t < un.n_tiles; t++, tc++) {
-                const uint32_t acc = tc & 1;
-                mbar_wait(t_full + 8 * acc, (tc >> 1) & 1, dbg, 6);
-                tc_fence_after();
-                if (t > 0) {
-                    float o1[3], o2[3];
+        if constexpr (KP == 2) {
+            uint32_t tc = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const MatchUnit un = units[u];
+                float b1 = -INFINITY, b2 = -INFINITY, f = -INFINITY;
+                int i1 = -1, i2 = -1;
+                for (int t = 0; t < un.n_tiles; t++, tc++) {
+                    const uint32_t acc = tc & 1;
+                    mbar_wait(t_full + 8 * acc, (tc >> 1) & 1, dbg, 6);
+                    tc_fence_after();
+                    if (t > 0) {
+                        float o1[3], o2[3];
+                        #pragma unroll
+                        for (int pp = 0; pp < 3; pp++) {
+                            const int op = (part + 1 + pp) & 3;
+                            share_load(share + (uint32_t)(op * TILE_M + row_in_tile) * 8u, o1[pp], o2[pp]);
+                        }
+                        // second largest of the four bests, and the largest of the four seconds
+                        const float m1 = fmaxf(b1, o1[0]), n1 = fminf(b1, o1[0]);
+                        const float m2 = fmaxf(o1[1], o1[2]), n2 = fminf(o1[1], o1[2]);
+                        const float second_best = fmaxf(fminf(m1, m2), fmaxf(n1, n2));
+                        const float foreign = fmaxf(fmaxf(second_best, o2[0]), fmaxf(o2[1], o2[2]));
+                        f = fmaxf(f, float_pred(foreign));
+                    }
+                    const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TILE_N + part * 64;
+                    const int col_base = un.t_local0 + t * TILE_N + part * 64;
+                    if (!(exp_mode & 1)) {
+                        uint32_t ra[32], rb[32];
+                        tc_ld32(tbase, ra);                           // two loads in flight before the wait
+                        tc_ld32(tbase + 32, rb);
+                        tc_wait_ld();
+                        top2_scan32(ra, col_base, b1, i1, b2, i2, f);
+                        top2_scan32(rb, col_base + 32, b1, i1, b2, i2, f);
+                        share_store(my_share, b1, b2);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_empty + 8 * acc);
+                }
+                // ---- unit flush: merge the four column parts, convert to distances, write the partial ----
+                share_store(my_share, -INFINITY, -INFINITY);     // reset before the barriers below
+                if (b1 < ABSENT_BELOW) { i1 = -1; }
+                if (b2 < ABSENT_BELOW) { i2 = -1; }
+                if (part > 0) {
+                    Top2 o; o.d1 = b1; o.i1 = i1; o.d2 = b2; o.i2 = i2;
+                    scratch[(part - 1) * TILE_M + row_in_tile] = o;
+                }
+                asm volatile("bar.sync 1, %0;" :: "n"(32 * TC_EPI_WARPS) : "memory");
+                if (part == 0) {
+                    // larger acc' first, ties -> lower train index
                     #pragma unroll
                     for (int pp = 0; pp < 3; pp++) {
-                        const int op = (part + 1 + pp) & 3;
-                        share_load(share + (uint32_t)(op * TILE_M + row_in_tile) * 8u, o1[pp], o2[pp]);
+                        const Top2 o = scratch[pp * TILE_M + row_in_tile];
+                        const float cv[2] = { o.d1, o.d2 };
+                        const int ci[2] = { o.i1, o.i2 };
+                        #pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            const float v = cv[k]; const int i = ci[k];
+                            if (i < 0) continue;
+                            if (i1 < 0 || v > b1 || (v == b1 && i < i1)) { b2 = b1; i2 = i1; b1 = v; i1 = i; }
+                            else if (i2 < 0 || v > b2 || (v == b2 && i < i2)) { b2 = v; i2 = i; }
+                        }
                     }
-                    // second largest of the four bests, and the largest of the four seconds
-                    const float m1 = fmaxf(b1, o1[0]), n1 = fminf(b1, o1[0]);
-                    const float m2 = fmaxf(o1[1], o1[2]), n2 = fminf(o1[1], o1[2]);
-                    const float second_best = fmaxf(fminf(m1, m2), fmaxf(n1, n2));
-                    const float foreign = fmaxf(fmaxf(second_best, o2[0]), fmaxf(o2[1], o2[2]));
-                    f = fmaxf(f, float_pred(foreign));
+                    const float qn = qnorm[un.q_row0 + row_in_tile];
+                    Top2 out;
+                    out.i1 = i1; out.i2 = i2;
+                    out.d1 = i1 >= 0 ? sqrtf(fmaxf(qn - b1, 0.f)) : INFINITY;
+                    out.d2 = i2 >= 0 ? sqrtf(fmaxf(qn - b2, 0.f)) : INFINITY;
+                    reinterpret_cast<Top2*>(parts_out)[(size_t)un.part_slot * TILE_M + row_in_tile] = out;
                 }
-                const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TILE_N + part * 64;
-                const int col_base = un.t_local0 + t * TILE_N + part * 64;
-                if (!(exp_mode & 1)) {
-                    uint32_t ra[32], rb[32];
-                    tc_ld32(tbase, ra);                           // two loads in flight before the wait
-                    tc_ld32(tbase + 32, rb);
-                    tc_wait_ld();
-                    top2_scan32(ra, col_base, b1, i1, b2, i2, f);
-                    top2_scan32(rb, col_base + 32, b1, i1, b2, i2, f);
-                    share_store(my_share, b1, b2);
+                asm volatile("bar.sync 1, %0;" :: "n"(32 * TC_EPI_WARPS) : "memory");
+            }
+        } else {
+            uint32_t tc = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const MatchUnit un = units[u];
+                float b[4] = { -INFINITY, -INFINITY, -INFINITY, -INFINITY }, f = -INFINITY;
+                int ix[4] = { -1, -1, -1, -1 };
+                for (int t = 0; t < un.n_tiles; t++, tc++) {
+                    const uint32_t acc = tc & 1;
+                    mbar_wait(t_full + 8 * acc, (tc >> 1) & 1, dbg, 6);
+                    tc_fence_after();
+                    if (t > 0) {
+                        // a part's fourth best is a lower bound of the row's fourth best: columns at or below it are no candidates
+                        float foreign = -INFINITY;
+                        #pragma unroll
+                        for (int pp = 0; pp < 3; pp++) {
+                            const int op = (part + 1 + pp) & 3;
+                            float o1, o2;
+                            share_load(share + (uint32_t)(op * TILE_M + row_in_tile) * 8u, o1, o2);
+                            foreign = fmaxf(foreign, o2);
+                        }
+                        f = fmaxf(f, foreign);
+                    }
+                    const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TILE_N + part * 64;
+                    const int col_base = un.t_local0 + t * TILE_N + part * 64;
+                    if (!(exp_mode & 1)) {
+                        uint32_t ra[32], rb[32];
+                        tc_ld32(tbase, ra);
+                        tc_ld32(tbase + 32, rb);
+                        tc_wait_ld();
+                        top4_scan32(ra, col_base, b, ix, f);
+                        top4_scan32(rb, col_base + 32, b, ix, f);
+                        share_store(my_share, b[0], b[3]);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_empty + 8 * acc);
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(t_empty + 8 * acc);
-            }
-            // ---- unit flush: merge the four column parts, convert to distances, write the partial ----
-            share_store(my_share, -INFINITY, -INFINITY);     // reset before the barriers below
-            if (b1 < ABSENT_BELOW) { i1 = -1; }
-            if (b2 < ABSENT_BELOW) { i2 = -1; }
-            if (part > 0) {
-                Top2 o; o.d1 = b1; o.i1 = i1; o.d2 = b2; o.i2 = i2;
-                scratch[(part - 1) * TILE_M + row_in_tile] = o;
-            }
-            asm volatile("bar.sync 1, %0;" :: "n"(32 * TC_EPI_WARPS) : "memory");
-            if (part == 0) {
-                // larger acc' first, ties -> lower train index
+                // ---- unit flush: every column part writes its own candidate record ----
+                share_store(my_share, -INFINITY, -INFINITY);
+                Top4 out;
                 #pragma unroll
-                for (int pp = 0; pp < 3; pp++) {
-                    const Top2 o = scratch[pp * TILE_M + row_in_tile];
-                    const float cv[2] = { o.d1, o.d2 };
-                    const int ci[2] = { o.i1, o.i2 };
-                    #pragma unroll
-                    for (int k = 0; k < 2; k++) {
-                        const float v = cv[k]; const int i = ci[k];
-                        if (i < 0) continue;
-                        if (i1 < 0 || v > b1 || (v == b1 && i < i1)) { b2 = b1; i2 = i1; b1 = v; i1 = i; }
-                        else if (i2 < 0 || v > b2 || (v == b2 && i < i2)) { b2 = v; i2 = i; }
-                    }
-                }
-                const float qn = qnorm[un.q_row0 + row_in_tile];
-                Top2 out;
-                out.i1 = i1; out.i2 = i2;
-                out.d1 = i1 >= 0 ? sqrtf(fmaxf(qn - b1, 0.f)) : INFINITY;
-                out.d2 = i2 >= 0 ? sqrtf(fmaxf(qn - b2, 0.f)) : INFINITY;
-                parts[(size_t)un.part_slot * TILE_M + row_in_tile] = out;
+                for (int k = 0; k < 4; k++) { out.v[k] = b[k]; out.i[k] = b[k] < ABSENT_BELOW ? -1 : ix[k]; }
+                reinterpret_cast<Top4*>(parts_out)[((size_t)un.part_slot * 4 + part) * TILE_M + row_in_tile] = out;
+                asm volatile("bar.sync 1, %0;" :: "n"(32 * TC_EPI_WARPS) : "memory");     // all share slots reset before the next unit
             }
-            asm volatile("bar.sync 1, %0;" :: "n"(32 * TC_EPI_WARPS) : "memory");
         }
     }
     tc_fence_before();
@@ -405,7 +512,9 @@ int tc_init(char* err, size_t errlen)
         return 1;
     }
     g_encode = (EncodeTiledFn)fn;
-    e = cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+    e = cudaFuncSetAttribute(match_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(match_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
     if (e != cudaSuccess) {
         snprintf(err, errlen, "cudaFuncSetAttribute(match_tc_kernel): %s", cudaGetErrorString(e));
         g_encode = nullptr;
@@ -431,8 +540,8 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint32_t co
     return 0;
 }
 
-int launch_match_tc(const TcOperands& op, const MatchUnit* units, int n_units, Top2* parts,
-                    const int* skip_if_flag, int* dbg, int n_sms, cudaStream_t st, char* err, size_t errlen)
+int launch_match_tc(const TcOperands& op, const MatchUnit* units, int n_units, void* parts, int candidates,
+                    const int* gate_flag, int gate_want, int* dbg, int n_sms, cudaStream_t st, char* err, size_t errlen)
 {
     if (n_units <= 0) return 0;
     if (tc_init(err, errlen)) return 1;
@@ -441,10 +550,19 @@ int launch_match_tc(const TcOperands& op, const MatchUnit* units, int n_units, T
     if (make_map(&maps.qaug, op.Qaug, op.nq_pad, KAUG, KAUG, TILE_M, CU_TENSOR_MAP_SWIZZLE_32B, err, errlen)) return 1;
     if (make_map(&maps.t, op.Tb, op.nt_pad, DIM, 64, TILE_N, CU_TENSOR_MAP_SWIZZLE_128B, err, errlen)) return 1;
     if (make_map(&maps.taug, op.Taug, op.nt_pad, KAUG, KAUG, TILE_N, CU_TENSOR_MAP_SWIZZLE_32B, err, errlen)) return 1;
+    maps.qlo = maps.q; maps.tlo = maps.t;
+    if (candidates == 4) {
+        if (!op.Qlo || !op.Tlo) { snprintf(err, errlen, "candidate path needs the lo operand halves"); return 1; }
+        if (make_map(&maps.qlo, op.Qlo, op.nq_pad, DIM, 64, TILE_M, CU_TENSOR_MAP_SWIZZLE_128B, err, errlen)) return 1;
+        if (make_map(&maps.tlo, op.Tlo, op.nt_pad, DIM, 64, TILE_N, CU_TENSOR_MAP_SWIZZLE_128B, err, errlen)) return 1;
+    }
     const int grid = n_units < n_sms ? n_units : n_sms;
     static int exp_mode = -1;
     if (exp_mode < 0) { const char* e = getenv("CVG_TC_EXP"); exp_mode = e ? atoi(e) : 0; }
-    match_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, op.qnorm, units, n_units, parts, skip_if_flag, dbg, exp_mode);
+    if (candidates == 4)
+        match_tc_kernel<4><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, op.qnorm, units, n_units, parts, gate_flag, gate_want, dbg, exp_mode);
+    else
+        match_tc_kernel<2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, op.qnorm, units, n_units, parts, gate_flag, gate_want, dbg, exp_mode);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(err, errlen, "match_tc_kernel launch: %s", cudaGetErrorString(e));

@@ -4,18 +4,22 @@
 // dense contraction  acc' = 2 q.t - ||t||^2  so that  d^2 = ||q||^2 - acc'.  SIFT descriptors are
 // integers 0..255: they are exact in bf16, every product and every partial sum is
 // an integer below 2^24, so the fp32 accumulation in TMEM is exact and no re-rank is needed (App. A.6).
-// ||t||^2 (< 2^24) is folded into the contraction through KAUG extra K columns: the train row carries
-// -(a*65536), -(b*256), -c with ||t||^2 = a*65536 + b*256 + c (each piece exact in bf16) against ones
-// on the query side.  Rows that are not integer-valued raise *nonint_flag and the exact fp32 kernel
-// serves the call instead.
+// ||t||^2 is folded into the contraction through KAUG extra K columns: the train row carries -p1, -p2, -p3 with
+// p1 = bf16(tn), p2 = bf16(tn - p1), p3 = bf16(tn - p1 - p2) — three 8-bit pieces that add up to the fp32 value of
+// tn = ||t||^2 exactly (for integer rows tn < 2^24 is the exact norm and every piece is an integer) — against ones on
+// the query side.  *flag collects what the rows are: bit 0 = some value is not an integer in [0, 255] (the
+// accumulator is then only an approximation: the call is served by the candidate + fp32 re-rank path), bit 1 = a
+// norm is not finite or huge (exact SIMT kernel).  *tnmax_bits (train side) = largest ||t||^2 as float bits, for the
+// error bound of the re-rank path.
 #include "common.cuh"
 
 namespace cvg {
 
 // one warp per row; lane handles 4 consecutive floats
 __global__ void prep_rows_kernel(const float* __restrict__ X, int n_rows, int n_pad, int is_train,
-                                 __nv_bfloat16* __restrict__ Xb, __nv_bfloat16* __restrict__ Xaug,
-                                 float* __restrict__ norms, int* __restrict__ nonint_flag)
+                                 __nv_bfloat16* __restrict__ Xb, __nv_bfloat16* __restrict__ Xlo,
+                                 __nv_bfloat16* __restrict__ Xaug,
+                                 float* __restrict__ norms, int* __restrict__ nonint_flag, int* __restrict__ tnmax_bits)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -23,9 +27,11 @@ __global__ void prep_rows_kernel(const float* __restrict__ X, int n_rows, int n_
     const int row = warp;
     __nv_bfloat162* out = reinterpret_cast<__nv_bfloat162*>(Xb + (size_t)row * DIM) + lane * 2;
     __nv_bfloat16* aug = Xaug + (size_t)row * KAUG;
+    __nv_bfloat162* outlo = Xlo ? reinterpret_cast<__nv_bfloat162*>(Xlo + (size_t)row * DIM) + lane * 2 : nullptr;
     if (row >= n_rows) {                      // padding row: never selected / never read back
         out[0] = __floats2bfloat162_rn(0.f, 0.f);
         out[1] = __floats2bfloat162_rn(0.f, 0.f);
+        if (outlo) { outlo[0] = __floats2bfloat162_rn(0.f, 0.f); outlo[1] = __floats2bfloat162_rn(0.f, 0.f); }
         if (lane < KAUG) aug[lane] = __float2bfloat16((is_train && lane == 0) ? -1073741824.f : 0.f);
         if (lane == 0 && norms) norms[row] = 0.f;
         return;
@@ -42,17 +48,37 @@ __global__ void prep_rows_kernel(const float* __restrict__ X, int n_rows, int n_
     #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss = __fadd_rn(ss, __shfl_xor_sync(0xffffffffu, ss, o));
     const bool all_ok = __all_sync(0xffffffffu, ok);
-    if (!all_ok && lane == 0) atomicOr(nonint_flag, 1);
+    if (lane == 0) {
+        int bits = all_ok ? 0 : 1;
+        if (!(ss < 1e30f)) bits |= 2;                        // inf / NaN / out of any sensible range
+        if (bits) atomicOr(nonint_flag, bits);
+        if (tnmax_bits && ss < 1e30f) atomicMax(tnmax_bits, __float_as_int(ss));
+    }
     const float sc = is_train ? 1.f : 2.f;
     out[0] = __floats2bfloat162_rn(e[0] * sc, e[1] * sc);
     out[1] = __floats2bfloat162_rn(e[2] * sc, e[3] * sc);
+    if (outlo) {                                             // x = hi + lo + O(2^-18 |x|); lo == 0 for integers 0..255
+        float lo[4];
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float x = e[k] * sc;                       // exact (sc is 1 or 2)
+            const float hi = __bfloat162float(__float2bfloat16(x));
+            lo[k] = (fabsf(x) < 1e30f) ? __fsub_rn(x, hi) : 0.f;
+        }
+        outlo[0] = __floats2bfloat162_rn(lo[0], lo[1]);
+        outlo[1] = __floats2bfloat162_rn(lo[2], lo[3]);
+    }
     if (lane < KAUG) {
         float a = 0.f;
         if (is_train) {
-            const uint32_t tn = all_ok ? (uint32_t)ss : 0u;      // exact integer < 2^24 when all_ok
-            if (lane == 0) a = -(float)(tn & 0xFF0000u);
-            if (lane == 1) a = -(float)(tn & 0x00FF00u);
-            if (lane == 2) a = -(float)(tn & 0x0000FFu);
+            const float tn = ss < 1e30f ? ss : 0.f;
+            const float p1 = __bfloat162float(__float2bfloat16(tn));
+            const float r1 = __fsub_rn(tn, p1);
+            const float p2 = __bfloat162float(__float2bfloat16(r1));
+            const float p3 = __fsub_rn(r1, p2);                  // <= 8 significant bits left: exact in bf16
+            if (lane == 0) a = -p1;
+            if (lane == 1) a = -p2;
+            if (lane == 2) a = -p3;
         } else {
             a = lane < 3 ? 1.f : 0.f;
         }
@@ -61,13 +87,13 @@ __global__ void prep_rows_kernel(const float* __restrict__ X, int n_rows, int n_
     if (lane == 0 && norms) norms[row] = ss;
 }
 
-void launch_prep_rows(const float* X, int n_rows, int n_pad, int is_train, __nv_bfloat16* Xb,
-                      __nv_bfloat16* Xaug, float* norms, int* nonint_flag, cudaStream_t st)
+void launch_prep_rows(const float* X, int n_rows, int n_pad, int is_train, __nv_bfloat16* Xb, __nv_bfloat16* Xlo,
+                      __nv_bfloat16* Xaug, float* norms, int* nonint_flag, int* tnmax_bits, cudaStream_t st)
 {
     if (n_pad <= 0) return;
     const int threads = 256;
     const int blocks = (int)(((int64_t)n_pad * 32 + threads - 1) / threads);
-    prep_rows_kernel<<<blocks, threads, 0, st>>>(X, n_rows, n_pad, is_train, Xb, Xaug, norms, nonint_flag);
+    prep_rows_kernel<<<blocks, threads, 0, st>>>(X, n_rows, n_pad, is_train, Xb, Xlo, Xaug, norms, nonint_flag, tnmax_bits);
 }
 
 __global__ void pack_points_kernel(const float2* __restrict__ src, const float2* __restrict__ dst, int64_t n,

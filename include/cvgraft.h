@@ -190,9 +190,14 @@ int  cvg_dev_merge_top2(cvg_ctx* ctx, void* stream, const float* dist_parts_dev,
                         int32_t* idx_dev, float* dist_dev, uint8_t* accept_dev);
 
 /* ---- introspection for tests / bench --------------------------------------------------------- */
-/* Which match kernel served the last match call on this context: 1 = tcgen05 tensor-core kernel,
- * 2 = exact fp32 SIMT kernel (non-integer descriptors), 0 = none yet. */
+/* Which match path served the last match call on this context: 1 = tcgen05 tensor-core kernel, exact (integer
+ * descriptors, what SIFT emits); 3 = tcgen05 kernel on hi/lo split bf16 operands keeping four candidates per row,
+ * then an fp32 re-rank in cv::batchDistance's summation order that proves the answer with an error bound
+ * (non-integer descriptors; unproven rows are redone exactly); 2 = exact fp32 SIMT kernel (CVG_FORCE_EXACT_MATCH,
+ * non-finite values); 0 = none yet.  Results are cv2's bit for bit on every path. */
 int  cvg_last_match_path(const cvg_ctx* ctx);
+/* Rows of the last path-3 call that the re-rank could not prove and the exact fallback kernel redid. */
+int  cvg_last_match_fallback_rows(const cvg_ctx* ctx);
 /* The context's cudaStream_t (all of its GPU work is issued there); lets a harness record its own
  * CUDA events around calls. */
 void* cvg_stream(const cvg_ctx* ctx);

@@ -59,11 +59,64 @@ def test_match_ties_and_duplicates(ctx, api, gsynth):
     assert np.array_equal(dist, gsynth["knn_int_dist"])
 
 
-def test_match_exact_path_float_descriptors(ctx, api, gsynth):
-    idx, dist, acc = ctx.match_knn2(gsynth["knn_float_q"], gsynth["knn_float_t"])
-    assert ctx.last_match_path == api.PATH_EXACT             # non-integer data is routed to the fp32 kernel
-    assert np.array_equal(idx, gsynth["knn_float_idx"])
-    assert np.array_equal(dist, gsynth["knn_float_dist"])    # cv::batchDistance summation order, bit-exact
+def test_match_float_descriptors_candidate_path_and_exact_path(ctx, ctx_exact, api, gsynth):
+    """Non-integer descriptors: tensor-core candidates + fp32 re-rank with proof (+ exact fallback rows) must give
+    cv2's indices and distances bit for bit, like the exact SIMT kernel (cv::batchDistance summation order)."""
+    for c, path in ((ctx, api.PATH_TENSOR_RERANK), (ctx_exact, api.PATH_EXACT)):
+        idx, dist, acc = c.match_knn2(gsynth["knn_float_q"], gsynth["knn_float_t"])
+        assert c.last_match_path == path
+        assert np.array_equal(idx, gsynth["knn_float_idx"])
+        assert np.array_equal(dist, gsynth["knn_float_dist"])
+
+
+def test_match_float_candidate_path_stress(ctx, ctx_exact, api, oracle):
+    """Shapes and data that stress the candidate path's proof: near-duplicate train rows (distance gaps far below the
+    bf16 error bound -> fallback rows), exact duplicates (ties -> lower index), tiny and ragged sizes, mixed integer
+    query vs float train, large dynamic range, unit-norm (RootSIFT-like) rows."""
+    rng = np.random.default_rng(1103)
+    cases = []
+    q = synth.float_desc(rng, 300, 128); t = synth.float_desc(rng, 2000, 128)
+    t[500:700] = t[0:200] + rng.normal(0, 1e-3, size=(200, 128)).astype(np.float32)     # near duplicates
+    t[900] = t[17]; t[1500] = t[17]                                                     # exact duplicates
+    q[:50] = t[rng.integers(0, 2000, 50)] + rng.normal(0, 0.5, size=(50, 128)).astype(np.float32)
+    q[7] = t[17]
+    cases.append((q, t))
+    for nq, nt in [(1, 3), (5, 4), (129, 5), (77, 257), (260, 1000)]:
+        cases.append((synth.float_desc(rng, nq, 128), synth.float_desc(rng, nt, 128)))
+    qi, ti, _ = synth.planted_pair(rng, 200, 900)
+    cases.append((qi, ti + np.float32(0.25)))                                           # integer queries, float train
+    cases.append((qi + np.float32(0.5), ti))
+    u = np.abs(rng.standard_normal((400, 128))).astype(np.float32); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    cases.append((np.sqrt(u[:100]).astype(np.float32), np.sqrt(u[100:]).astype(np.float32)))
+    big = (synth.float_desc(rng, 150, 128) * np.float32(1e4)).astype(np.float32)
+    cases.append((big[:50], big[50:]))
+    n_fallback = 0
+    for q, t in cases:
+        got = ctx.match_knn2(q, t)
+        assert ctx.last_match_path == api.PATH_TENSOR_RERANK
+        n_fallback += ctx.last_match_fallback_rows
+        oi, od = oracle.knn2(q, t, nthreads=8)
+        _assert_match(got, (oi, od, oracle.ratio(oi, od)))
+        ref = ctx_exact.match_knn2(q, t)
+        for x, y in zip(got, ref):
+            assert np.array_equal(x, y)
+    assert n_fallback > 0                                    # the near-duplicate rows cannot be proven: fallback exercised
+
+
+def test_match_float_8k_candidate_path(ctx, api, oracle):
+    """8192 x 8192 non-integer descriptors (BASELINE config 3 shape, 'float' generator of SURVEY 8d) through the
+    candidate path: bit-equal to the CPU oracle on 1024 sampled rows."""
+    rng = np.random.default_rng(3103)
+    q = synth.float_desc(rng, 8192, 128); t = synth.float_desc(rng, 8192, 128)
+    rows = rng.permutation(8192)[:4096]
+    t[rows[:2048]] = q[rows[2048:]] + rng.normal(0, 6.0, size=(2048, 128)).astype(np.float32)   # planted neighbours
+    idx, dist, acc = ctx.match_knn2(q, t)
+    assert ctx.last_match_path == api.PATH_TENSOR_RERANK
+    assert ctx.last_match_fallback_rows < 82                 # < 1 % of the rows need the exact fallback
+    chk = rng.permutation(8192)[:1024]
+    oi, od = oracle.knn2(q[chk], t, nthreads=8)
+    assert np.array_equal(idx[chk], oi) and np.array_equal(dist[chk], od)
+    assert np.array_equal(acc[chk], oracle.ratio(oi, od))
 
 
 def test_match_both_paths_agree(ctx, ctx_exact, api):
@@ -363,7 +416,7 @@ def test_async_upload_pipeline_equals_sync(ctx, feats, api):
     off = np.asarray(so[:n_sc + 1], np.int64)
     d_int = np.ascontiguousarray(feats["scene_desc"][:off[-1]].astype(np.float32))
     kp = np.ascontiguousarray(feats["scene_kpt"][:off[-1]].astype(np.float32))
-    d_flt = d_int.copy(); d_flt[::7, 3] += 0.25                          # non-integer rows -> exact kernel
+    d_flt = d_int.copy(); d_flt[::7, 3] += 0.25                          # non-integer rows -> candidate path
     want = []
     for d in (d_int, d_flt):
         sc = ctx.upload_scenes(d, kp, off)
@@ -374,7 +427,7 @@ def test_async_upload_pipeline_equals_sync(ctx, feats, api):
     rb = ctx.detect_scenes(models, b).copy(); pb = ctx.last_match_path
     b.wait()
     a.free(); b.free()
-    assert pa == api.PATH_TENSOR and pb == api.PATH_EXACT
+    assert pa == api.PATH_TENSOR and pb == api.PATH_TENSOR_RERANK
     for got, w in zip((ra, rb), want):
         assert np.array_equal(got["status"], w["status"]) and np.array_equal(got["n_inliers"], w["n_inliers"])
         assert np.array_equal(got["H"], w["H"])
