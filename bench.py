@@ -54,20 +54,26 @@ def load_peaks():
     return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback"}
 
 
-def make_workload(seed, n_scenes, n_batches):
-    """One model view + n_batches batches of n_scenes scene sets (planted matches, 30% geometric inliers)."""
+def make_workload(seed, n_scenes, n_batches, desc="sift"):
+    """One model view + n_batches batches of n_scenes scene sets (planted matches, 30% geometric inliers).
+    desc = "sift": integer-valued fp32 rows as cv2 SIFT emits them; "float": non-integer rows (SURVEY 8d 'float'
+    generator), which take the candidate + fp32 re-rank match path."""
     rng = np.random.default_rng(seed)
-    q = synth.sift_like(rng, NQ)
+    gen = synth.sift_like if desc == "sift" else synth.float_desc
+    q = gen(rng, NQ)
     qk = rng.uniform([0, 0], [640, 480], size=(NQ, 2)).astype(np.float32)
     batches = []
     for _ in range(n_batches):
         descs, kpts = [], []
         for _ in range(n_scenes):
-            t = synth.sift_like(rng, NT)
+            t = gen(rng, NT)
             tk = rng.uniform([0, 0], [640, 480], size=(NT, 2)).astype(np.float32)
             k = NQ // 2                                           # 50% planted matches
             rq = rng.permutation(NQ)[:k]; rt = rng.permutation(NT)[:k]
-            t[rt] = np.clip(q[rq] + np.round(rng.normal(0, 12.0, size=(k, DIM))).astype(np.float32), 0, 255)
+            if desc == "sift":
+                t[rt] = np.clip(q[rq] + np.round(rng.normal(0, 12.0, size=(k, DIM))).astype(np.float32), 0, 255)
+            else:
+                t[rt] = q[rq] + rng.normal(0, 6.0, size=(k, DIM)).astype(np.float32)
             H = synth.random_homography(rng)
             geo = rng.random(k) < 0.3                             # 30% of the planted matches follow H
             p = np.c_[qk[rq[geo]], np.ones(int(geo.sum()))] @ H.T
@@ -165,7 +171,7 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     pairs_per_step = max(2, min(threads, 32))            # enough pairs per step to keep every thread busy in the verify stage
-    q, qk, batches = make_workload(3000, pairs_per_step, 1)
+    q, qk, batches = make_workload(3000, pairs_per_step, 1, args.desc)
     for _ in range(args.warmup):
         cpu_pairs(q, qk, batches[0], 2, threads)
     total = 0.0; kind = "reference"
@@ -197,7 +203,7 @@ def run_cvgraft(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B, R = args.pairs, args.batches
-    q, qk, batches = make_workload(3000 + rank, B, R)
+    q, qk, batches = make_workload(3000 + rank, B, R, args.desc)
     ctx = api.Context(local)
     ctx.set_timing(True)
     models = ctx.upload_models(q, qk, [0, NQ], [0])
@@ -300,6 +306,9 @@ def run_cvgraft(args):
                 "dtype": "bf16 operands (exact for u8 descriptors) / f32 accumulate; f64+f32 verify", "data": "synthetic",
                 "config": {"workload": "c3: 1 resident model view x 8192 desc vs B scenes x 8192 desc, ratio 0.9, "
                                        "RANSAC 2000 iters thr 5.0 conf 0.995", "pairs_per_step_per_gpu": B,
+                           "descriptors": "fp32, integer-valued 0..255 (SIFT-like)" if args.desc == "sift" else
+                                          "fp32, non-integer (candidate + fp32 re-rank match path)",
+                           "match_path": ctx.last_match_path,
                            "scene_batches_rotated": R, "parallelism": f"pair-sharded x{world}, no data-path collective",
                            "l2": f"{R} rotating batches, {R * B * NT * DIM * 2 / 2**20:.0f} MiB of bf16 operands > 126 MB L2"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -356,6 +365,8 @@ def main():
     ap.add_argument("--batches", type=int, default=4, help="distinct scene batches rotated over the steps")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--desc", default="sift", choices=["sift", "float"],
+                    help="descriptor generator: integer-valued SIFT-like rows (default) or non-integer float rows")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cvgraft" else args.warmup
     if args.impl == "reference":
