@@ -1043,8 +1043,13 @@ int cvg_dev_match_top2(cvg_ctx* c, void* stream, const float* query_dev, int n_q
     if (!units.empty()) CU_CHECK(cudaMemcpyAsync(c->units.p, units.data(), units.size() * sizeof(MatchUnit), cudaMemcpyHostToDevice, c->stream));
     CU_CHECK(cudaMemcpyAsync(c->dir.p, dir.data(), dir.size() * sizeof(MergeEntry), cudaMemcpyHostToDevice, c->stream));
     CU_CHECK(cudaStreamSynchronize(c->stream));
+    // this entry point does not synchronise: the mapped staging area (reset by the next synchronous call) must not
+    // carry parameter blocks that a still-queued copy kernel has to read
+    const size_t stage_saved = c->stage_used;
+    c->stage_used = c->stage_cap;
     rc = launch_match(c, q, ts, c->units.as<MatchUnit>(), (int)units.size(), c->dir.as<MergeEntry>(), n_rb, 0.9f, 0,
                       c->parts.as<Top2>(), c->idx.as<int32_t>(), c->dist.as<float>(), nullptr);
+    c->stage_used = stage_saved;
     if (rc) return rc;
     launch_shift_index(c->idx.as<int32_t>(), c->dist.as<float>(), n_query, train_index_base, dist_dev, idx_dev, c->stream);
     c->launches++;

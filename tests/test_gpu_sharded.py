@@ -18,12 +18,18 @@ def test_logical_shards_on_one_gpu(oracle):
     import torch
     from computervision_objectdetection_featurematching_b200 import api
     rng = np.random.default_rng(21)
+    datasets = []
     q, t, _ = synth.planted_pair(rng, 700, 5000)
     t[2600] = t[100]; q[9] = t[100]                              # tie across shards
-    oi, od = oracle.knn2(q, t, nthreads=8)
-    oa = oracle.ratio(oi, od)
+    datasets.append((q, t))
+    qf = synth.float_desc(rng, 700, 128); tf = synth.float_desc(rng, 5000, 128)      # candidate + re-rank path per shard
+    tf[3100] = tf[40]; qf[5] = tf[40]; tf[4000:4100] = tf[:100] + np.float32(1e-3)
+    datasets.append((qf, tf))
     dev = torch.device("cuda", 0)
     with api.Context(0) as ctx:
+      for q, t in datasets:
+        oi, od = oracle.knn2(q, t, nthreads=8)
+        oa = oracle.ratio(oi, od)
         qd = torch.from_numpy(q).to(dev); td = torch.from_numpy(t).to(dev)
         for world in (1, 2, 4):
             dp = torch.empty((world, 700, 2), dtype=torch.float32, device=dev)
