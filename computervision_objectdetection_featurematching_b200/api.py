@@ -153,6 +153,15 @@ class Context:
         self._check(self.lib.cvg_scenes_upload_async(self.handle, _ptr(d), _ptr(k), _ptr(off), len(off) - 1, C.byref(h)))
         return Scenes(self, h, off, keep=(d, k, off))
 
+    def upload_scenes_u8_async(self, descriptors_u8, keypoints_xy, offsets):
+        """Streaming upload of uint8 descriptor rows [N,128] (a quarter of the PCIe bytes of the fp32 form)."""
+        d = np.ascontiguousarray(descriptors_u8, dtype=np.uint8).reshape(-1, 128)
+        k = _f32(keypoints_xy, 2) if keypoints_xy is not None else None
+        off = np.ascontiguousarray(offsets, np.int64)
+        h = C.c_void_p()
+        self._check(self.lib.cvg_scenes_upload_u8_async(self.handle, _ptr(d), _ptr(k), _ptr(off), len(off) - 1, C.byref(h)))
+        return Scenes(self, h, off, keep=(d, k, off))
+
     # ---- match stage ---------------------------------------------------------------------------
     def match_knn2(self, query, train, ratio=0.9, view=-1):
         """query: Models (resident, optionally one view) or an [nq,128] array.  -> idx[nq,2] (-1 = absent),

@@ -106,13 +106,9 @@ struct cvg_models {
 
 struct cvg_scenes {
     TrainSet ts;
-    DevBuf f32, b, blo, aug, kpt, kptoff;
+    DevBuf f32, b, blo, aug, kpt, kptoff, u8, segtab;
     int* d_flag = nullptr;             // non-integer flag of this batch (tail of kptoff)
     cudaEvent_t ready = nullptr;       // set by cvg_scenes_upload_async: upload + conversion finished
-    // cached match plan for a given model set
-    const cvg_models* plan_models = nullptr;
-    int plan_units = 0, plan_slots = 0;
-    DevBuf units, dir;
 };
 
 struct cvg_ctx {
@@ -131,9 +127,11 @@ struct cvg_ctx {
     unsigned long long* d_scored = nullptr;
     // scratch
     DevBuf q_f32, q_b, q_blo, q_aug, q_norm;           // raw-query path
-    DevBuf t_f32, t_b, t_blo, t_aug, t_kpt, t_kptoff;  // per-call train path
+    DevBuf t_f32, t_b, t_blo, t_aug, t_kpt, t_kptoff, t_segtab;  // per-call train path
     DevBuf units, dir, parts, idx, dist, accept;
     DevBuf parts4, segdev, fb;                         // candidate path: Top4 records, segment table, unproven rows
+    DevBuf plan_units, plan_dir;                       // match plan of the fused path, cached by (model set, scene shapes)
+    const cvg_models* plan_models = nullptr; std::vector<int> plan_shape; int plan_units_n = 0;
     DevBuf pts, starts, counts_n, sample_pos, n_samples, counts, best_iter, best_count, iters_run, niters_cur, smp_state, sel;
     DevBuf H, mask, rmask, found, sflags, results, inl_xy, inl_cnt, scales, src, dst;
     BufPool pool;                                      // recycled buffers of freed scene batches
@@ -228,8 +226,8 @@ void cvg_destroy(cvg_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
-    DevBuf* bufs[] = { &c->q_f32, &c->q_b, &c->q_blo, &c->q_aug, &c->q_norm, &c->t_f32, &c->t_b, &c->t_blo, &c->t_aug, &c->t_kpt, &c->t_kptoff,
-                       &c->units, &c->dir, &c->parts, &c->parts4, &c->segdev, &c->fb, &c->idx, &c->dist, &c->accept, &c->pts, &c->starts, &c->counts_n,
+    DevBuf* bufs[] = { &c->q_f32, &c->q_b, &c->q_blo, &c->q_aug, &c->q_norm, &c->t_f32, &c->t_b, &c->t_blo, &c->t_aug, &c->t_segtab, &c->t_kpt, &c->t_kptoff,
+                       &c->units, &c->dir, &c->parts, &c->parts4, &c->segdev, &c->fb, &c->plan_units, &c->plan_dir, &c->idx, &c->dist, &c->accept, &c->pts, &c->starts, &c->counts_n,
                        &c->sample_pos, &c->n_samples, &c->counts, &c->best_iter, &c->best_count, &c->iters_run, &c->niters_cur, &c->smp_state, &c->sel,
                        &c->H, &c->mask, &c->rmask, &c->found, &c->sflags, &c->results, &c->inl_xy, &c->inl_cnt,
                        &c->scales, &c->src, &c->dst };
@@ -307,8 +305,8 @@ static int ensure_rng(cvg_ctx* c, int max_iters, int64_t min_len = 0)
 }
 
 // Prepare (convert) a train set that is already in device fp32 memory.
-static int prep_train(cvg_ctx* c, TrainSet& ts, DevBuf& b, DevBuf& blo, DevBuf& aug, int flag_slot, bool pooled = false,
-                      cudaStream_t st = nullptr, int* d_flag = nullptr)
+static int prep_train(cvg_ctx* c, TrainSet& ts, DevBuf& b, DevBuf& blo, DevBuf& aug, DevBuf& segtab, int flag_slot,
+                      bool pooled = false, cudaStream_t st = nullptr, int* d_flag = nullptr)
 {
     if (!st) st = c->stream;
     if (!d_flag) d_flag = c->d_flags + flag_slot;
@@ -319,10 +317,20 @@ static int prep_train(cvg_ctx* c, TrainSet& ts, DevBuf& b, DevBuf& blo, DevBuf& 
     if (pooled) { CU_CHECK(c->pool.acquire(b, nb)); CU_CHECK(c->pool.acquire(blo, nb)); CU_CHECK(c->pool.acquire(aug, na)); }
     else { CU_CHECK(b.ensure(nb)); CU_CHECK(blo.ensure(nb)); CU_CHECK(aug.ensure(na)); }
     ts.d_b = b.as<__nv_bfloat16>(); ts.d_blo = blo.as<__nv_bfloat16>(); ts.d_aug = aug.as<__nv_bfloat16>();
-    for (const SegInfo& s : ts.segs) {
-        const int n_pad = s.ct * TILE_N;
-        launch_prep_rows(ts.d_f32 + s.f32_row0 * DIM, s.rows, n_pad, 1, ts.d_b + s.pad_row0 * DIM,
-                         ts.d_blo + s.pad_row0 * DIM, ts.d_aug + s.pad_row0 * KAUG, nullptr, d_flag, ts.d_tnmax, st);
+    if (ts.n_segs == 1) {
+        const SegInfo& s = ts.segs[0];
+        launch_prep_rows(ts.d_f32 + s.f32_row0 * DIM, s.rows, s.ct * TILE_N, 1, ts.d_b, ts.d_blo, ts.d_aug, nullptr, d_flag,
+                         ts.d_tnmax, st);
+        c->launches++;
+    } else if (ts.n_segs > 1) {
+        // one launch for the whole batch: the segment table rides in front of the augmentation buffer's slack
+        std::vector<PrepSeg> tab((size_t)ts.n_segs);
+        for (int i = 0; i < ts.n_segs; i++) tab[(size_t)i] = PrepSeg{ ts.segs[(size_t)i].f32_row0, ts.segs[(size_t)i].pad_row0, ts.segs[(size_t)i].rows, 0 };
+        if (pooled) CU_CHECK(c->pool.acquire(segtab, tab.size() * sizeof(PrepSeg)));
+        else CU_CHECK(segtab.ensure(tab.size() * sizeof(PrepSeg)));
+        CU_CHECK(cudaMemcpyAsync(segtab.p, tab.data(), tab.size() * sizeof(PrepSeg), cudaMemcpyHostToDevice, st));   // pageable: staged before return
+        launch_prep_train_segments(ts.d_f32, segtab.as<PrepSeg>(), ts.n_segs, ts.rows_pad_total, ts.d_b, ts.d_blo, ts.d_aug,
+                                   d_flag, ts.d_tnmax, st);
         c->launches++;
     }
     CU_CHECK(cudaGetLastError());
@@ -576,6 +584,7 @@ int cvg_models_upload(cvg_ctx* c, const float* desc, const float* kpt_xy, const 
 
 void cvg_models_free(cvg_ctx* c, cvg_models* m)
 {
+    if (c && c->plan_models == m) { c->plan_models = nullptr; c->plan_units_n = 0; }   // a later set may reuse the address
     if (!m) return;
     if (c) cudaSetDevice(c->device);
     cudaFree(m->d_f32); cudaFree(m->d_b); cudaFree(m->d_blo); cudaFree(m->d_aug); cudaFree(m->d_norm); cudaFree(m->d_kpt);
@@ -603,7 +612,7 @@ static int match_host_train(cvg_ctx* c, QuerySide q, int q_nonint, const float* 
     ts.d_f32 = c->t_f32.as<float>();
     if (n_train > 0) CU_CHECK(cudaMemcpyAsync(ts.d_f32, train, (size_t)n_train * DIM * 4, cudaMemcpyHostToDevice, c->stream));
     CU_CHECK(cudaMemsetAsync(c->d_flags, 0, 4, c->stream));
-    int rc = prep_train(c, ts, c->t_b, c->t_blo, c->t_aug, 0);
+    int rc = prep_train(c, ts, c->t_b, c->t_blo, c->t_aug, c->t_segtab, 0);
     if (rc) return rc;
     CU_CHECK(cudaMemcpyAsync(c->d_flags + 1, &q_nonint, 4, cudaMemcpyHostToDevice, c->stream));
     combine_flags_kernel<<<1, 1, 0, c->stream>>>(c->d_flags, c->d_flags, (c->flags & CVG_FORCE_EXACT_MATCH) ? 4 : 0);
@@ -750,26 +759,24 @@ static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, Tra
     QuerySide q{ m->d_f32, m->d_b, m->d_blo, m->d_aug, m->d_norm, 0, nq, m->n_pad };
     int n_units = 0, n_rb = 0;
     const MatchUnit* d_units; const MergeEntry* d_dir;
-    if (cache && cache->plan_models == m) {
-        n_units = cache->plan_units; n_rb = (nq + TILE_M - 1) / TILE_M;
-        d_units = cache->units.as<MatchUnit>(); d_dir = cache->dir.as<MergeEntry>();
+    // The match plan depends only on the model set and on the row counts of the scenes: a streaming caller whose
+    // batches have the same shape (same number of descriptors per scene) reuses the plan already on the device.
+    std::vector<int> shape((size_t)S);
+    for (int i = 0; i < S; i++) shape[(size_t)i] = ts.segs[(size_t)i].rows;
+    if (c->plan_models == m && c->plan_shape == shape && c->plan_units_n > 0) {
+        n_units = c->plan_units_n; n_rb = (nq + TILE_M - 1) / TILE_M;
+        d_units = c->plan_units.as<MatchUnit>(); d_dir = c->plan_dir.as<MergeEntry>();
     } else {
         std::vector<MatchUnit> units; std::vector<MergeEntry> dir;
         build_plan(q, ts, c->n_sms, units, dir, n_rb);
-        DevBuf& ub = cache ? cache->units : c->units; DevBuf& db = cache ? cache->dir : c->dir;
-        if (cache) {
-            CU_CHECK(c->pool.acquire(ub, std::max<size_t>(units.size(), 1) * sizeof(MatchUnit) + 16));
-            CU_CHECK(c->pool.acquire(db, std::max<size_t>(dir.size(), 1) * sizeof(MergeEntry) + 16));
-        } else {
-            CU_CHECK(ub.ensure(std::max<size_t>(units.size(), 1) * sizeof(MatchUnit) + 16));
-            CU_CHECK(db.ensure(std::max<size_t>(dir.size(), 1) * sizeof(MergeEntry) + 16));
-        }
-        if (!units.empty()) CU_CHECK(h2d_small(c, ub.p, units.data(), units.size() * sizeof(MatchUnit)));
-        if (!dir.empty()) CU_CHECK(h2d_small(c, db.p, dir.data(), dir.size() * sizeof(MergeEntry)));
+        CU_CHECK(c->plan_units.ensure(std::max<size_t>(units.size(), 1) * sizeof(MatchUnit) + 16));
+        CU_CHECK(c->plan_dir.ensure(std::max<size_t>(dir.size(), 1) * sizeof(MergeEntry) + 16));
+        if (!units.empty()) CU_CHECK(h2d_small(c, c->plan_units.p, units.data(), units.size() * sizeof(MatchUnit)));
+        if (!dir.empty()) CU_CHECK(h2d_small(c, c->plan_dir.p, dir.data(), dir.size() * sizeof(MergeEntry)));
         if (c->stage_fallback) CU_CHECK(cudaStreamSynchronize(c->stream));    // memcpy fallback: host vectors go out of scope
         n_units = (int)units.size();
-        d_units = ub.as<MatchUnit>(); d_dir = db.as<MergeEntry>();
-        if (cache) { cache->plan_models = m; cache->plan_units = n_units; }
+        d_units = c->plan_units.as<MatchUnit>(); d_dir = c->plan_dir.as<MergeEntry>();
+        c->plan_models = m; c->plan_shape = shape; c->plan_units_n = n_units;
     }
     const size_t rows = (size_t)S * std::max(nq, 1);
     CU_CHECK(c->parts.ensure(std::max<size_t>(n_units, 1) * TILE_M * sizeof(Top2)));
@@ -878,7 +885,7 @@ int cvg_detect_pairs(cvg_ctx* c, const cvg_models* m, const float* scene_desc, c
     std::vector<float> scales(std::max(V, 1), scale);
     CU_CHECK(cudaMemcpyAsync(c->scales.p, scales.data(), scales.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CU_CHECK(cudaMemsetAsync(c->d_flags, 0, 4, c->stream));
-    rc = prep_train(c, ts, c->t_b, c->t_blo, c->t_aug, 0);
+    rc = prep_train(c, ts, c->t_b, c->t_blo, c->t_aug, c->t_segtab, 0);
     if (rc) return rc;
     ts.nonint = -1;                                    // decided on the device
     const bool want_inl = inlier_scene_xy != nullptr && inlier_offsets != nullptr;
@@ -900,8 +907,17 @@ int cvg_detect_pairs(cvg_ctx* c, const cvg_models* m, const float* scene_desc, c
     return CVG_OK;
 }
 
-static int scenes_upload_impl(cvg_ctx* c, const float* desc, const float* kpt_xy, const int64_t* offsets, int n_scenes,
-                              cvg_scenes** out, bool async)
+// uint8 descriptor rows (cv::SIFT with descriptorType = CV_8U) -> the fp32 rows every kernel reads
+__global__ void u8_to_f32_kernel(const uchar4* __restrict__ in, float4* __restrict__ out, size_t n4)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const uchar4 v = in[i];
+        out[i] = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+    }
+}
+
+static int scenes_upload_impl(cvg_ctx* c, const float* desc, const uint8_t* desc_u8, const float* kpt_xy,
+                              const int64_t* offsets, int n_scenes, cvg_scenes** out, bool async)
 {
     if (!c || !out || !offsets || n_scenes < 0) return set_err(CVG_ERR_INVALID, "cvg_scenes_upload: bad argument");
     *out = nullptr;
@@ -909,7 +925,7 @@ static int scenes_upload_impl(cvg_ctx* c, const float* desc, const float* kpt_xy
     for (int s = 0; s < n_scenes; s++)
         if (offsets[s + 1] < offsets[s]) return set_err(CVG_ERR_INVALID, "offsets must be non-decreasing");
     const int64_t total = offsets[n_scenes];
-    if (total > 0 && !desc) return set_err(CVG_ERR_INVALID, "NULL desc");
+    if (total > 0 && !desc && !desc_u8) return set_err(CVG_ERR_INVALID, "NULL desc");
     cvg_scenes* sc = new cvg_scenes();
     layout_segments(sc->ts, offsets, n_scenes);
     if (sc->ts.rows_pad_total > 0x7fffff00LL) { delete sc; return set_err(CVG_ERR_LIMIT, "scene batch too large (>2^31 padded rows)"); }
@@ -920,12 +936,19 @@ static int scenes_upload_impl(cvg_ctx* c, const float* desc, const float* kpt_xy
     sc->ts.d_f32 = sc->f32.as<float>(); sc->ts.d_kpt = sc->kpt.as<float>(); sc->ts.d_kpt_offsets = sc->kptoff.as<int64_t>();
     sc->d_flag = reinterpret_cast<int*>(sc->kptoff.as<int64_t>() + (n_scenes + 1));
     sc->ts.d_tnmax = sc->d_flag + 1;
-    if (total > 0) CU_CHECK(cudaMemcpyAsync(sc->ts.d_f32, desc, (size_t)total * DIM * 4, cudaMemcpyHostToDevice, st));
+    if (total > 0 && desc_u8) {                                 // a quarter of the PCIe bytes; widened on the device
+        CU_CHECK(c->pool.acquire(sc->u8, (size_t)total * DIM));
+        CU_CHECK(cudaMemcpyAsync(sc->u8.p, desc_u8, (size_t)total * DIM, cudaMemcpyHostToDevice, st));
+        const size_t n4 = (size_t)total * DIM / 4;
+        u8_to_f32_kernel<<<(unsigned)std::min<size_t>((n4 + 255) / 256, (size_t)c->n_sms * 16), 256, 0, st>>>(
+            sc->u8.as<uchar4>(), reinterpret_cast<float4*>(sc->ts.d_f32), n4);
+        c->launches++;
+    } else if (total > 0) CU_CHECK(cudaMemcpyAsync(sc->ts.d_f32, desc, (size_t)total * DIM * 4, cudaMemcpyHostToDevice, st));
     if (total > 0 && kpt_xy) CU_CHECK(cudaMemcpyAsync(sc->ts.d_kpt, kpt_xy, (size_t)total * 8, cudaMemcpyHostToDevice, st));
     else if (total > 0) CU_CHECK(cudaMemsetAsync(sc->ts.d_kpt, 0, (size_t)total * 8, st));
     CU_CHECK(cudaMemcpyAsync(sc->ts.d_kpt_offsets, offsets, (size_t)(n_scenes + 1) * 8, cudaMemcpyHostToDevice, st));
     CU_CHECK(cudaMemsetAsync(sc->d_flag, 0, 8, st));
-    int rc = prep_train(c, sc->ts, sc->b, sc->blo, sc->aug, 0, true, st, sc->d_flag);
+    int rc = prep_train(c, sc->ts, sc->b, sc->blo, sc->aug, sc->segtab, 0, true, st, sc->d_flag);
     if (rc) { cvg_scenes_free(c, sc); return rc; }
     if (async) {
         // the caller's buffers are read by the copy engine until `ready`; cvg_detect_scenes orders itself after it
@@ -945,13 +968,19 @@ static int scenes_upload_impl(cvg_ctx* c, const float* desc, const float* kpt_xy
 int cvg_scenes_upload(cvg_ctx* c, const float* desc, const float* kpt_xy, const int64_t* offsets, int n_scenes,
                       cvg_scenes** out)
 {
-    return scenes_upload_impl(c, desc, kpt_xy, offsets, n_scenes, out, false);
+    return scenes_upload_impl(c, desc, nullptr, kpt_xy, offsets, n_scenes, out, false);
 }
 
 int cvg_scenes_upload_async(cvg_ctx* c, const float* desc, const float* kpt_xy, const int64_t* offsets, int n_scenes,
                             cvg_scenes** out)
 {
-    return scenes_upload_impl(c, desc, kpt_xy, offsets, n_scenes, out, true);
+    return scenes_upload_impl(c, desc, nullptr, kpt_xy, offsets, n_scenes, out, true);
+}
+
+int cvg_scenes_upload_u8_async(cvg_ctx* c, const uint8_t* desc, const float* kpt_xy, const int64_t* offsets, int n_scenes,
+                               cvg_scenes** out)
+{
+    return scenes_upload_impl(c, nullptr, desc, kpt_xy, offsets, n_scenes, out, true);
 }
 
 int cvg_scenes_wait(cvg_ctx* c, cvg_scenes* sc)
@@ -974,11 +1003,10 @@ void cvg_scenes_free(cvg_ctx* c, cvg_scenes* sc)
     if (sc->ready) { cudaEventSynchronize(sc->ready); cudaEventDestroy(sc->ready); sc->ready = nullptr; }
     if (c) {
         cudaSetDevice(c->device);
-        DevBuf* bufs[] = { &sc->f32, &sc->b, &sc->blo, &sc->aug, &sc->kpt, &sc->kptoff, &sc->units, &sc->dir };
+        DevBuf* bufs[] = { &sc->f32, &sc->b, &sc->blo, &sc->aug, &sc->kpt, &sc->kptoff, &sc->u8, &sc->segtab };
         for (DevBuf* b : bufs) c->pool.release(*b);
     } else {
-        sc->f32.release(); sc->b.release(); sc->blo.release(); sc->aug.release(); sc->kpt.release(); sc->kptoff.release();
-        sc->units.release(); sc->dir.release();
+        sc->f32.release(); sc->b.release(); sc->blo.release(); sc->aug.release(); sc->u8.release(); sc->segtab.release(); sc->kpt.release(); sc->kptoff.release();
     }
     delete sc;
 }
@@ -1029,7 +1057,7 @@ int cvg_dev_match_top2(cvg_ctx* c, void* stream, const float* query_dev, int n_q
     const int64_t offs[2] = { 0, n_train };
     layout_segments(ts, offs, 1);
     ts.d_f32 = const_cast<float*>(train_dev);
-    int rc = prep_train(c, ts, c->t_b, c->t_blo, c->t_aug, 0);
+    int rc = prep_train(c, ts, c->t_b, c->t_blo, c->t_aug, c->t_segtab, 0);
     if (rc) return rc;
     combine_flags_kernel<<<1, 1, 0, c->stream>>>(c->d_flags, c->d_flags, (c->flags & CVG_FORCE_EXACT_MATCH) ? 4 : 0);
     c->launches++;

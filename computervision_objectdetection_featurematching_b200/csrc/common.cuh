@@ -56,6 +56,10 @@ struct MergeEntry {
 void launch_prep_rows(const float* X, int n_rows, int n_pad, int is_train, __nv_bfloat16* Xb,
                       __nv_bfloat16* Xlo /*lo half: bf16(x - hi), zero for integer rows; or NULL*/, __nv_bfloat16* Xaug, float* norms, int* nonint_flag /*bit0 non-integer, bit1 non-finite*/,
                       int* tnmax_bits /*train side: max ||t||^2 as float bits, or NULL*/, cudaStream_t st);
+struct PrepSeg { int64_t f32_row0; int64_t pad_row0; int32_t rows; int32_t pad; };   // ascending pad_row0
+void launch_prep_train_segments(const float* X, const PrepSeg* segs_dev, int n_segs, int64_t rows_pad_total,
+                                __nv_bfloat16* Xb, __nv_bfloat16* Xlo, __nv_bfloat16* Xaug, int* nonint_flag,
+                                int* tnmax_bits, cudaStream_t st);
 void launch_pack_points(const float* src_xy, const float* dst_xy, int64_t n, float4* pts, cudaStream_t st);
 
 // match_exact.cu — fp32 SIMT kernel in cv::batchDistance's summation order

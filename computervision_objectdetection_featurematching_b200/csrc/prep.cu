@@ -15,16 +15,14 @@
 
 namespace cvg {
 
-// one warp per row; lane handles 4 consecutive floats
-__global__ void prep_rows_kernel(const float* __restrict__ X, int n_rows, int n_pad, int is_train,
-                                 __nv_bfloat16* __restrict__ Xb, __nv_bfloat16* __restrict__ Xlo,
-                                 __nv_bfloat16* __restrict__ Xaug,
-                                 float* __restrict__ norms, int* __restrict__ nonint_flag, int* __restrict__ tnmax_bits)
+// one warp per (padded) row; lane handles 4 consecutive floats.  X, Xb, Xlo, Xaug, norms point at row 0 of the matrix
+// (segment) the row belongs to.
+__device__ __forceinline__ void prep_one_row(const float* __restrict__ X, int n_rows, int row, int is_train,
+                                             __nv_bfloat16* __restrict__ Xb, __nv_bfloat16* __restrict__ Xlo,
+                                             __nv_bfloat16* __restrict__ Xaug, float* __restrict__ norms,
+                                             int* __restrict__ nonint_flag, int* __restrict__ tnmax_bits)
 {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (warp >= n_pad) return;
-    const int row = warp;
     __nv_bfloat162* out = reinterpret_cast<__nv_bfloat162*>(Xb + (size_t)row * DIM) + lane * 2;
     __nv_bfloat16* aug = Xaug + (size_t)row * KAUG;
     __nv_bfloat162* outlo = Xlo ? reinterpret_cast<__nv_bfloat162*>(Xlo + (size_t)row * DIM) + lane * 2 : nullptr;
@@ -85,6 +83,46 @@ __global__ void prep_rows_kernel(const float* __restrict__ X, int n_rows, int n_
         aug[lane] = __float2bfloat16(a);
     }
     if (lane == 0 && norms) norms[row] = ss;
+}
+
+__global__ void prep_rows_kernel(const float* __restrict__ X, int n_rows, int n_pad, int is_train,
+                                 __nv_bfloat16* __restrict__ Xb, __nv_bfloat16* __restrict__ Xlo,
+                                 __nv_bfloat16* __restrict__ Xaug,
+                                 float* __restrict__ norms, int* __restrict__ nonint_flag, int* __restrict__ tnmax_bits)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= n_pad) return;
+    prep_one_row(X, n_rows, warp, is_train, Xb, Xlo, Xaug, norms, nonint_flag, tnmax_bits);
+}
+
+// All train segments of a scene batch in one launch: padded row r belongs to the segment whose padded range holds it
+// (binary search over the segment table; segments are padded to multiples of TILE_N rows).
+__global__ void prep_train_segments_kernel(const float* __restrict__ X, const PrepSeg* __restrict__ segs, int n_segs,
+                                           int64_t rows_pad_total, __nv_bfloat16* __restrict__ Xb,
+                                           __nv_bfloat16* __restrict__ Xlo, __nv_bfloat16* __restrict__ Xaug,
+                                           int* __restrict__ nonint_flag, int* __restrict__ tnmax_bits)
+{
+    const int64_t prow = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (prow >= rows_pad_total) return;
+    int lo = 0, hi = n_segs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (segs[mid].pad_row0 <= prow) lo = mid; else hi = mid - 1;
+    }
+    const PrepSeg g = segs[lo];
+    prep_one_row(X + g.f32_row0 * DIM, g.rows, (int)(prow - g.pad_row0), 1, Xb + g.pad_row0 * DIM,
+                 Xlo ? Xlo + g.pad_row0 * DIM : nullptr, Xaug + g.pad_row0 * KAUG, nullptr, nonint_flag, tnmax_bits);
+}
+
+void launch_prep_train_segments(const float* X, const PrepSeg* segs_dev, int n_segs, int64_t rows_pad_total,
+                                __nv_bfloat16* Xb, __nv_bfloat16* Xlo, __nv_bfloat16* Xaug, int* nonint_flag,
+                                int* tnmax_bits, cudaStream_t st)
+{
+    if (rows_pad_total <= 0 || n_segs <= 0) return;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((rows_pad_total * 32 + threads - 1) / threads);
+    prep_train_segments_kernel<<<blocks, threads, 0, st>>>(X, segs_dev, n_segs, rows_pad_total, Xb, Xlo, Xaug, nonint_flag,
+                                                           tnmax_bits);
 }
 
 void launch_prep_rows(const float* X, int n_rows, int n_pad, int is_train, __nv_bfloat16* Xb, __nv_bfloat16* Xlo,

@@ -171,6 +171,11 @@ void cvg_scenes_free(cvg_ctx* ctx, cvg_scenes* scenes);
 int  cvg_scenes_upload_async(cvg_ctx* ctx, const float* desc, const float* kpt_xy,
                              const int64_t* offsets, int n_scenes, cvg_scenes** out);
 int  cvg_scenes_wait(cvg_ctx* ctx, cvg_scenes* scenes);
+/* Same for uint8 descriptor rows [N,128] (cv::SIFT::create(..., descriptorType = CV_8U), or SIFT's CV_32F output —
+ * whose values are integers 0..255 — narrowed by the caller): a quarter of the host->device bytes of the fp32 form
+ * (SURVEY 8f-3); widened to fp32 on the device, results identical. */
+int  cvg_scenes_upload_u8_async(cvg_ctx* ctx, const uint8_t* desc, const float* kpt_xy,
+                                const int64_t* offsets, int n_scenes, cvg_scenes** out);
 int  cvg_detect_scenes(cvg_ctx* ctx, const cvg_models* models, const cvg_scenes* scenes,
                        const float* scales, const cvg_detect_params* p, cvg_pair_result* per_pair);
 

@@ -427,6 +427,9 @@ def test_async_upload_pipeline_equals_sync(ctx, feats, api):
     rb = ctx.detect_scenes(models, b).copy(); pb = ctx.last_match_path
     b.wait()
     a.free(); b.free()
+    u = ctx.upload_scenes_u8_async(d_int.astype(np.uint8), kp, off)      # uint8 rows: same results as their fp32 form
+    ru = ctx.detect_scenes(models, u).copy(); u.free()
+    assert np.array_equal(ru["status"], want[0]["status"]) and np.array_equal(ru["H"], want[0]["H"])
     assert pa == api.PATH_TENSOR and pb == api.PATH_TENSOR_RERANK
     for got, w in zip((ra, rb), want):
         assert np.array_equal(got["status"], w["status"]) and np.array_equal(got["n_inliers"], w["n_inliers"])
