@@ -46,6 +46,7 @@ SYMBOLS = {
     "cvg_scenes_wait": (C.c_int, [_P, _P]),
     "cvg_scenes_upload_u8_async": (C.c_int, [_P, _P, _P, _P, C.c_int, C.POINTER(_P)]),
     "cvg_detect_scenes": (C.c_int, [_P, _P, _P, _P, C.POINTER(DetectParams), _P]),
+    "cvg_detect_scenes_inliers": (C.c_int, [_P, _P, _P, _P, C.POINTER(DetectParams), _P, _P, _P]),
     "cvg_dev_match_top2": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int, C.c_int32, _P, _P]),
     "cvg_dev_merge_top2": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P]),
     "cvg_last_match_path": (C.c_int, [_P]),

@@ -269,6 +269,18 @@ class Context:
         self._check(self.lib.cvg_detect_scenes(self.handle, models.handle, scenes.handle, _ptr(sc), C.byref(p), _ptr(res)))
         return res[:S * V].reshape(S, V)
 
+    def detect_scenes_inliers(self, models, scenes, scales=None, params=None):
+        """detect_scenes + the inlier scene points of the accepted pairs -> ([S, V] results, xy [k,2], offsets [S*V+1])."""
+        p = params if params is not None else detect_params()
+        S, V = scenes.n_scenes, models.n_views
+        res = np.zeros(max(S * V, 1), PAIR_DTYPE)
+        sc = np.ascontiguousarray(scales, np.float32) if scales is not None else None
+        inl = np.zeros((max(S * models.n_rows, 1), 2), np.float32)
+        off = np.zeros(S * V + 1, np.int64)
+        self._check(self.lib.cvg_detect_scenes_inliers(self.handle, models.handle, scenes.handle, _ptr(sc), C.byref(p),
+                                                       _ptr(res), _ptr(inl), _ptr(off)))
+        return res[:S * V].reshape(S, V), inl[:off[-1]], off
+
     # ---- device-pointer building blocks (multi-GPU train-tile shards) ---------------------------
     def dev_match_top2(self, query_ptr, n_query, train_ptr, n_train, index_base, dist_ptr, idx_ptr, stream=None):
         self._check(self.lib.cvg_dev_match_top2(self.handle, stream, query_ptr, n_query, train_ptr, n_train,

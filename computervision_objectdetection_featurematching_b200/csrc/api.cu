@@ -1011,8 +1011,9 @@ void cvg_scenes_free(cvg_ctx* c, cvg_scenes* sc)
     delete sc;
 }
 
-int cvg_detect_scenes(cvg_ctx* c, const cvg_models* m, const cvg_scenes* scenes, const float* scales,
-                      const cvg_detect_params* p, cvg_pair_result* per_pair)
+int cvg_detect_scenes_inliers(cvg_ctx* c, const cvg_models* m, const cvg_scenes* scenes, const float* scales,
+                              const cvg_detect_params* p, cvg_pair_result* per_pair, float* inlier_scene_xy,
+                              int64_t* inlier_offsets)
 {
     if (!c || !m || !scenes || !per_pair) return set_err(CVG_ERR_INVALID, "cvg_detect_scenes: NULL argument");
     int rc = check_detect_params(p);
@@ -1031,7 +1032,30 @@ int cvg_detect_scenes(cvg_ctx* c, const cvg_models* m, const cvg_scenes* scenes,
         if (c->stage_fallback) CU_CHECK(cudaStreamSynchronize(c->stream));
         d_scales = c->scales.as<float>();
     }
-    return detect_common(c, m, sc, sc->ts, d_scales, p, per_pair, nullptr, nullptr, false);
+    const bool want_inl = inlier_scene_xy != nullptr && inlier_offsets != nullptr;
+    if (!want_inl) return detect_common(c, m, sc, sc->ts, d_scales, p, per_pair, nullptr, nullptr, false);
+    // the device pool has one slot range per (scene, view) at scene * n_rows + view offset; pack it pair after pair
+    const size_t rows = (size_t)S * std::max(m->n_rows, 1);
+    std::vector<float> pool(rows * 2); std::vector<int32_t> cnt((size_t)std::max(S * V, 1));
+    rc = detect_common(c, m, sc, sc->ts, d_scales, p, per_pair, pool.data(), cnt.data(), true);
+    if (rc) return rc;
+    int64_t o = 0;
+    for (int s = 0; s < S; s++)
+        for (int v = 0; v < V; v++) {
+            const size_t pair = (size_t)s * V + v;
+            inlier_offsets[pair] = o;
+            const size_t start = (size_t)s * m->n_rows + (size_t)m->view_offsets[v];
+            memcpy(inlier_scene_xy + 2 * (size_t)o, pool.data() + 2 * start, (size_t)cnt[pair] * 8);
+            o += cnt[pair];
+        }
+    inlier_offsets[(size_t)S * V] = o;
+    return CVG_OK;
+}
+
+int cvg_detect_scenes(cvg_ctx* c, const cvg_models* m, const cvg_scenes* scenes, const float* scales,
+                      const cvg_detect_params* p, cvg_pair_result* per_pair)
+{
+    return cvg_detect_scenes_inliers(c, m, scenes, scales, p, per_pair, nullptr, nullptr);
 }
 
 // ---- device-pointer building blocks -----------------------------------------------------------------

@@ -47,6 +47,9 @@ constexpr uint32_t OFF_BAR = OFF_SHARE + SHARE_BYTES;
 constexpr uint32_t TC_SMEM_SLACK = 512;                           // the dynamic window is 1024-aligned in practice; checked in the kernel
 constexpr uint32_t TC_SMEM_BYTES = OFF_BAR + 512 + TC_SMEM_SLACK;
 static_assert(TC_SMEM_BYTES <= 232448, "shared memory budget of one CTA (227 KB)");
+#ifndef TOP2_GROUPS_PER_TEST
+#define TOP2_GROUPS_PER_TEST 2
+#endif
 constexpr float ABSENT_BELOW = -5.0e8f;                           // padded train rows carry -2^30
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -136,6 +139,19 @@ constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T
 // of groups of 4 columns are compared with it first, so a group costs ~2 instructions per lane unless one of
 // the warp's 32 rows really has a candidate in it.  Strict > against the warp's own values keeps the earlier
 // (lower) train index on ties, as cv::batchDistance's insertion does.
+__device__ __forceinline__ void top2_insert4(const uint32_t* r4, int c, float& b1, int& i1, float& b2, int& i2, float& f)
+{
+    #pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const float v = __uint_as_float(r4[j]);
+        if (v > f) {
+            if (v > b1) { b2 = b1; i2 = i1; b1 = v; i1 = c + j; }
+            else        { b2 = v; i2 = c + j; }
+            f = fmaxf(f, b2);
+        }
+    }
+}
+
 __device__ __forceinline__ void top2_scan32(const uint32_t* r, int c0, float& b1, int& i1, float& b2, int& i2, float& f)
 {
     float g[8];
@@ -143,18 +159,16 @@ __device__ __forceinline__ void top2_scan32(const uint32_t* r, int c0, float& b1
     for (int k = 0; k < 8; k++)
         g[k] = fmaxf(fmaxf(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1])),
                      fmaxf(__uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3])));
+    // one branch per 8 columns on the fast path (branch resolution was 17 % of the epilogue's stalls with one per 4)
     #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        if (g[k] > f) {
+    for (int k = 0; k < 8; k += TOP2_GROUPS_PER_TEST) {
+        float gm = g[k];
+        #pragma unroll
+        for (int e = 1; e < TOP2_GROUPS_PER_TEST; e++) gm = fmaxf(gm, g[k + e]);
+        if (gm > f) {
             #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float v = __uint_as_float(r[4 * k + j]);
-                if (v > f) {
-                    if (v > b1) { b2 = b1; i2 = i1; b1 = v; i1 = c0 + 4 * k + j; }
-                    else        { b2 = v; i2 = c0 + 4 * k + j; }
-                    f = fmaxf(f, b2);
-                }
-            }
+            for (int e = 0; e < TOP2_GROUPS_PER_TEST; e++)
+                if (g[k + e] > f) top2_insert4(r + 4 * (k + e), c0 + 4 * (k + e), b1, i1, b2, i2, f);
         }
     }
 }

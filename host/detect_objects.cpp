@@ -125,33 +125,59 @@ std::vector<Rect> mergeBoxes(const std::vector<Rect>& boxes, float merge_distanc
     return merged;
 }
 
+// All scaled versions of one test image as one streaming batch (copy + conversion on the copy stream).
+cvg_scenes* uploadScales(cvg_ctx* ctx, const std::vector<ScaledScene>& scales)
+{
+    std::vector<int64_t> offsets(1, 0);
+    size_t total = 0;
+    for (const ScaledScene& s : scales) { total += (size_t)s.n; offsets.push_back((int64_t)total); }
+    // the upload is asynchronous: it reads these staging vectors until the batch is waited for, so they live in it
+    static thread_local std::vector<std::vector<float>> ring_desc(4), ring_kpt(4);
+    static thread_local int ring_pos = 0;
+    std::vector<float>& desc = ring_desc[(size_t)ring_pos]; std::vector<float>& kpt = ring_kpt[(size_t)ring_pos];
+    ring_pos = (ring_pos + 1) % 4;
+    desc.resize(std::max<size_t>(total, 1) * 128); kpt.resize(std::max<size_t>(total, 1) * 2);
+    size_t row = 0;
+    for (const ScaledScene& s : scales) {
+        std::copy(s.desc, s.desc + (size_t)s.n * 128, desc.begin() + row * 128);
+        std::copy(s.kpt_xy, s.kpt_xy + (size_t)s.n * 2, kpt.begin() + row * 2);
+        row += (size_t)s.n;
+    }
+    cvg_scenes* batch = nullptr;
+    if (cvg_scenes_upload_async(ctx, desc.data(), kpt.data(), offsets.data(), (int)scales.size(), &batch) != CVG_OK)
+        throw std::runtime_error(std::string("cvg_scenes_upload_async: ") + cvg_last_error());
+    return batch;
+}
+
 std::vector<std::pair<Rect, std::string>> detectObjects(cvg_ctx* ctx, const cvg_models* resident,
                                                         const std::vector<ObjectModel>& models,
                                                         const std::vector<ScaledScene>& scales,
                                                         const cvg_detect_params& params, const DetectConstants& k,
-                                                        std::vector<cvg_pair_result>* per_pair_out)
+                                                        std::vector<cvg_pair_result>* per_pair_out, cvg_scenes* prepared)
 {
     const int V = cvg_models_num_views(resident);
     const int N = cvg_models_num_rows(resident);
+    const int S = (int)scales.size();
     // The reference recomputes every scaled scene per model (:99-106 inside the model loop) and matches only that
-    // model's views; the pairs are independent, so one fused call per scale serves all models.
-    std::vector<std::vector<cvg_pair_result>> res(scales.size(), std::vector<cvg_pair_result>(V));
-    std::vector<std::vector<float>> inl(scales.size(), std::vector<float>(2 * (size_t)std::max(N, 1)));
-    std::vector<std::vector<int32_t>> off(scales.size(), std::vector<int32_t>(V + 1));
-    for (size_t s = 0; s < scales.size(); ++s) {
-        const ScaledScene& sc = scales[s];
-        if (cvg_detect_pairs(ctx, resident, sc.desc, sc.kpt_xy, sc.n, sc.scale, &params, res[s].data(),
-                             inl[s].data(), off[s].data()) != CVG_OK)
-            throw std::runtime_error(std::string("cvg_detect_pairs: ") + cvg_last_error());
-        if (per_pair_out) per_pair_out->insert(per_pair_out->end(), res[s].begin(), res[s].end());
-    }
+    // model's views; the pairs are independent, so ONE fused call covers all scales x all views of all models.
+    cvg_scenes* batch = prepared;
+    if (!batch) batch = uploadScales(ctx, scales);
+    std::vector<float> sc(S);
+    for (int s = 0; s < S; ++s) sc[(size_t)s] = scales[(size_t)s].scale;
+    std::vector<cvg_pair_result> res((size_t)S * V);
+    std::vector<float> inl(2 * (size_t)S * (size_t)std::max(N, 1));
+    std::vector<int64_t> off((size_t)S * V + 1);
+    const int rc = cvg_detect_scenes_inliers(ctx, resident, batch, sc.data(), &params, res.data(), inl.data(), off.data());
+    cvg_scenes_free(ctx, batch);
+    if (rc != CVG_OK) throw std::runtime_error(std::string("cvg_detect_scenes_inliers: ") + cvg_last_error());
+    if (per_pair_out) per_pair_out->insert(per_pair_out->end(), res.begin(), res.end());
     std::vector<std::pair<Rect, std::string>> detections;
     for (const ObjectModel& model : models) {
         std::vector<Point2f> scenePts;                                     // allUnfilteredScenePts
-        for (size_t s = 0; s < scales.size(); ++s)
+        for (int s = 0; s < S; ++s)
             for (int v = model.first_view; v < model.first_view + model.n_views; ++v)
-                for (int j = off[s][v]; j < off[s][v + 1]; ++j)
-                    scenePts.push_back(Point2f{ inl[s][2 * (size_t)j], inl[s][2 * (size_t)j + 1] });
+                for (int64_t j = off[(size_t)s * V + v]; j < off[(size_t)s * V + v + 1]; ++j)
+                    scenePts.push_back(Point2f{ inl[2 * (size_t)j], inl[2 * (size_t)j + 1] });
         if (scenePts.empty()) continue;
         const auto clusters = clusterPoints(scenePts, k.cluster_distance, k.min_points_per_cluster);
         if (clusters.empty()) continue;

@@ -36,14 +36,20 @@ struct DetectConstants {                                   // src/TestsDetector.
     float dynamic_margin = 1.0f;                           // DYNAMIC_MARGIN
 };
 
-// Per model: the hot path at every scale (view order inside scale order, as :100-108), then clustering, boxes,
-// merge and area filter.  Returns (box, model name) in the reference's order.
+// The hot path for every (scale, view) pair of the image in one fused call (view order inside scale order, as
+// :100-108), then per model clustering, boxes, merge and area filter.  Returns (box, model name) in the reference's order.
 std::vector<std::pair<Rect, std::string>> detectObjects(cvg_ctx* ctx, const cvg_models* resident,
                                                         const std::vector<ObjectModel>& models,
                                                         const std::vector<ScaledScene>& scales,
                                                         const cvg_detect_params& params,
                                                         const DetectConstants& k = DetectConstants(),
-                                                        std::vector<cvg_pair_result>* per_pair_out = nullptr);
+                                                        std::vector<cvg_pair_result>* per_pair_out = nullptr,
+                                                        cvg_scenes* prepared = nullptr);
+
+// Streaming upload of an image's scaled scenes (cvg_scenes_upload_async); hand the batch to detectObjects as
+// `prepared` so that the next image's upload overlaps this image's detection (the loop of src/Output.cpp:27-47).
+// At most 4 batches may be in flight per thread (the host staging ring).
+cvg_scenes* uploadScales(cvg_ctx* ctx, const std::vector<ScaledScene>& scales);
 
 // consumer stages, exposed for the tests
 std::vector<std::vector<Point2f>> clusterPoints(const std::vector<Point2f>& pts, float max_dist, int min_points);

@@ -43,13 +43,20 @@ int main(int argc, char** argv)
 
     const auto t0 = std::chrono::steady_clock::now();
     long n_pairs = 0, n_det = 0;
-    for (int s = 0; s < fc.n_scenes; ++s) {
+    auto scalesOf = [&](int s) {
         std::vector<ScaledScene> scales;
         for (int k = 0; k < fc.n_scales; ++k) {
             const int64_t a = fc.scene_offsets[(size_t)s * fc.n_scales + k], b = fc.scene_offsets[(size_t)s * fc.n_scales + k + 1];
             scales.push_back(ScaledScene{ fc.scene_desc.data() + a * 128, fc.scene_kpt.data() + a * 2, (int)(b - a), fc.scales[k] });
         }
-        const auto det = detectObjects(ctx, resident, models, scales, params);
+        return scales;
+    };
+    cvg_scenes* next = fc.n_scenes > 0 ? uploadScales(ctx, scalesOf(0)) : nullptr;
+    for (int s = 0; s < fc.n_scenes; ++s) {
+        const std::vector<ScaledScene> scales = scalesOf(s);
+        cvg_scenes* cur = next;
+        next = s + 1 < fc.n_scenes ? uploadScales(ctx, scalesOf(s + 1)) : nullptr;     // overlaps this image's detection
+        const auto det = detectObjects(ctx, resident, models, scales, params, DetectConstants(), nullptr, cur);
         n_pairs += (long)fc.n_views * fc.n_scales;
         n_det += (long)det.size();
         const std::string folder = out_dir + "/" + fc.model_names[fc.scene_folder[s]];

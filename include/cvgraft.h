@@ -162,6 +162,14 @@ int  cvg_detect_pairs(cvg_ctx* ctx, const cvg_models* models,
 int  cvg_scenes_upload(cvg_ctx* ctx, const float* desc, const float* kpt_xy,
                        const int64_t* offsets, int n_scenes, cvg_scenes** out);
 void cvg_scenes_free(cvg_ctx* ctx, cvg_scenes* scenes);
+/* cvg_detect_scenes plus the inlier scene points of every ACCEPTED pair (the consumer of the hot path,
+ * src/TestsDetector.cpp:87-94 -> :112-248): inlier_scene_xy receives them pair after pair (scene-major, then view),
+ * divided by the scene's scale when it is != 1.0f; inlier_offsets [S*V+1] delimits them.  Capacity of
+ * inlier_scene_xy: S x n_rows of the model set x 2 floats.  All five scaled versions of a test image form one
+ * batch, so one call covers the whole loop nest of detectObjects for that image (:38, :99-100, :58). */
+int  cvg_detect_scenes_inliers(cvg_ctx* ctx, const cvg_models* models, const cvg_scenes* scenes,
+                               const float* scales, const cvg_detect_params* p, cvg_pair_result* per_pair,
+                               float* inlier_scene_xy, int64_t* inlier_offsets);
 /* Streaming form for a caller that walks a list of test images (reference src/Output.cpp:27-47):
  * cvg_scenes_upload_async enqueues the copy and the operand conversion on the context's copy stream
  * and returns at once, so the upload of batch k+1 overlaps cvg_detect_scenes of batch k.  The host
