@@ -313,6 +313,44 @@ def run_cvgraft(args):
                   "h2d_bytes_per_step": int(batches[0][0].size + batches[0][1].nbytes + batches[0][2].nbytes),
                   "note": "uint8 descriptor rows in pinned host memory (cvg_scenes_upload_u8_async); not the headline"}
 
+    # ---- extra key: the reference's own dataset (BASELINE configs 1-2: 30 test images x 5 scales x 89 model views), when
+    # the feature cache travelled with the tree (data_cache/, built by __graft_entry__.build() from the reference's
+    # data with cv2 SIFT).  Per test image: one streaming upload of its 5 scaled scenes + one fused call, as the
+    # reference's processAllTestImages loop would issue them (src/Output.cpp:27-47).
+    real = None
+    cache = os.path.join(ROOT, "data_cache", "features_full.npz")
+    if rank == 0 and args.desc == "sift" and os.path.exists(cache):
+        try:
+            Z = np.load(cache)
+            md = Z["model_desc"].astype(np.float32); so = Z["scene_offsets"]; n_img = (len(so) - 1) // 5
+            sd = torch.from_numpy(Z["scene_desc"].astype(np.float32)).pin_memory(); sk = torch.from_numpy(Z["scene_kpt"].astype(np.float32)).pin_memory()
+            sdn, skn = sd.numpy(), sk.numpy()
+            rmodels = ctx.upload_models(md, Z["model_kpt"], Z["view_offsets"], Z["view_model"])
+            sc5 = Z["scales"].astype(np.float32)
+
+            def up(i):
+                a, b = so[5 * i], so[5 * i + 5]
+                return ctx.upload_scenes_async(sdn[a:b], skn[a:b], so[5 * i:5 * i + 6] - a)
+
+            def whole():
+                hist = np.zeros(5, np.int64); nxt = up(0)
+                for i in range(n_img):
+                    cur = nxt; nxt = up(i + 1) if i + 1 < n_img else None
+                    res, _, _ = ctx.detect_scenes_inliers(rmodels, cur, scales=sc5, params=params)
+                    cur.free()
+                    hist += np.bincount(res["status"].ravel(), minlength=5)[:5]
+                return hist
+            whole()
+            ms_real = timed(lambda k: whole(), 1)
+            hist = whole()
+            real = {"pairs": int(n_img * 5 * rmodels.n_views), "images": int(n_img), "seconds": ms_real * 1e-3,
+                    "pairs_per_s": n_img * 5 * rmodels.n_views / (ms_real * 1e-3),
+                    "gate_histogram[accept,<4 matches,H empty,<4 inliers,det]": [int(v) for v in hist],
+                    "note": "host buffers in, per-pair results + inlier points out, one call per test image"}
+            rmodels.free()
+        except Exception as e:                             # the cache is optional
+            real = {"unavailable": str(e)[:200]}
+
     if rank == 0:
         peaks = load_peaks()
         traffic = hyp_traffic = None                    # dram bytes per launch, from the committed ncu --set full captures
@@ -340,6 +378,7 @@ def run_cvgraft(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "e2e_u8": e2e_u8,
+                "real_dataset": real,
                 "gpu_launches": int(launches),
                 "clocks": clk,
                 # dominant kernel of the step by device time: the RANSAC hypothesis kernel (DLT solve + scoring).
