@@ -30,6 +30,8 @@ SYMBOLS = {
     "cvg_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_uint]),
     "cvg_destroy": (None, [_P]),
     "cvg_last_error": (C.c_char_p, []),
+    "cvg_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "cvg_host_free": (None, [_P]),
     "cvg_version": (C.c_char_p, []),
     "cvg_models_upload": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.POINTER(_P)]),
     "cvg_models_free": (None, [_P, _P]),

@@ -68,12 +68,11 @@ struct BufPool {
     void release(DevBuf& b)
     {
         if (!b.p) return;
-        if (free_list.size() >= 24) {               // bounded: drop the smallest cached buffer
-            int small = 0;
-            for (int i = 1; i < (int)free_list.size(); i++) if (free_list[i].cap < free_list[small].cap) small = i;
-            if (free_list[small].cap < b.cap) { free_list[small].release(); free_list[small] = b; }
-            else b.release();
-        } else free_list.push_back(b);
+        if (free_list.size() >= 64) {               // bounded: the buffer that has waited longest goes (sizes of a
+            free_list.front().release();            // streaming caller drift; keeping the smallest ones thrashed)
+            free_list.erase(free_list.begin());
+        }
+        free_list.push_back(b);
         b.p = nullptr; b.cap = 0;
     }
     void clear() { for (DevBuf& b : free_list) b.release(); free_list.clear(); }
@@ -243,6 +242,14 @@ void cvg_destroy(cvg_ctx* c)
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
 }
+
+void* cvg_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void cvg_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int cvg_last_match_path(const cvg_ctx* c) { return c ? c->last_match_path : 0; }
 int cvg_last_match_fallback_rows(const cvg_ctx* c)

@@ -102,14 +102,30 @@ __global__ void prep_train_segments_kernel(const float* __restrict__ X, const Pr
                                            __nv_bfloat16* __restrict__ Xlo, __nv_bfloat16* __restrict__ Xaug,
                                            int* __restrict__ nonint_flag, int* __restrict__ tnmax_bits)
 {
-    const int64_t prow = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (prow >= rows_pad_total) return;
-    int lo = 0, hi = n_segs - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (segs[mid].pad_row0 <= prow) lo = mid; else hi = mid - 1;
+    // the 8 rows of a CTA lie in one segment (segments are padded to multiples of 256 rows): one search per CTA,
+    // by warp 0 with the table probes spread over its lanes
+    __shared__ PrepSeg s_seg;
+    const int64_t prow0 = ((int64_t)blockIdx.x * blockDim.x) >> 5;
+    if (prow0 >= rows_pad_total) return;
+    if (threadIdx.x < 32) {
+        int lo = 0, hi = n_segs - 1;                             // last segment with pad_row0 <= prow0
+        while (hi - lo >= 32) {
+            const int step = (hi - lo + 32) / 32;
+            const int probe = min(lo + (int)threadIdx.x * step, hi);
+            const unsigned ok = __ballot_sync(0xffffffffu, segs[probe].pad_row0 <= prow0);
+            const int last = 31 - __clz(ok);                     // lane 0 probes lo, which always qualifies
+            const int nlo = min(lo + last * step, hi);
+            hi = min(nlo + step - 1, hi); lo = nlo;
+        }
+        const int probe = min(lo + (int)threadIdx.x, hi);
+        const unsigned ok = __ballot_sync(0xffffffffu, segs[probe].pad_row0 <= prow0);
+        const int idx = min(lo + (31 - __clz(ok)), hi);
+        if (threadIdx.x == 0) s_seg = segs[idx];
     }
-    const PrepSeg g = segs[lo];
+    __syncthreads();
+    const PrepSeg g = s_seg;
+    const int64_t prow = prow0 + (threadIdx.x >> 5);
+    if (prow >= rows_pad_total) return;
     prep_one_row(X + g.f32_row0 * DIM, g.rows, (int)(prow - g.pad_row0), 1, Xb + g.pad_row0 * DIM,
                  Xlo ? Xlo + g.pad_row0 * DIM : nullptr, Xaug + g.pad_row0 * KAUG, nullptr, nonint_flag, tnmax_bits);
 }

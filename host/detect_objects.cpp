@@ -131,20 +131,24 @@ cvg_scenes* uploadScales(cvg_ctx* ctx, const std::vector<ScaledScene>& scales)
     std::vector<int64_t> offsets(1, 0);
     size_t total = 0;
     for (const ScaledScene& s : scales) { total += (size_t)s.n; offsets.push_back((int64_t)total); }
-    // the upload is asynchronous: it reads these staging vectors until the batch is waited for, so they live in it
-    static thread_local std::vector<std::vector<float>> ring_desc(4), ring_kpt(4);
+    // the upload is asynchronous: it reads these page-locked staging buffers until the batch has been consumed, so they
+    // live in a ring (grow-only, per thread)
+    struct Pinned { float* p = nullptr; size_t cap = 0;
+                    float* get(size_t n) { if (n > cap) { cvg_host_free(p); cap = n + n / 4; p = (float*)cvg_host_alloc(cap * sizeof(float)); } return p; } };
+    static thread_local Pinned ring_desc[4], ring_kpt[4];
     static thread_local int ring_pos = 0;
-    std::vector<float>& desc = ring_desc[(size_t)ring_pos]; std::vector<float>& kpt = ring_kpt[(size_t)ring_pos];
+    float* desc = ring_desc[ring_pos].get(std::max<size_t>(total, 1) * 128);
+    float* kpt = ring_kpt[ring_pos].get(std::max<size_t>(total, 1) * 2);
+    if (!desc || !kpt) throw std::runtime_error("cvg_host_alloc failed");
     ring_pos = (ring_pos + 1) % 4;
-    desc.resize(std::max<size_t>(total, 1) * 128); kpt.resize(std::max<size_t>(total, 1) * 2);
     size_t row = 0;
     for (const ScaledScene& s : scales) {
-        std::copy(s.desc, s.desc + (size_t)s.n * 128, desc.begin() + row * 128);
-        std::copy(s.kpt_xy, s.kpt_xy + (size_t)s.n * 2, kpt.begin() + row * 2);
+        std::copy(s.desc, s.desc + (size_t)s.n * 128, desc + row * 128);
+        std::copy(s.kpt_xy, s.kpt_xy + (size_t)s.n * 2, kpt + row * 2);
         row += (size_t)s.n;
     }
     cvg_scenes* batch = nullptr;
-    if (cvg_scenes_upload_async(ctx, desc.data(), kpt.data(), offsets.data(), (int)scales.size(), &batch) != CVG_OK)
+    if (cvg_scenes_upload_async(ctx, desc, kpt, offsets.data(), (int)scales.size(), &batch) != CVG_OK)
         throw std::runtime_error(std::string("cvg_scenes_upload_async: ") + cvg_last_error());
     return batch;
 }

@@ -4,6 +4,7 @@
 // Usage: cvg_replay <features.bin> <output_dir> [--consumer-only]
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <sys/stat.h>
@@ -41,30 +42,37 @@ int main(int argc, char** argv)
     cvg_detect_params params;
     cvg_detect_params_default(&params);
 
-    const auto t0 = std::chrono::steady_clock::now();
-    long n_pairs = 0, n_det = 0;
-    auto scalesOf = [&](int s) {
-        std::vector<ScaledScene> scales;
-        for (int k = 0; k < fc.n_scales; ++k) {
-            const int64_t a = fc.scene_offsets[(size_t)s * fc.n_scales + k], b = fc.scene_offsets[(size_t)s * fc.n_scales + k + 1];
-            scales.push_back(ScaledScene{ fc.scene_desc.data() + a * 128, fc.scene_kpt.data() + a * 2, (int)(b - a), fc.scales[k] });
+    // Pass 1 includes one-time costs (lazy kernel loading, scratch and pool allocation, the RNG table); pass 2 is the
+    // steady state of a long-running detector.  Both write the same results files.
+    for (int pass = 1; pass <= 2; ++pass) {
+        const auto t0 = std::chrono::steady_clock::now();
+        long n_pairs = 0, n_det = 0;
+        auto scalesOf = [&](int s) {
+            std::vector<ScaledScene> scales;
+            for (int k = 0; k < fc.n_scales; ++k) {
+                const int64_t a = fc.scene_offsets[(size_t)s * fc.n_scales + k], b = fc.scene_offsets[(size_t)s * fc.n_scales + k + 1];
+                scales.push_back(ScaledScene{ fc.scene_desc.data() + a * 128, fc.scene_kpt.data() + a * 2, (int)(b - a), fc.scales[k] });
+            }
+            return scales;
+        };
+        cvg_scenes* next = fc.n_scenes > 0 ? uploadScales(ctx, scalesOf(0)) : nullptr;
+        for (int s = 0; s < fc.n_scenes; ++s) {
+            const std::vector<ScaledScene> scales = scalesOf(s);
+            cvg_scenes* cur = next;
+            next = s + 1 < fc.n_scenes ? uploadScales(ctx, scalesOf(s + 1)) : nullptr;     // overlaps this image's detection
+            const auto ti0 = std::chrono::steady_clock::now();
+            const auto det = detectObjects(ctx, resident, models, scales, params, DetectConstants(), nullptr, cur);
+            if (getenv("CVG_REPLAY_VERBOSE"))
+                printf("image %2d  %6.2f ms\n", s, 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - ti0).count());
+            n_pairs += (long)fc.n_views * fc.n_scales;
+            n_det += (long)det.size();
+            const std::string folder = out_dir + "/" + fc.model_names[fc.scene_folder[s]];
+            make_dir(folder);
+            saveDetections(folder + "/" + fc.scene_names[s] + "_results.txt", det);      // src/Output.cpp:46-47
         }
-        return scales;
-    };
-    cvg_scenes* next = fc.n_scenes > 0 ? uploadScales(ctx, scalesOf(0)) : nullptr;
-    for (int s = 0; s < fc.n_scenes; ++s) {
-        const std::vector<ScaledScene> scales = scalesOf(s);
-        cvg_scenes* cur = next;
-        next = s + 1 < fc.n_scenes ? uploadScales(ctx, scalesOf(s + 1)) : nullptr;     // overlaps this image's detection
-        const auto det = detectObjects(ctx, resident, models, scales, params, DetectConstants(), nullptr, cur);
-        n_pairs += (long)fc.n_views * fc.n_scales;
-        n_det += (long)det.size();
-        const std::string folder = out_dir + "/" + fc.model_names[fc.scene_folder[s]];
-        make_dir(folder);
-        saveDetections(folder + "/" + fc.scene_names[s] + "_results.txt", det);      // src/Output.cpp:46-47
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        printf("pass %d: scenes %d  pairs %ld  detections %ld  %.3f s  %.1f pairs/s\n", pass, fc.n_scenes, n_pairs, n_det, sec, n_pairs / sec);
     }
-    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    printf("scenes %d  pairs %ld  detections %ld  %.3f s  %.1f pairs/s\n", fc.n_scenes, n_pairs, n_det, sec, n_pairs / sec);
     cvg_models_free(ctx, resident);
     cvg_destroy(ctx);
     return 0;

@@ -23,6 +23,7 @@
 #ifndef CVGRAFT_H
 #define CVGRAFT_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -99,6 +100,10 @@ void cvg_detect_params_default(cvg_detect_params* p);
 int  cvg_create(cvg_ctx** out, int device, unsigned flags);
 void cvg_destroy(cvg_ctx* ctx);
 const char* cvg_last_error(void);   /* thread-local message of the last failing call                 */
+/* Page-locked host memory for callers without CUDA headers: buffers handed to the *_async uploads are copied
+ * by DMA while the GPU computes only if they are page-locked (pageable memory is staged, which serialises). */
+void* cvg_host_alloc(size_t bytes);
+void  cvg_host_free(void* p);
 const char* cvg_version(void);
 
 /* ---- model set: replaces nothing, hooks after src/ModelsDetector.cpp:78-80 -------------------

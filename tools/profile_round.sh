@@ -7,9 +7,9 @@ nvidia-smi --query-gpu=name,driver_version,clocks.max.sm,clocks.max.mem,memory.t
 lscpu | head -25 > $out/${tag}_cpu_info.txt
 python bench.py --steps 20 --warmup 3 > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
 python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_reference_n1.json 2> $out/${tag}_bench_reference_n1.err
-python bench.py --steps 3 --warmup 3 --no-cpu > $out/${tag}_plain.log 2>&1 &&
+python bench.py --steps 3 --warmup 3 --no-cpu --no-extras > $out/${tag}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $out/${tag}_launches_bench.csv \
-    python bench.py --steps 3 --warmup 3 --no-cpu > $out/${tag}_ncu_launches.log 2>&1
+    python bench.py --steps 3 --warmup 3 --no-cpu --no-extras > $out/${tag}_ncu_launches.log 2>&1
 python tools/gpu_prof_match.py 64 > $out/${tag}_plain_prof.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:match_tc -s 1 -c 1 -o $out/${tag}_prof_match \
     python tools/gpu_prof_match.py 64 > $out/${tag}_ncu_match.log 2>&1
