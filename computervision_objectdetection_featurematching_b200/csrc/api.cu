@@ -462,7 +462,9 @@ static int launch_match(cvg_ctx* c, const QuerySide& q, const TrainSet& ts, cons
     }
     if (c->timing) cudaEventRecord(c->ev[4], c->stream);
     if (want_int || want_simt || n_units == 0) {
-        launch_merge(d_parts, d_dir, ts.n_segs, n_rb, nq, ratio, d_idx, d_dist, d_accept, gate, 1, c->stream);
+        // without units (no train rows at all) nothing else writes the results: the merge runs ungated and emits -1
+        launch_merge(d_parts, d_dir, ts.n_segs, n_rb, nq, ratio, d_idx, d_dist, d_accept, n_units == 0 ? nullptr : gate, 1,
+                     c->stream);
         c->launches++;
     }
     if (want_cand && n_units > 0) {

@@ -139,6 +139,12 @@ def test_match_tiny_train_sets(ctx, gsynth):
             assert not acc.any()                            # m.size()==2 fails, src/TestsDetector.cpp:67
     idx, dist, acc = ctx.match_knn2(q, t[:0])
     assert (idx == -1).all() and not acc.any()
+    qf = q + np.float32(0.5)                                 # non-integer queries: candidate path, same contract
+    for nt in (0, 1, 2, 3):
+        idx, dist, acc = ctx.match_knn2(qf, t[:nt])
+        assert (idx[:, min(nt, 2):] == -1).all() and (idx[:, :min(nt, 2)] >= 0).all()
+        if nt < 2:
+            assert not acc.any()
 
 
 def test_match_resident_models_per_view_and_all(ctx, oracle, feats, gpairs):
