@@ -377,35 +377,47 @@ def run_cvgraft(args):
             md = Z["model_desc"].astype(np.float32); so = Z["scene_offsets"]; n_img = (len(so) - 1) // 5
             sd = torch.from_numpy(Z["scene_desc"].astype(np.float32)).pin_memory(); sk = torch.from_numpy(Z["scene_kpt"].astype(np.float32)).pin_memory()
             sdn, skn = sd.numpy(), sk.numpy()
-            rctx = api.Context(local)                      # its own context: its buffer pool holds this workload's sizes
-            rstream = torch.cuda.ExternalStream(rctx.stream, device=torch.device("cuda", local))
-            rmodels = rctx.upload_models(md, Z["model_kpt"], Z["view_offsets"], Z["view_model"])
+            # own contexts (their buffer pools hold this workload's sizes), C of them on C threads, image i on context
+            # i mod C — test images are independent (src/Output.cpp:27-47 carries no state from one to the next)
+            rctxs = [api.Context(local) for _ in range(C)]
+            rstreams = [torch.cuda.ExternalStream(c.stream, device=torch.device("cuda", local)) for c in rctxs]
+            rmodels = [c.upload_models(md, Z["model_kpt"], Z["view_offsets"], Z["view_model"]) for c in rctxs]
             sc5 = Z["scales"].astype(np.float32)
 
-            def up(i):
+            def up(c, i):
                 a, b = so[5 * i], so[5 * i + 5]
-                return rctx.upload_scenes_async(sdn[a:b], skn[a:b], so[5 * i:5 * i + 6] - a)
+                return c.upload_scenes_async(sdn[a:b], skn[a:b], so[5 * i:5 * i + 6] - a)
 
             def whole():
-                hist = np.zeros(5, np.int64); nxt = up(0)
-                for i in range(n_img):
-                    cur = nxt; nxt = up(i + 1) if i + 1 < n_img else None
-                    res, _, _ = rctx.detect_scenes_inliers(rmodels, cur, scales=sc5, params=params)
-                    cur.free()
-                    hist += np.bincount(res["status"].ravel(), minlength=5)[:5]
-                return hist
+                hists = [np.zeros(5, np.int64) for _ in range(C)]
+                ends = [torch.cuda.Event(enable_timing=True) for _ in range(C)]
+
+                def work(j):
+                    torch.cuda.set_device(local)
+                    mine = list(range(j, n_img, C))
+                    nxt = up(rctxs[j], mine[0]) if mine else None
+                    for t, i in enumerate(mine):
+                        cur = nxt; nxt = up(rctxs[j], mine[t + 1]) if t + 1 < len(mine) else None
+                        res, _, _ = rctxs[j].detect_scenes_inliers(rmodels[j], cur, scales=sc5, params=params)
+                        cur.free()
+                        hists[j] += np.bincount(res["status"].ravel(), minlength=5)[:5]
+                    ends[j].record(rstreams[j])
+                torch.cuda.synchronize()
+                r0 = torch.cuda.Event(enable_timing=True); r0.record(rstreams[0])
+                th = [threading.Thread(target=work, args=(j,)) for j in range(C)]
+                [t.start() for t in th]; [t.join() for t in th]
+                for e in ends:
+                    e.synchronize()
+                return sum(hists), max(r0.elapsed_time(e) for e in ends)
             whole()                                        # warm-up pass: allocations, lazy kernel loading
-            torch.cuda.synchronize()
-            r0 = torch.cuda.Event(enable_timing=True); r1 = torch.cuda.Event(enable_timing=True)
-            r0.record(rstream)
-            hist = whole()
-            r1.record(rstream); r1.synchronize()
-            ms_real = r0.elapsed_time(r1)
-            real = {"pairs": int(n_img * 5 * rmodels.n_views), "images": int(n_img), "seconds": ms_real * 1e-3,
-                    "pairs_per_s": n_img * 5 * rmodels.n_views / (ms_real * 1e-3),
+            hist, ms_real = whole()
+            n_views = rmodels[0].n_views
+            real = {"pairs": int(n_img * 5 * n_views), "images": int(n_img), "seconds": ms_real * 1e-3,
+                    "pairs_per_s": n_img * 5 * n_views / (ms_real * 1e-3), "contexts": C,
                     "gate_histogram[accept,<4 matches,H empty,<4 inliers,det]": [int(v) for v in hist],
                     "note": "host buffers in, per-pair results + inlier points out, one call per test image"}
-            rmodels.free(); rctx.close()
+            for m_, c_ in zip(rmodels, rctxs):
+                m_.free(); c_.close()
         except Exception as e:                             # the cache is optional
             real = {"unavailable": str(e)[:200]}
 
