@@ -86,50 +86,61 @@ def make_workload(seed, n_scenes, n_batches, desc="sift"):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md recipe).  Started at process start so that the tool is
+    already looping when the short timed regions run; samples are kept by timestamp for the windows marked."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu):
-        self.gpu = gpu; self.proc = None; self.path = None
+        self.gpu = gpu; self.proc = None; self.path = None; self.windows = []
 
     def start(self):
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv"); os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def mark(self, t0, t1):
+        self.windows.append((t0, t1))
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if not self.proc:
             return out
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, sm_all = [], [], set(), []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
-                if len(f) < 9:
+                if len(f) < 10:
                     continue
                 try:
-                    sm.append(float(f[1])); mx.append(float(f[2]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    v = float(f[2]); m = float(f[3])
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                sm_all.append(v); mx.append(m)
+                if any(a - 0.02 <= ts <= b + 0.02 for a, b in self.windows):
+                    sm.append(v)
+                    for name, r in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[6:10]):
+                        if r.lower().startswith("active"):
+                            reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
+        if not sm and sm_all:                                   # windows shorter than the sampling period: busy samples of the run
+            sm = [v for v in sm_all if v >= 0.5 * max(sm_all)]
         if sm:
-            busy = [v for v in sm if v >= 0.5 * max(sm)]
-            out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
         return out
 
 
@@ -205,6 +216,7 @@ def run_cvgraft(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B, R = args.pairs, args.batches
+    clocks = ClockSampler(local); clocks.start()
     q, qk, batches = make_workload(3000 + rank, B, R, args.desc)
     ctx = api.Context(local)
     ctx.set_timing(True)
@@ -295,13 +307,13 @@ def run_cvgraft(args):
         res = ctxs[i].detect_scenes(cmodels[i], cres[i][k % R], params=params)
         acc_multi[i] += int((res["status"] == 0).sum())
 
-    clocks = ClockSampler(local); clocks.start()       # samples from the warm-up on: the timed region is short
+    tw0 = time.time()                                  # clock samples: from the warm-up on (the timed region is short)
     run_multi(step_resident_multi, max(C, args.warmup))
     acc_multi = [0] * C
     l0 = sum(c.launch_count for c in ctxs)
     ms_total = run_multi(step_resident_multi, args.steps)
     launches = sum(c.launch_count for c in ctxs) - l0
-    clk = clocks.stop()
+    clocks.mark(tw0, time.time())
     value = world * B * args.steps / (ms_total * 1e-3)
     accepted_multi = sum(acc_multi)
     for rs in cres:
@@ -333,9 +345,12 @@ def run_cvgraft(args):
         c.detect_scenes(cmodels[i], sc, params=params)
         sc.free()
 
+    tw0 = time.time()
     run_multi(step_e2e, max(2 * C, args.warmup))
     ms_e2e = run_multi(step_e2e, args.steps)
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    clocks.mark(tw0, time.time())
+    clk = clocks.stop()
 
     # ---- same loop with uint8 descriptor rows in host memory (cv::SIFT can emit CV_8U): extra key only
     e2e_u8 = None
