@@ -8,11 +8,14 @@
 // parallel decomposition keeps its results bit for bit (App. D.5):
 //   1. sample kernel   — replays cv::RNG + getSubset + checkSubset.  The raw RNG stream for the fixed
 //                        per-call seed is a constant table in HBM, so the attempt starting at any draw
-//                        position p can be evaluated independently; a block evaluates a window of 512
-//                        positions in parallel, then one thread follows the chain p -> p + consumed(p).
-//   2. hypothesis kernel — one hypothesis per thread: 4-point normalised DLT (9x9 Jacobi in shared memory,
-//                        fp64, no FMA), then fp32 scoring of all correspondences staged through shared
-//                        memory (each point is read once per 64 hypotheses, broadcast to the warp).
+//                        position p can be evaluated independently; a block evaluates a window of 2048
+//                        positions in parallel and recovers the chain p -> p + consumed(p) by pointer jumping.
+//   2. hypothesis kernel — 4-point normalised DLT (9x9 Jacobi, fp64, no FMA) + fp32 scoring of all
+//                        correspondences, in rounds sized to one full wave.  ransac_hyp_t_kernel (default): one
+//                        hypothesis per thread, matrix state element-major in shared memory (jacobi_thread.cuh),
+//                        scoring from correspondences staged in the same shared memory.  Bit-identical variants
+//                        for few hypotheses / A-B runs: one warp per hypothesis (jacobi_warp.cuh), four per warp,
+//                        and the generic serial routine (CVG_HYP_MODE = 1, 2, 3).
 //   3. select kernel   — the sequential "good > max(best,3)" / RANSACUpdateNumIters scan, one warp per
 //                        set, so the winner is the hypothesis the serial loop would have kept.
 //   4. finish kernel   — winner's inlier mask, DLT refit on the inliers, 9-parameter LM (10 iterations),
@@ -248,11 +251,11 @@ ransac_sample_kernel(RansacWork w, int round_base, int round_end)
     }
 }
 
-// ---- 2. hypothesis kernel: solve + score ------------------------------------------------------------
-// LtL and V (the Jacobi working set, 162 doubles, dynamically indexed) live in shared memory: as
-// thread-local arrays they thrash L1 and every access costs an L2 round trip.  The layout is
-// element-major (element e of thread t at e*HYP_THREADS + t): a thread always hits its own banks, so
-// the divergent indices of 32 different Jacobi sweeps never conflict.
+// ---- 2. hypothesis kernels: solve + score -----------------------------------------------------------
+// Generic variant (CVG_HYP_MODE=3, kept as the plain restatement the others are checked against): the serial
+// routine of homography_math.cuh per thread.  LtL and V (162 doubles, dynamically indexed) live in shared memory —
+// as thread-local arrays they thrash L1 — element-major (element e of thread t at e*HYP_THREADS + t), so the
+// divergent indices of 32 different Jacobi sweeps never conflict.
 constexpr int JAC_DOUBLES = 162;
 
 template <int S>
