@@ -33,7 +33,8 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    extra = os.environ.get("CVG_NVCC_EXTRA", "").split()            # experiments, e.g. -DHYPT_THREADS_DEF=96 -DHYPT_CTAS_DEF=2
+    cmd = [nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", SO] + [os.path.join(CSRC, f) for f in SOURCES]
     env = dict(os.environ)
     env.pop("CC", None); env.pop("CXX", None)

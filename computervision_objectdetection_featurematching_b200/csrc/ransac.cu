@@ -427,12 +427,17 @@ ransac_hyp_g8_kernel(RansacWork w, int round_base)
 // memory, one CTA per SM.  Hypotheses are numbered flat over (set, iteration) so CTAs stay full whatever the
 // round length; lanes of one warp almost always share a set, so the scoring loop's float4 loads are warp-uniform
 // (one L1 transaction, broadcast).  Bit-identical to the other hypothesis kernels.
-constexpr int HYPT_THREADS = 224;
+#ifndef HYPT_THREADS_DEF
+#define HYPT_THREADS_DEF 224
+#define HYPT_CTAS_DEF 1
+#endif
+constexpr int HYPT_THREADS = HYPT_THREADS_DEF;
+constexpr int HYPT_CTAS_PER_SM = HYPT_CTAS_DEF;
 constexpr int HYPT_SMEM = HYPT_THREADS * JT_DOUBLES * 8;
 
 struct WarpAny { __device__ __forceinline__ bool operator()(bool x) const { return __any_sync(0xffffffffu, x); } };
 
-__global__ void __launch_bounds__(HYPT_THREADS, 1)
+__global__ void __launch_bounds__(HYPT_THREADS, HYPT_CTAS_PER_SM)
 ransac_hyp_t_kernel(RansacWork w, int round_base, int round_len)
 {
     extern __shared__ double jt_smem[];
@@ -1019,7 +1024,7 @@ int launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events,
     if (!n_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev); if (n_sms <= 0) n_sms = 148; }
     int round_len = w.max_iters;
     if (!(w.flags & CVG_RANSAC_NO_EARLY_STOP)) {
-        const int64_t wave = (int64_t)n_sms * HYPT_THREADS;
+        const int64_t wave = (int64_t)n_sms * HYPT_THREADS * HYPT_CTAS_PER_SM;
         int64_t fill = wave / w.n_sets / 32 * 32;              // rounded down: n_sets x round_len must not spill into a second wave
         round_len = (int)std::min<int64_t>(std::max<int64_t>(256, fill), w.max_iters);
         if (round_env > 0) round_len = std::min(round_env, w.max_iters);
