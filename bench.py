@@ -144,6 +144,29 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(props):
+    """Run this rank's host threads (and first-touch its pinned buffers) on the NUMA node the GPU hangs off, when the
+    box exposes one: with 8 ranks streaming 50 GB/s each the host memory is the end-to-end limit."""
+    try:
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def cpu_pairs(q, qk, batch, n_pairs, threads, first=0):
     """The reference's CPU path on pairs [first, first + n_pairs) of a batch; returns (seconds, kind).
     All host threads are used: knnMatch is parallel inside OpenCV (parallel_for_ over query rows), findHomography
@@ -213,6 +236,8 @@ def run_cvgraft(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libcvgraft has no CPU fallback")
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(torch.cuda.get_device_properties(local))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B, R = args.pairs, args.batches
@@ -459,7 +484,7 @@ def run_cvgraft(args):
                                           "fp32, non-integer (candidate + fp32 re-rank match path)",
                            "match_path": ctx.last_match_path,
                            "scene_batches_rotated": R, "parallelism": f"pair-sharded x{world}, no data-path collective",
-                           "contexts_per_gpu": C,
+                           "contexts_per_gpu": C, "host_numa_node": numa,
                            "l2": f"{R} rotating batches, {R * B * NT * DIM * 2 / 2**20:.0f} MiB of bf16 operands > 126 MB L2"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
@@ -497,6 +522,7 @@ def run_cvgraft(args):
                 "stage_ms_per_step": {"match_kernel": kms, "verify": statistics.mean(ransac_ms), "verify_hyp_kernels": statistics.mean(hyp_ms)},
                 "accepted_pairs": accepted_multi}
         if world == 1 and not args.no_cpu:
+            os.sched_setaffinity(0, all_cpus)           # the CPU baseline gets every core of the box
             threads = os.cpu_count() or 1
             n = 0; t_cpu = 0.0; kind = "reference"
             chunk = max(2, min(threads, 32, B))
