@@ -1,0 +1,138 @@
+// cvgraft_opencv.hpp — the reference-side binding of libcvgraft (INTEGRATION.md as code).
+//
+// Included by the reference's src/ModelsDetector.cpp and src/TestsDetector.cpp (mattreturn1/
+// ComputerVision_ObjectDetection_FeatureMatching); uses only cv:: types the reference already uses and the C ABI of
+// include/cvgraft.h — no CUDA headers.  ObjectModel (include/objectModel.hpp:11-16), detectObjects
+// (include/TestsDetector.hpp:13-17) and processAllModelsImages (include/ModelsDetector.hpp:13-14) keep their
+// signatures.  Two forms:
+//   call for call  cvg::knnMatch(...)        <- matcher.knnMatch(model.descriptors[i], sceneDesc, knnMatches, 2)   :59-60
+//                  cvg::findHomography(...)  <- findHomography(objPts, scenePts, RANSAC, 5.0, inlierMask)          :77-78
+//   fused          cvg::detectAtScale(...)   <- the body of the view loop of detectAtScale                         :58-95
+// OpenCV C++ is not installed in the build container of this repository: tests/test_shim.py compiles this header
+// against a minimal stand-in for the few cv:: types it touches (tests/shim/opencv_stub) and runs it on the GPU.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <opencv2/opencv.hpp>
+
+#include "cvgraft.h"
+#include "objectModel.hpp"
+
+namespace cvg {
+
+// Resident copy of every model view (hook: end of processAllModelsImages, after src/ModelsDetector.cpp:84).
+struct ModelSet {
+    cvg_ctx* ctx = nullptr;
+    cvg_models* models = nullptr;
+    std::vector<int32_t> view_offsets;            // [V+1] rows of the concatenated descriptor matrix
+    std::vector<int> first_view_of_model;         // [M] index of a model's first view in the resident set
+    ~ModelSet() { if (models) cvg_models_free(ctx, models); if (ctx) cvg_destroy(ctx); }
+    ModelSet() = default;
+    ModelSet(const ModelSet&) = delete;
+    ModelSet& operator=(const ModelSet&) = delete;
+};
+
+inline void check(int rc, const char* what)
+{
+    if (rc != CVG_OK) throw std::runtime_error(std::string(what) + ": " + cvg_last_error());
+}
+
+inline void uploadModels(const std::vector<ObjectModel>& models, ModelSet& set, int device = 0)
+{
+    check(cvg_create(&set.ctx, device, 0), "cvg_create");
+    std::vector<float> desc, kpt;
+    std::vector<int32_t> view_model;
+    set.view_offsets.assign(1, 0);
+    for (size_t m = 0; m < models.size(); ++m) {
+        set.first_view_of_model.push_back((int)view_model.size());
+        for (size_t i = 0; i < models[m].descriptors.size(); ++i) {
+            const cv::Mat& d = models[m].descriptors[i];                      // Nq x 128, CV_32F (cv::SIFT)
+            for (int r = 0; r < d.rows; ++r) desc.insert(desc.end(), d.ptr<float>(r), d.ptr<float>(r) + d.cols);
+            for (const cv::KeyPoint& k : models[m].keypoints[i]) { kpt.push_back(k.pt.x); kpt.push_back(k.pt.y); }
+            set.view_offsets.push_back(set.view_offsets.back() + d.rows);
+            view_model.push_back((int32_t)m);
+        }
+    }
+    check(cvg_models_upload(set.ctx, desc.data(), kpt.data(), set.view_offsets.data(), view_model.data(),
+                            (int)view_model.size(), &set.models), "cvg_models_upload");
+}
+
+inline std::vector<float> continuousRows(const cv::Mat& m)
+{
+    std::vector<float> out;
+    out.reserve((size_t)m.rows * (size_t)m.cols);
+    for (int r = 0; r < m.rows; ++r) out.insert(out.end(), m.ptr<float>(r), m.ptr<float>(r) + m.cols);
+    return out;
+}
+
+// matcher.knnMatch(model.descriptors[i], sceneDesc, knnMatches, 2) for view i of model m        :59-60
+inline void knnMatch(const ModelSet& set, int m, size_t i, const cv::Mat& sceneDesc,
+                     std::vector<std::vector<cv::DMatch>>& knnMatches)
+{
+    const int view = set.first_view_of_model[(size_t)m] + (int)i;
+    const int nq = set.view_offsets[(size_t)view + 1] - set.view_offsets[(size_t)view];
+    std::vector<int32_t> idx(2 * (size_t)nq);
+    std::vector<float> dist(2 * (size_t)nq);
+    const std::vector<float> train = continuousRows(sceneDesc);
+    check(cvg_match_knn2(set.ctx, set.models, view, train.data(), sceneDesc.rows, 0.9f, idx.data(), dist.data(), nullptr),
+          "cvg_match_knn2");
+    knnMatches.assign((size_t)nq, {});
+    for (int q = 0; q < nq; ++q)
+        for (int k = 0; k < 2; ++k)
+            if (idx[2 * (size_t)q + k] >= 0)                                   // shorter lists where OpenCV returns them
+                knnMatches[(size_t)q].push_back(cv::DMatch(q, idx[2 * (size_t)q + k], 0, dist[2 * (size_t)q + k]));
+}
+
+// Mat H = findHomography(objPts, scenePts, RANSAC, ransacThreshold, inlierMask)                  :77-78
+inline cv::Mat findHomography(const ModelSet& set, const std::vector<cv::Point2f>& objPts,
+                              const std::vector<cv::Point2f>& scenePts, double ransacThreshold, cv::Mat& inlierMask)
+{
+    cvg_ransac_params rp;
+    cvg_ransac_params_default(&rp);
+    rp.threshold = ransacThreshold;
+    double Hd[9];
+    int found = 0;
+    std::vector<uint8_t> mask(objPts.size());
+    static_assert(sizeof(cv::Point2f) == 2 * sizeof(float), "cv::Point2f is two packed floats");
+    const int rc = cvg_find_homography(set.ctx, reinterpret_cast<const float*>(objPts.data()),
+                                       reinterpret_cast<const float*>(scenePts.data()), (int)objPts.size(), &rp, Hd,
+                                       mask.data(), &found, nullptr);
+    if (rc == CVG_ERR_TOO_FEW_POINTS) throw std::invalid_argument(cvg_last_error());   // OpenCV throws cv::Exception here
+    check(rc, "cvg_find_homography");
+    inlierMask.create((int)mask.size(), 1, CV_8U);
+    for (size_t j = 0; j < mask.size(); ++j) inlierMask.at<uchar>((int)j) = mask[j];
+    cv::Mat H;
+    if (found) {
+        H.create(3, 3, CV_64F);
+        for (int j = 0; j < 9; ++j) H.at<double>(j / 3, j % 3) = Hd[j];
+    }
+    return H;
+}
+
+// Fused replacement of the view loop (:58-95) for model m at one scale: appends the inlier scene points of every
+// accepted view, divided by `scale` when it is != 1.0f, to allUnfilteredScenePts — exactly what the loop appends.
+inline void detectAtScale(const ModelSet& set, int m, size_t n_views_of_model, const std::vector<cv::KeyPoint>& sceneKP,
+                          const cv::Mat& sceneDesc, float scale, std::vector<cv::Point2f>& allUnfilteredScenePts)
+{
+    std::vector<float> skpt;
+    skpt.reserve(sceneKP.size() * 2);
+    for (const cv::KeyPoint& k : sceneKP) { skpt.push_back(k.pt.x); skpt.push_back(k.pt.y); }
+    const std::vector<float> train = continuousRows(sceneDesc);
+    cvg_detect_params p;
+    cvg_detect_params_default(&p);                     // 0.9f, MIN_INLIERS 4, RANSAC 5.0, det in [0.1f, 10.0f]   :21-25
+    const int V = cvg_models_num_views(set.models);
+    std::vector<cvg_pair_result> per_view((size_t)V);
+    std::vector<float> inl(2 * (size_t)cvg_models_num_rows(set.models));
+    std::vector<int32_t> off((size_t)V + 1);
+    check(cvg_detect_pairs(set.ctx, set.models, train.data(), skpt.data(), sceneDesc.rows, scale, &p, per_view.data(),
+                           inl.data(), off.data()), "cvg_detect_pairs");
+    const int first = set.first_view_of_model[(size_t)m];
+    for (int v = first; v < first + (int)n_views_of_model; ++v)
+        for (int j = off[(size_t)v]; j < off[(size_t)v + 1]; ++j)
+            allUnfilteredScenePts.emplace_back(inl[2 * (size_t)j], inl[2 * (size_t)j + 1]);
+}
+
+}  // namespace cvg
