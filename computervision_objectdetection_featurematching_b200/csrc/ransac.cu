@@ -544,6 +544,41 @@ __global__ void ransac_select_kernel(RansacWork w, int round_base, int round_len
     }
 }
 
+// Without the adaptive stop (CVG_RANSAC_NO_EARLY_STOP) niters never changes, so the serial scan reduces to "first
+// iteration with the largest count, if it beats the running best and 3": a block-wide argmax, one CTA per set.
+constexpr int SELP_THREADS = 256;
+__global__ void __launch_bounds__(SELP_THREADS)
+ransac_select_all_kernel(RansacWork w, int round_base, int round_len)
+{
+    const int set = blockIdx.x;
+    const int n = w.counts_n[set];
+    const int n_samples = w.n_samples[set];
+    const int32_t* __restrict__ counts = w.counts + (size_t)set * w.max_iters;
+    const int end = min(min(round_base + round_len, n_samples), w.niters_cur[set]);
+    // key = (count, first index wins): larger count first, then smaller index
+    long long best = -1;
+    for (int it = round_base + (int)threadIdx.x; it < end; it += SELP_THREADS) {
+        const long long key = ((long long)counts[it] << 32) | (unsigned int)(0x7fffffff - it);
+        best = key > best ? key : best;
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const long long ob = __shfl_xor_sync(0xffffffffu, best, o); best = ob > best ? ob : best; }
+    __shared__ long long s_best[SELP_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < SELP_THREADS / 32; k++) best = s_best[k] > best ? s_best[k] : best;
+        int bc = w.best_count[set], bi = w.best_iter[set];
+        if (best >= 0) {
+            const int c = (int)(best >> 32), it = 0x7fffffff - (int)(unsigned int)best;
+            if (c > max(bc, 3)) { bc = c; bi = it; }
+        }
+        w.best_count[set] = bc; w.best_iter[set] = bi;
+        const int niters = w.niters_cur[set];
+        w.iters_run[set] = n <= 4 ? 0 : min(max(niters, bi + 1), n_samples);
+    }
+}
+
 // ---- block reductions (parallel mode of the finish kernel) ----------------------------------------
 __device__ __forceinline__ double shfl_down_d(double v, int o)
 {
@@ -1056,7 +1091,10 @@ int launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events,
             ransac_hyp_t_kernel<<<(unsigned)blocks, HYPT_THREADS, HYPT_SMEM, st>>>(w, rb, len);
         }
         if (timed) { cudaEventRecord(hyp_events[2 * round + 1], st); *n_hyp_rounds = round + 1; }
-        ransac_select_kernel<<<(w.n_sets + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(w, rb, len);
+        if (w.flags & CVG_RANSAC_NO_EARLY_STOP)
+            ransac_select_all_kernel<<<w.n_sets, SELP_THREADS, 0, st>>>(w, rb, len);
+        else
+            ransac_select_kernel<<<(w.n_sets + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(w, rb, len);
         launches += 3;
     }
     ransac_finish_kernel<<<w.n_sets, RS_THREADS, 0, st>>>(w);

@@ -279,6 +279,14 @@ def test_find_homography_no_early_stop_scores_every_hypothesis(ctx, api, oracle)
                                          want_ransac_mask=True)
     tr = oracle.ransac_stage(src, dst, max_iters=2000, want_trace=True)
     assert mask.sum() >= tr["mask"].sum()                    # more hypotheses can only improve the best count
+    # at 5 % inliers the adaptive niters of the reference stays above 30 000, so its loop IS the exhaustive one:
+    # the parallel argmax selection must pick the same hypothesis as the serial scan
+    for seed in (1, 2, 3):
+        s2, d2, _ = synth.correspondences(np.random.default_rng(5100 + seed), 600, 0.05)
+        ref = oracle.ransac_stage(s2, d2, max_iters=30000)
+        assert ref["info"]["iters_run"] == 30000
+        H2, m2 = ctx.find_homography(s2, d2, max_iters=30000, flags=api.RANSAC_NO_EARLY_STOP | api.RANSAC_NO_REFINE)
+        assert np.array_equal(m2, ref["mask"]) and np.array_equal(H2, ref["H"])
 
 
 def test_find_homography_batch_shapes_thread_kernel(ctx, api, oracle):
