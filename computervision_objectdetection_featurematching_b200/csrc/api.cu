@@ -129,6 +129,7 @@ struct cvg_ctx {
     DevBuf t_f32, t_b, t_blo, t_aug, t_kpt, t_kptoff, t_segtab;  // per-call train path
     DevBuf units, dir, parts, idx, dist, accept;
     DevBuf parts4, segdev, fb;                         // candidate path: Top4 records, segment table, unproven rows
+    DevBuf chunk;                                      // chunked sampler scratch (huge no-early-stop rounds)
     DevBuf plan_units, plan_dir;                       // match plan of the fused path, cached by (model set, scene shapes)
     const cvg_models* plan_models = nullptr; std::vector<int> plan_shape; int plan_units_n = 0;
     DevBuf pts, starts, counts_n, sample_pos, n_samples, counts, best_iter, best_count, iters_run, niters_cur, smp_state, sel;
@@ -226,7 +227,7 @@ void cvg_destroy(cvg_ctx* c)
     cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     DevBuf* bufs[] = { &c->q_f32, &c->q_b, &c->q_blo, &c->q_aug, &c->q_norm, &c->t_f32, &c->t_b, &c->t_blo, &c->t_aug, &c->t_segtab, &c->t_kpt, &c->t_kptoff,
-                       &c->units, &c->dir, &c->parts, &c->parts4, &c->segdev, &c->fb, &c->plan_units, &c->plan_dir, &c->idx, &c->dist, &c->accept, &c->pts, &c->starts, &c->counts_n,
+                       &c->units, &c->dir, &c->parts, &c->parts4, &c->segdev, &c->fb, &c->plan_units, &c->plan_dir, &c->chunk, &c->idx, &c->dist, &c->accept, &c->pts, &c->starts, &c->counts_n,
                        &c->sample_pos, &c->n_samples, &c->counts, &c->best_iter, &c->best_count, &c->iters_run, &c->niters_cur, &c->smp_state, &c->sel,
                        &c->H, &c->mask, &c->rmask, &c->found, &c->sflags, &c->results, &c->inl_xy, &c->inl_cnt,
                        &c->scales, &c->src, &c->dst };
@@ -524,6 +525,20 @@ static int run_ransac(cvg_ctx* c, const float4* d_pts, const int64_t* d_starts, 
     w.sel = c->sel.as<int32_t>(); w.H = c->H.as<double>(); w.mask = c->mask.as<uint8_t>();
     w.ransac_mask = want_rmask ? c->rmask.as<uint8_t>() : nullptr;
     w.found = c->found.as<int32_t>(); w.status_flags = c->sflags.as<int32_t>();
+    w.chunk_outs = nullptr; w.chunk_lists = nullptr; w.chunk_offsets = nullptr; w.chunk_serial = nullptr; w.n_chunks = 0;
+    if ((p->flags & CVG_RANSAC_NO_EARLY_STOP) && mi >= 32768) {
+        // one huge round: the draw stream of every set is walked by many CTAs at once (ransac_sample_chunk_kernel)
+        const int n_chunks = ransac_chunks_for_table(c->rng_len);
+        size_t o_outs, o_lists, o_off, o_ser;
+        const int64_t bytes = ransac_chunk_scratch_bytes(n_sets, n_chunks, &o_outs, &o_lists, &o_off, &o_ser);
+        if (n_chunks > 1 && bytes < (8LL << 30)) {
+            CU_CHECK(c->chunk.ensure((size_t)bytes));
+            uint8_t* b = c->chunk.as<uint8_t>();
+            w.chunk_outs = b + o_outs; w.chunk_lists = reinterpret_cast<int32_t*>(b + o_lists);
+            w.chunk_offsets = reinterpret_cast<int32_t*>(b + o_off); w.chunk_serial = reinterpret_cast<int*>(b + o_ser);
+            w.n_chunks = n_chunks;
+        }
+    }
     w.err_flag = c->d_flags + 4;
     CU_CHECK(cudaMemsetAsync(c->d_flags + 4, 0, 4, c->stream));
     w.scored_pts = c->timing ? c->d_scored : nullptr;

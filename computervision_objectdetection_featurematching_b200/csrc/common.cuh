@@ -126,7 +126,11 @@ struct RansacWork {
     int32_t* found;             // [P]
     int32_t* status_flags;      // [P] bit0: rng table exhausted
     int* err_flag;              // one word, OR of all status_flags (or NULL)
+    // chunked sampler scratch (huge single rounds; NULL / 0 = not available)
+    void* chunk_outs; int32_t* chunk_lists; int32_t* chunk_offsets; int* chunk_serial; int n_chunks;
 };
+int64_t ransac_chunk_scratch_bytes(int n_sets, int n_chunks, size_t* outs, size_t* lists, size_t* offsets, size_t* serial);
+int ransac_chunks_for_table(int64_t rng_len);
 // returns the number of kernel launches; hyp_events (optional, 32 events) bracket the hypothesis kernel of each round
 int  launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events = nullptr, int* n_hyp_rounds = nullptr);
 

@@ -83,9 +83,10 @@ constexpr int SW_PER_THREAD = SW / SMP_THREADS;
 // running failure count persist in smp_state between rounds, and a set whose adaptive niters already
 // ended before round_base is skipped.
 __global__ void __launch_bounds__(SMP_THREADS)
-ransac_sample_kernel(RansacWork w, int round_base, int round_end)
+ransac_sample_kernel(RansacWork w, int round_base, int round_end, const int* __restrict__ only_if_flag)
 {
     const int set = blockIdx.x;
+    if (only_if_flag && only_if_flag[set] == 0) return;          // chunked sampler handled this set
     const int n = w.counts_n[set];
     int32_t* out = w.sample_pos + (size_t)set * w.max_iters;
     if (round_base == 0) {
@@ -249,6 +250,266 @@ ransac_sample_kernel(RansacWork w, int round_base, int round_end)
         w.smp_state[2 * set] = base;
         w.smp_state[2 * set + 1] = finished ? -1 : attempts;
     }
+}
+
+
+// ---- 1b. chunked sampler: one set's draw stream cut into chunks that many CTAs walk at once ----------------
+// The serial chain p -> p + consumed(p) forgets where it came from within a few attempts: chains started at ANY of the
+// first 64 positions of a window meet long before its end.  So the CTA of chunk c > 0 evaluates the window in front of
+// its chunk with all 64 starts marked; if every marked chain leaves that window at the same position (checked, not
+// assumed) that position is taken as the chunk's entry — no information from chunk c-1 is needed.  Each CTA then walks
+// its chunk window by window like the serial kernel and leaves its accepted positions in a list.  A stitch kernel (one
+// thread per set, a few thousand steps) walks the chunk summaries in order and ACCEPTS a chunk only if
+// exit(c-1) == entry(c): the entry is then a position of the true chain, and everything the chunk computed from it is
+// what the serial walk computes (induction from chunk 0, which starts at the true position).  It also applies the
+// 10000-consecutive-failures rule and the end of the round; a scatter kernel numbers the samples.  Anything unusual
+// (chains that did not meet, a mismatch, a failure run that could reach 10000, ...) hands the set to the serial kernel.
+constexpr int CH_WINDOWS = 8;
+constexpr int CH_DRAWS = CH_WINDOWS * SW;             // 16 384 draw positions per chunk
+constexpr int CH_LIST = CH_DRAWS / 4 + 8;             // accepted attempts per chunk (an attempt consumes >= 4 draws)
+constexpr int CH_STARTS = 64;
+constexpr int64_t CHUNKED_MIN_ITERS = 32768;       // rounds shorter than this stay on the one-CTA-per-set kernel
+
+struct ChunkOut { int64_t entry, exit; int32_t n_ok, n_nodes, head, tail; int32_t flags, pad; };   // flags: 1 table short, 2 unsafe
+
+__global__ void __launch_bounds__(SMP_THREADS)
+ransac_sample_chunk_kernel(RansacWork w, int round_base, int n_chunks, ChunkOut* __restrict__ outs, int32_t* __restrict__ lists)
+{
+    const int set = blockIdx.y, chunk = blockIdx.x;
+    const int n = w.counts_n[set];
+    ChunkOut* out = outs + (size_t)set * n_chunks + chunk;
+    int32_t* list = lists + ((size_t)set * n_chunks + chunk) * CH_LIST;
+    if (n <= 4 || (round_base > 0 && (w.smp_state[2 * set + 1] < 0 || w.n_samples[set] < round_base))) {
+        if (threadIdx.x == 0) { out->entry = out->exit = 0; out->n_ok = out->n_nodes = out->head = out->tail = 0; out->flags = 4; }
+        return;                                                   // flags 4: nothing to do for this set
+    }
+    const float4* __restrict__ pts = w.pts + w.starts[set];
+    __shared__ float4 spts[SMEM_PTS];
+    __shared__ uint16_t info[SW];
+    __shared__ int32_t s_draw[SW + SW_TAIL];
+    __shared__ uint16_t jump[2][SW];
+    __shared__ uint8_t reach[SW];
+    __shared__ int s_wsum[SMP_THREADS / 32][2];
+    __shared__ int s_last, s_first_ok, s_last_ok, s_bad, s_xmin, s_xmax;
+    const bool staged = n <= SMEM_PTS;
+    if (staged)
+        for (int i = threadIdx.x; i < n; i += SMP_THREADS) spts[i] = pts[i];
+    const int64_t B0 = round_base == 0 ? 0 : w.smp_state[2 * set];
+    const int64_t c_begin = B0 + (int64_t)chunk * CH_DRAWS, c_end = c_begin + CH_DRAWS;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const TabGet slow{ w.rng_tab, w.rng_len, (uint32_t)n };
+    int flags = 0;
+    int64_t base = c_begin;                                       // first window; chunk 0 enters exactly at B0
+    int sw_eff = SW;
+    bool warm = chunk > 0;
+    if (warm) base = c_begin - SW;
+    if (c_end + SW + SW_TAIL + 64 >= w.rng_len) flags |= 1;       // the table must cover the chunk and its look-ahead
+    int n_ok_total = 0, n_nodes_total = 0, head = 0, run = 0;
+    bool seen_ok = false;
+    int64_t entry = c_begin, exit_pos = c_begin;
+    while (!flags) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < SW + SW_TAIL; j += SMP_THREADS) {
+            const int64_t pp = base + j;
+            s_draw[j] = pp < w.rng_len ? (int32_t)(w.rng_tab[pp] % (uint32_t)n) : -1;
+        }
+        if (threadIdx.x == 0) { s_last = 0; s_first_ok = SW; s_last_ok = -1; s_bad = 0; s_xmin = 1 << 30; s_xmax = -1; }
+        __syncthreads();
+        auto get = [&](int64_t pos) -> int {
+            const int64_t j = pos - base;
+            return (j >= 0 && j < SW + SW_TAIL) ? s_draw[j] : slow(pos);
+        };
+        #pragma unroll 1
+        for (int k = 0; k < SW_PER_THREAD; k++) {
+            const int o = k * SMP_THREADS + threadIdx.x;
+            uint16_t e = 0;
+            if (o < sw_eff) {
+                int idx[4];
+                const int cons = draw_subset_g(get, base + o, idx);
+                if (cons > 0 && cons < 0x7fff) {
+                    float ms1[8], ms2[8];
+                    #pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const float4 q = staged ? spts[idx[i]] : pts[idx[i]];
+                        ms1[2 * i] = q.x; ms1[2 * i + 1] = q.y; ms2[2 * i] = q.z; ms2[2 * i + 1] = q.w;
+                    }
+                    e = (uint16_t)(cons | (check_subset4(ms1, ms2) ? 0x8000 : 0));
+                }
+            }
+            info[o] = e;
+            const int c = e & 0x7fff;
+            jump[0][o] = (uint16_t)((o >= sw_eff || c == 0 || o + c >= sw_eff) ? SW : o + c);
+            reach[o] = warm ? (o < CH_STARTS ? 1 : 0) : (o == 0 ? 1 : 0);
+        }
+        __syncthreads();
+        int cur = 0;
+        #pragma unroll 1
+        for (int r = 0; r < SW_ROUNDS; r++) {
+            #pragma unroll
+            for (int k = 0; k < SW_PER_THREAD; k++) {
+                const int o = k * SMP_THREADS + threadIdx.x;
+                const int j = jump[cur][o];
+                if (reach[o] && j < SW) reach[j] = 1;
+                jump[cur ^ 1][o] = (uint16_t)(j < SW ? jump[cur][j] : SW);
+            }
+            __syncthreads();
+            cur ^= 1;
+        }
+        if (warm) {
+            // where do the marked chains leave the window?  (a chain node leaves when o + consumed >= SW)
+            #pragma unroll
+            for (int k = 0; k < SW_PER_THREAD; k++) {
+                const int o = threadIdx.x * SW_PER_THREAD + k;
+                if (reach[o]) {
+                    const int c = info[o] & 0x7fff;
+                    if (c == 0) atomicExch(&s_bad, 1);
+                    else if (o + c >= SW) { atomicMin(&s_xmin, o + c - SW); atomicMax(&s_xmax, o + c - SW); }
+                }
+            }
+            __syncthreads();
+            if (s_bad == 1) { flags |= 1; break; }
+            if (s_xmin != s_xmax || s_xmax < 0) { flags |= 2; break; }     // the marked chains did not meet: serial kernel
+            entry = c_begin + s_xmin;
+            base = entry; warm = false;
+            sw_eff = (int)min((int64_t)SW, c_end - base);
+            continue;
+        }
+        // rank the chain nodes (blocked layout, so ranks follow stream order)
+        int n_reach = 0, n_ok = 0, mask_r = 0, mask_ok = 0;
+        #pragma unroll
+        for (int k = 0; k < SW_PER_THREAD; k++) {
+            const int o = threadIdx.x * SW_PER_THREAD + k;
+            if (reach[o]) {
+                const uint16_t e = info[o];
+                mask_r |= 1 << k; n_reach++;
+                if ((e & 0x7fff) == 0) atomicExch(&s_bad, 1);
+                if (e & 0x8000) { mask_ok |= 1 << k; n_ok++; atomicMin(&s_first_ok, o); atomicMax(&s_last_ok, o); }
+                atomicMax(&s_last, o);
+            }
+        }
+        int pre_r = n_reach, pre_ok = n_ok;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int a = __shfl_up_sync(0xffffffffu, pre_r, d), b2 = __shfl_up_sync(0xffffffffu, pre_ok, d);
+            if (lane >= d) { pre_r += a; pre_ok += b2; }
+        }
+        if (lane == 31) { s_wsum[wid][0] = pre_r; s_wsum[wid][1] = pre_ok; }
+        __syncthreads();
+        int off_ok = 0, tot_r = 0, tot_ok = 0;
+        #pragma unroll
+        for (int q = 0; q < SMP_THREADS / 32; q++) {
+            if (q < wid) off_ok += s_wsum[q][1];
+            tot_r += s_wsum[q][0]; tot_ok += s_wsum[q][1];
+        }
+        const int excl_ok = off_ok + pre_ok - n_ok;
+        const int first_ok = s_first_ok, last_ok = s_last_ok, last = s_last;
+        if (s_bad) { flags |= 1; break; }
+        int fails_head = 0, fails_tail = 0;
+        {
+            int h = 0, t = 0;
+            #pragma unroll
+            for (int k = 0; k < SW_PER_THREAD; k++) {
+                const int o = threadIdx.x * SW_PER_THREAD + k;
+                if ((mask_r >> k) & 1) { h += o < first_ok; t += o > last_ok; }
+            }
+            #pragma unroll
+            for (int d = 16; d > 0; d >>= 1) { h += __shfl_xor_sync(0xffffffffu, h, d); t += __shfl_xor_sync(0xffffffffu, t, d); }
+            __syncthreads();
+            if (lane == 0) { s_wsum[wid][0] = h; s_wsum[wid][1] = t; }
+            __syncthreads();
+            #pragma unroll
+            for (int q = 0; q < SMP_THREADS / 32; q++) { fails_head += s_wsum[q][0]; fails_tail += s_wsum[q][1]; }
+        }
+        // failure runs: `run` = consecutive failed chain nodes since the chunk's last accept (or since its entry).  A window
+        // holds at most SW / 4 = 512 nodes, so a run of 10000 always spans windows and shows up in these sums.
+        if (tot_ok > 0) {
+            const int gap = run + fails_head;
+            if (!seen_ok) head = gap;
+            else if (gap >= 10000) { flags |= 2; break; }         // getSubset would have given up inside the chunk
+            seen_ok = true; run = fails_tail;
+        } else run += tot_r;
+        if (seen_ok && run >= 10000) { flags |= 2; break; }
+        {
+            int r = n_ok_total + excl_ok;
+            #pragma unroll
+            for (int k = 0; k < SW_PER_THREAD; k++)
+                if ((mask_ok >> k) & 1) { if (r < CH_LIST) list[r] = (int32_t)(base + threadIdx.x * SW_PER_THREAD + k); r++; }
+        }
+        n_ok_total += tot_ok; n_nodes_total += tot_r;
+        base = base + last + (info[last] & 0x7fff);
+        if (base >= c_end) { exit_pos = base; break; }
+        sw_eff = (int)min((int64_t)SW, c_end - base);
+        if (base + SW + SW_TAIL + 64 >= w.rng_len) { flags |= 1; break; }
+    }
+    if (threadIdx.x == 0) {
+        out->entry = entry; out->exit = exit_pos; out->n_ok = n_ok_total; out->n_nodes = n_nodes_total;
+        out->head = seen_ok ? head : run; out->tail = run; out->flags = flags | (n_ok_total > CH_LIST ? 2 : 0);
+    }
+}
+
+// one thread per set walks the chunk summaries in order
+__global__ void ransac_sample_stitch_kernel(RansacWork w, int round_base, int round_end, int n_chunks,
+                                            const ChunkOut* __restrict__ outs, const int32_t* __restrict__ lists,
+                                            int32_t* __restrict__ offsets, int* __restrict__ serial_flag)
+{
+    const int set = blockIdx.x * blockDim.x + threadIdx.x;
+    if (set >= w.n_sets) return;
+    const ChunkOut* o = outs + (size_t)set * n_chunks;
+    int32_t* off = offsets + (size_t)set * n_chunks;
+    serial_flag[set] = 0;
+    for (int c = 0; c < n_chunks; c++) off[c] = -1;
+    const int n = w.counts_n[set];
+    if (round_base == 0) {
+        w.niters_cur[set] = max(w.max_iters, 1); w.best_iter[set] = -1; w.best_count[set] = 0;
+        w.n_samples[set] = 0; w.status_flags[set] = 0;
+        w.smp_state[2 * set] = 0; w.smp_state[2 * set + 1] = 0;
+    }
+    if (o[0].flags & 4) return;
+    int64_t expect = round_base == 0 ? 0 : w.smp_state[2 * set];
+    int attempts = round_base == 0 ? 0 : (int)w.smp_state[2 * set + 1];
+    int iter = round_base, flags = 0;
+    bool finished = false, done = false, unsafe = false;
+    for (int c = 0; c < n_chunks && !done; c++) {
+        if (o[c].flags & 2) { unsafe = true; break; }
+        if (o[c].flags & 1) { flags |= 1; finished = true; break; }
+        if (o[c].entry != expect) { unsafe = true; break; }
+        off[c] = iter;
+        if (o[c].n_ok == 0) {
+            attempts += o[c].n_nodes;
+            if (attempts >= 10000) { unsafe = true; break; }      // exact give-up point: let the serial kernel find it
+        } else {
+            if (attempts + o[c].head >= 10000) { unsafe = true; break; }
+            attempts = o[c].tail;
+        }
+        if (iter + o[c].n_ok >= round_end) {
+            const int need = round_end - iter;                    // >= 1
+            const int64_t p = lists[((size_t)set * n_chunks + c) * CH_LIST + need - 1];
+            int idx[4];
+            const int cons = draw_subset(w.rng_tab, w.rng_len, p, (uint32_t)n, idx);
+            expect = p + cons; attempts = 0; iter = round_end; done = true;
+        } else {
+            iter += o[c].n_ok; expect = o[c].exit;
+        }
+    }
+    if (unsafe) { serial_flag[set] = 1; for (int c = 0; c < n_chunks; c++) off[c] = -1; return; }
+    if (!done && !finished) { flags |= 1; finished = true; }     // the chunks (= the draw table) ended before the round did
+    w.n_samples[set] = iter;
+    if (flags) { w.status_flags[set] = flags; if (w.err_flag) atomicOr(w.err_flag, flags); }
+    w.smp_state[2 * set] = expect;
+    w.smp_state[2 * set + 1] = finished ? -1 : attempts;
+}
+
+__global__ void ransac_sample_scatter_kernel(RansacWork w, int round_end, int n_chunks, const ChunkOut* __restrict__ outs,
+                                             const int32_t* __restrict__ lists, const int32_t* __restrict__ offsets)
+{
+    const int set = blockIdx.y, chunk = blockIdx.x;
+    const int o = offsets[(size_t)set * n_chunks + chunk];
+    if (o < 0) return;
+    const int cnt = outs[(size_t)set * n_chunks + chunk].n_ok;
+    const int32_t* list = lists + ((size_t)set * n_chunks + chunk) * CH_LIST;
+    int32_t* dst = w.sample_pos + (size_t)set * w.max_iters;
+    for (int r = threadIdx.x; r < cnt; r += blockDim.x)
+        if (o + r < round_end) dst[o + r] = list[r];
 }
 
 // ---- 2. hypothesis kernels: solve + score -----------------------------------------------------------
@@ -1036,6 +1297,22 @@ ransac_finish_kernel(RansacWork w)
     if (tid == 0) w.found[set] = 1;
 }
 
+// layout of the chunked sampler's scratch inside one allocation; returns the total size
+int64_t ransac_chunk_scratch_bytes(int n_sets, int n_chunks, size_t* outs, size_t* lists, size_t* offsets, size_t* serial)
+{
+    size_t o = 0;
+    *outs = o;    o += (size_t)n_sets * n_chunks * sizeof(ChunkOut);
+    *lists = o;   o += (size_t)n_sets * n_chunks * CH_LIST * sizeof(int32_t);
+    *offsets = o; o += (size_t)n_sets * n_chunks * sizeof(int32_t);
+    *serial = o;  o += (size_t)n_sets * sizeof(int) + 64;
+    return (int64_t)o;
+}
+int ransac_chunks_for_table(int64_t rng_len)
+{
+    const int64_t c = (rng_len - 2 * SW - SW_TAIL - 128) / CH_DRAWS;
+    return c < 0 ? 0 : (c > 1000000 ? 1000000 : (int)c);
+}
+
 int launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events, int* n_hyp_rounds)
 {
     if (n_hyp_rounds) *n_hyp_rounds = 0;
@@ -1068,7 +1345,18 @@ int launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events,
     int round = 0;
     for (int rb = 0; rb < w.max_iters; rb += round_len, round++) {
         const int len = w.max_iters - rb < round_len ? w.max_iters - rb : round_len;
-        ransac_sample_kernel<<<w.n_sets, SMP_THREADS, 0, st>>>(w, rb, rb + len);
+        if (rb == 0 && w.chunk_outs && w.n_chunks > 1 && (int64_t)len >= CHUNKED_MIN_ITERS) {
+            // a huge single round (the no-early-stop throughput mode): cut every set's draw stream into chunks
+            ChunkOut* outs = static_cast<ChunkOut*>(w.chunk_outs);
+            ransac_sample_chunk_kernel<<<dim3((unsigned)w.n_chunks, (unsigned)w.n_sets), SMP_THREADS, 0, st>>>(w, rb, w.n_chunks, outs, w.chunk_lists);
+            ransac_sample_stitch_kernel<<<(w.n_sets + 63) / 64, 64, 0, st>>>(w, rb, rb + len, w.n_chunks, outs, w.chunk_lists,
+                                                                            w.chunk_offsets, w.chunk_serial);
+            ransac_sample_scatter_kernel<<<dim3((unsigned)w.n_chunks, (unsigned)w.n_sets), 256, 0, st>>>(w, rb + len, w.n_chunks, outs,
+                                                                                                     w.chunk_lists, w.chunk_offsets);
+            ransac_sample_kernel<<<w.n_sets, SMP_THREADS, 0, st>>>(w, rb, rb + len, w.chunk_serial);   // sets the stitch rejected
+            launches += 3;
+        } else
+            ransac_sample_kernel<<<w.n_sets, SMP_THREADS, 0, st>>>(w, rb, rb + len, nullptr);
         const bool timed = hyp_events != nullptr && round < 16;
         if (timed) cudaEventRecord(hyp_events[2 * round], st);
         // Measured on B200 (round 1).  13 350 real pairs (3.4 M hypotheses per round), whole verify stage: generic

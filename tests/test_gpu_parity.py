@@ -324,6 +324,43 @@ def test_find_homography_batch_shapes_thread_kernel(ctx, api, oracle):
                 assert np.allclose(out["H"][k], ref["H"], rtol=1e-9, atol=1e-12), (case["max_iters"], k, n)
 
 
+def test_chunked_sampler_huge_single_round(ctx, api, oracle):
+    """max_iters >= 32768 without early stop: the draw stream is walked by many CTAs at once (chunks whose entry is
+    found by letting 64 marked chains meet, accepted only if exit(c-1) == entry(c)).  The result must be the serial
+    loop's: at 4-5 % inliers the reference's adaptive niters never drops below max_iters, so its loop is exhaustive."""
+    rng = np.random.default_rng(6100)
+    srcs, dsts, offs, refs = [], [], [0], []
+    for n, rho in ((600, 0.05), (300, 0.04), (4, 1.0), (2000, 0.03), (7, 0.6)):
+        s, d, _ = synth.correspondences(rng, n, rho)
+        srcs.append(s); dsts.append(d); offs.append(offs[-1] + n)
+    iters = 70000
+    out = ctx.find_homography_batch(np.concatenate(srcs), np.concatenate(dsts), offs, max_iters=iters,
+                                    flags=api.RANSAC_NO_EARLY_STOP | api.RANSAC_NO_REFINE)
+    for k, (s, d) in enumerate(zip(srcs, dsts)):
+        a, b = offs[k], offs[k + 1]
+        if len(s) == 4:
+            assert out["found"][k] and out["mask"][a:b].all()
+            continue
+        ref = oracle.ransac_stage(s, d, max_iters=iters)
+        if ref["info"]["iters_run"] != iters:
+            continue                                             # the reference stopped early on this set: not comparable
+        assert out["found"][k] == ref["found"], k
+        assert np.array_equal(out["mask"][a:b], ref["mask"]), k
+        assert np.array_equal(out["H"][k], ref["H"]), k
+        refs.append(k)
+    assert len(refs) >= 3
+    # a high-rejection set (most attempts fail checkSubset): long failure runs, the draw table is regrown
+    n = 200
+    src, dst, _ = synth.correspondences(rng, n, 0.5)
+    line = rng.random(n) < 0.85
+    t = rng.uniform(0, 600, size=int(line.sum())).astype(np.float32)
+    src[line] = np.c_[t, 0.5 * t + 20]
+    ref = oracle.ransac_stage(src, dst, max_iters=40000, conf=0.9999999)
+    assert ref["info"]["iters_run"] == 40000
+    H, mask = ctx.find_homography(src, dst, max_iters=40000, flags=api.RANSAC_NO_EARLY_STOP | api.RANSAC_NO_REFINE)
+    assert np.array_equal(mask, ref["mask"]) and np.array_equal(H, ref["H"])
+
+
 def test_rng_table_grows_on_high_rejection_rate(api, oracle):
     """85 % of the points on one line: ~95 % of the 4-point attempts fail checkSubset, so an iteration consumes ~80
     draws of the cv::RNG stream instead of ~5.  The draw table (48 per iteration) runs out, is regrown, and the verify
