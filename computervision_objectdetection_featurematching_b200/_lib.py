@@ -53,6 +53,7 @@ SYMBOLS = {
     "cvg_dev_merge_top2": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_float, _P, _P, _P]),
     "cvg_last_match_path": (C.c_int, [_P]),
     "cvg_last_match_fallback_rows": (C.c_int, [_P]),
+    "cvg_last_sampler_serial_sets": (C.c_int, [_P]),
     "cvg_stream": (C.c_void_p, [_P]),
     "cvg_launch_count": (C.c_int64, [_P]),
     "cvg_set_timing": (C.c_int, [_P, C.c_int]),

@@ -192,6 +192,11 @@ class Context:
         return int(self.lib.cvg_last_match_fallback_rows(self.handle))
 
     @property
+    def last_sampler_serial_sets(self):
+        """-1: the last verify call used the one-CTA-per-set sampler; else the sets the chunked sampler handed back."""
+        return int(self.lib.cvg_last_sampler_serial_sets(self.handle))
+
+    @property
     def stream(self):
         """cudaStream_t of the context as an int (all GPU work of this context is issued there)."""
         return int(self.lib.cvg_stream(self.handle) or 0)

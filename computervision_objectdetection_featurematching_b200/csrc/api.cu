@@ -116,7 +116,7 @@ struct cvg_ctx {
     cudaStream_t copy_stream = nullptr;                // uploads of cvg_scenes_upload_async (overlap with compute)
     int* d_flags = nullptr;            // [0] train row kinds, [1] query row kinds, [2] match path (0 tensor exact, 1 tensor
                                        // candidates + re-rank, 2 exact SIMT), [3] raw-query kinds, [4] RNG table short,
-                                       // [5] max ||t||^2 bits, [6] fallback row count, [8..16) kernel debug words
+                                       // [5] max ||t||^2 bits, [6] fallback row count, [8..16) kernel debug words, [17] sets the chunked sampler handed to the serial one
     uint32_t* d_rng = nullptr; int64_t rng_len = 0;
     int last_match_path = 0; int64_t launches = 0;
     int timing = 0; float t_match = 0, t_ransac = 0, t_total = 0;
@@ -131,6 +131,7 @@ struct cvg_ctx {
     DevBuf parts4, segdev, fb;                         // candidate path: Top4 records, segment table, unproven rows
     DevBuf chunk;                                      // chunked sampler scratch (huge no-early-stop rounds)
     DevBuf plan_units, plan_dir;                       // match plan of the fused path, cached by (model set, scene shapes)
+    bool last_chunked = false;                         // the last verify call used the chunked sampler (d_flags[17] = sets it handed back)
     const cvg_models* plan_models = nullptr; std::vector<int> plan_shape; int plan_units_n = 0;
     DevBuf pts, starts, counts_n, sample_pos, n_samples, counts, best_iter, best_count, iters_run, niters_cur, smp_state, sel;
     DevBuf H, mask, rmask, found, sflags, results, inl_xy, inl_cnt, scales, src, dst;
@@ -259,6 +260,14 @@ int cvg_last_match_fallback_rows(const cvg_ctx* c)
     int n = 0;
     cudaSetDevice(c->device);
     cudaMemcpy(&n, c->d_flags + 6, 4, cudaMemcpyDeviceToHost);
+    return n;
+}
+int cvg_last_sampler_serial_sets(const cvg_ctx* c)
+{
+    if (!c || !c->last_chunked) return -1;
+    int n = 0;
+    cudaSetDevice(c->device);
+    cudaMemcpy(&n, c->d_flags + 17, 4, cudaMemcpyDeviceToHost);
     return n;
 }
 void* cvg_stream(const cvg_ctx* c) { return c ? (void*)c->stream : nullptr; }
@@ -526,17 +535,22 @@ static int run_ransac(cvg_ctx* c, const float4* d_pts, const int64_t* d_starts, 
     w.ransac_mask = want_rmask ? c->rmask.as<uint8_t>() : nullptr;
     w.found = c->found.as<int32_t>(); w.status_flags = c->sflags.as<int32_t>();
     w.chunk_outs = nullptr; w.chunk_lists = nullptr; w.chunk_offsets = nullptr; w.chunk_serial = nullptr; w.n_chunks = 0;
+    w.chunk_maps = nullptr; w.chunk_entries = nullptr; w.chunk_serial_count = nullptr;
+    c->last_chunked = false;
     if ((p->flags & CVG_RANSAC_NO_EARLY_STOP) && mi >= 32768) {
         // one huge round: the draw stream of every set is walked by many CTAs at once (ransac_sample_chunk_kernel)
         const int n_chunks = ransac_chunks_for_table(c->rng_len);
-        size_t o_outs, o_lists, o_off, o_ser;
-        const int64_t bytes = ransac_chunk_scratch_bytes(n_sets, n_chunks, &o_outs, &o_lists, &o_off, &o_ser);
+        size_t o_outs, o_lists, o_off, o_ser, o_maps, o_ent;
+        const int64_t bytes = ransac_chunk_scratch_bytes(n_sets, n_chunks, &o_outs, &o_lists, &o_off, &o_ser, &o_maps, &o_ent);
         if (n_chunks > 1 && bytes < (8LL << 30)) {
             CU_CHECK(c->chunk.ensure((size_t)bytes));
             uint8_t* b = c->chunk.as<uint8_t>();
             w.chunk_outs = b + o_outs; w.chunk_lists = reinterpret_cast<int32_t*>(b + o_lists);
             w.chunk_offsets = reinterpret_cast<int32_t*>(b + o_off); w.chunk_serial = reinterpret_cast<int*>(b + o_ser);
-            w.n_chunks = n_chunks;
+            w.chunk_maps = b + o_maps; w.chunk_entries = reinterpret_cast<int32_t*>(b + o_ent);
+            w.n_chunks = n_chunks; w.chunk_serial_count = c->d_flags + 17;
+            CU_CHECK(cudaMemsetAsync(c->d_flags + 17, 0, 4, c->stream));
+            c->last_chunked = true;
         }
     }
     w.err_flag = c->d_flags + 4;

@@ -128,8 +128,10 @@ struct RansacWork {
     int* err_flag;              // one word, OR of all status_flags (or NULL)
     // chunked sampler scratch (huge single rounds; NULL / 0 = not available)
     void* chunk_outs; int32_t* chunk_lists; int32_t* chunk_offsets; int* chunk_serial; int n_chunks;
+    uint8_t* chunk_maps; int32_t* chunk_entries; int* chunk_serial_count;
 };
-int64_t ransac_chunk_scratch_bytes(int n_sets, int n_chunks, size_t* outs, size_t* lists, size_t* offsets, size_t* serial);
+int64_t ransac_chunk_scratch_bytes(int n_sets, int n_chunks, size_t* outs, size_t* lists, size_t* offsets, size_t* serial,
+                                   size_t* maps, size_t* entries);
 int ransac_chunks_for_table(int64_t rng_len);
 // returns the number of kernel launches; hyp_events (optional, 32 events) bracket the hypothesis kernel of each round
 int  launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events = nullptr, int* n_hyp_rounds = nullptr);

@@ -254,26 +254,123 @@ ransac_sample_kernel(RansacWork w, int round_base, int round_end, const int* __r
 
 
 // ---- 1b. chunked sampler: one set's draw stream cut into chunks that many CTAs walk at once ----------------
-// The serial chain p -> p + consumed(p) forgets where it came from within a few attempts: chains started at ANY of the
-// first 64 positions of a window meet long before its end.  So the CTA of chunk c > 0 evaluates the window in front of
-// its chunk with all 64 starts marked; if every marked chain leaves that window at the same position (checked, not
-// assumed) that position is taken as the chunk's entry — no information from chunk c-1 is needed.  Each CTA then walks
-// its chunk window by window like the serial kernel and leaves its accepted positions in a list.  A stitch kernel (one
-// thread per set, a few thousand steps) walks the chunk summaries in order and ACCEPTS a chunk only if
-// exit(c-1) == entry(c): the entry is then a position of the true chain, and everything the chunk computed from it is
-// what the serial walk computes (induction from chunk 0, which starts at the true position).  It also applies the
-// 10000-consecutive-failures rule and the end of the round; a scatter kernel numbers the samples.  Anything unusual
-// (chains that did not meet, a mismatch, a failure run that could reach 10000, ...) hands the set to the serial kernel.
+// The serial chain p -> p + consumed(p) enters chunk c (draw positions [c_begin, c_end)) at c_begin + e with a small
+// offset e (the last attempt of chunk c-1 overshoots c_begin by fewer draws than it consumed).  consumed(p) depends on
+// the draws alone — duplicates among the four indices — not on the correspondences, so:
+//   map kernel     — per chunk, the function e -> exit offset into chunk c+1 for EVERY e < CH_K, by pointer jumping over
+//                    the chunk's windows (no checkSubset, no point loads).  With large n nearly every attempt consumes
+//                    exactly four draws, so chains of different residues mod 4 do not meet for tens of thousands of
+//                    draws: waiting for convergence does not work, carrying all entries through does.
+//   entry kernel   — one CTA per set composes the maps in chunk order (entry(0) = 0): the true entry of every chunk.
+//   chunk kernel   — every CTA walks its chunk from its true entry window by window like the serial kernel and leaves
+//                    its accepted positions in a list.
+//   stitch kernel  — one thread per set walks the chunk summaries in order, re-checks exit(c-1) == entry(c), applies
+//                    the 10000-consecutive-failures rule and the end of the round; a scatter kernel numbers the samples.
+// Anything unusual (an exit offset >= CH_K, a failure run that could reach 10000, ...) hands the set to the serial kernel.
 constexpr int CH_WINDOWS = 8;
 constexpr int CH_DRAWS = CH_WINDOWS * SW;             // 16 384 draw positions per chunk
 constexpr int CH_LIST = CH_DRAWS / 4 + 8;             // accepted attempts per chunk (an attempt consumes >= 4 draws)
-constexpr int CH_STARTS = 64;
+constexpr int CH_K = 64;                              // entry offsets carried through a chunk
 constexpr int64_t CHUNKED_MIN_ITERS = 32768;       // rounds shorter than this stay on the one-CTA-per-set kernel
 
 struct ChunkOut { int64_t entry, exit; int32_t n_ok, n_nodes, head, tail; int32_t flags, pad; };   // flags: 1 table short, 2 unsafe
 
 __global__ void __launch_bounds__(SMP_THREADS)
-ransac_sample_chunk_kernel(RansacWork w, int round_base, int n_chunks, ChunkOut* __restrict__ outs, int32_t* __restrict__ lists)
+ransac_sample_map_kernel(RansacWork w, int round_base, int n_chunks, uint8_t* __restrict__ maps)
+{
+    const int set = blockIdx.y, chunk = blockIdx.x;
+    const int n = w.counts_n[set];
+    uint8_t* map = maps + ((size_t)set * n_chunks + chunk) * CH_K;
+    if (n <= 4) { if (threadIdx.x < CH_K) map[threadIdx.x] = 255; return; }
+    __shared__ int32_t s_draw[SW + SW_TAIL];
+    __shared__ uint16_t jump[2][SW];
+    __shared__ uint8_t cur_e[CH_K];
+    const int64_t B0 = round_base == 0 ? 0 : w.smp_state[2 * set];
+    const int64_t c_begin = B0 + (int64_t)chunk * CH_DRAWS;
+    const TabGet slow{ w.rng_tab, w.rng_len, (uint32_t)n };
+    if (threadIdx.x < CH_K) cur_e[threadIdx.x] = (uint8_t)threadIdx.x;
+    constexpr uint16_t BAD = 0xffff;
+    for (int k = 0; k < CH_WINDOWS; k++) {
+        const int64_t base = c_begin + (int64_t)k * SW;
+        __syncthreads();
+        for (int j = threadIdx.x; j < SW + SW_TAIL; j += SMP_THREADS) {
+            const int64_t pp = base + j;
+            s_draw[j] = pp < w.rng_len ? (int32_t)(w.rng_tab[pp] % (uint32_t)n) : -1;
+        }
+        __syncthreads();
+        auto get = [&](int64_t pos) -> int {
+            const int64_t j = pos - base;
+            return (j >= 0 && j < SW + SW_TAIL) ? s_draw[j] : slow(pos);
+        };
+        #pragma unroll 1
+        for (int q = 0; q < SW_PER_THREAD; q++) {
+            const int o = q * SMP_THREADS + threadIdx.x;
+            int idx[4];
+            const int c = draw_subset_g(get, base + o, idx);
+            // values >= SW are terminal: SW + (offset into the next window), or BAD (table overrun / absurd consumption)
+            jump[0][o] = (uint16_t)((c <= 0 || c >= 0x4000) ? BAD : o + c);
+        }
+        __syncthreads();
+        int cur = 0;
+        #pragma unroll 1
+        for (int r = 0; r < SW_ROUNDS; r++) {
+            #pragma unroll
+            for (int q = 0; q < SW_PER_THREAD; q++) {
+                const int o = q * SMP_THREADS + threadIdx.x;
+                const uint16_t j = jump[cur][o];
+                jump[cur ^ 1][o] = j < SW ? jump[cur][j] : j;
+            }
+            __syncthreads();
+            cur ^= 1;
+        }
+        if (threadIdx.x < CH_K) {
+            const uint8_t e = cur_e[threadIdx.x];
+            uint8_t out = 255;
+            if (e != 255) {
+                const uint16_t t = jump[cur][e];
+                if (t != BAD && t >= SW && t - SW < CH_K && t - SW < 255) out = (uint8_t)(t - SW);
+            }
+            cur_e[threadIdx.x] = out;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < CH_K) map[threadIdx.x] = cur_e[threadIdx.x];
+}
+
+// one CTA per set: entry(0) = 0, entry(c+1) = map_c[entry(c)]; -1 from the first chunk whose map has no answer
+constexpr int CH_ENTRY_BATCH = 64;
+__global__ void __launch_bounds__(256)
+ransac_sample_entry_kernel(int n_chunks, const uint8_t* __restrict__ maps, int32_t* __restrict__ entries)
+{
+    const int set = blockIdx.x;
+    __shared__ uint32_t s_maps[CH_ENTRY_BATCH * CH_K / 4];
+    __shared__ int32_t s_ent[CH_ENTRY_BATCH];
+    __shared__ int s_e;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(maps + (size_t)set * n_chunks * CH_K);
+    int32_t* ent = entries + (size_t)set * n_chunks;
+    if (threadIdx.x == 0) s_e = 0;
+    for (int c0 = 0; c0 < n_chunks; c0 += CH_ENTRY_BATCH) {
+        const int m = min(CH_ENTRY_BATCH, n_chunks - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < m * (CH_K / 4); i += blockDim.x) s_maps[i] = src[(size_t)c0 * (CH_K / 4) + i];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint8_t* mp = reinterpret_cast<const uint8_t*>(s_maps);
+            int e = s_e;
+            for (int c = 0; c < m; c++) {
+                s_ent[c] = e;
+                if (e >= 0) { const uint8_t x = mp[c * CH_K + e]; e = x == 255 ? -1 : (int)x; }
+            }
+            s_e = e;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < m; i += blockDim.x) ent[c0 + i] = s_ent[i];
+    }
+}
+
+__global__ void __launch_bounds__(SMP_THREADS)
+ransac_sample_chunk_kernel(RansacWork w, int round_base, int n_chunks, const int32_t* __restrict__ entries,
+                           ChunkOut* __restrict__ outs, int32_t* __restrict__ lists)
 {
     const int set = blockIdx.y, chunk = blockIdx.x;
     const int n = w.counts_n[set];
@@ -290,7 +387,7 @@ ransac_sample_chunk_kernel(RansacWork w, int round_base, int n_chunks, ChunkOut*
     __shared__ uint16_t jump[2][SW];
     __shared__ uint8_t reach[SW];
     __shared__ int s_wsum[SMP_THREADS / 32][2];
-    __shared__ int s_last, s_first_ok, s_last_ok, s_bad, s_xmin, s_xmax;
+    __shared__ int s_last, s_first_ok, s_last_ok, s_bad;
     const bool staged = n <= SMEM_PTS;
     if (staged)
         for (int i = threadIdx.x; i < n; i += SMP_THREADS) spts[i] = pts[i];
@@ -299,21 +396,22 @@ ransac_sample_chunk_kernel(RansacWork w, int round_base, int n_chunks, ChunkOut*
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const TabGet slow{ w.rng_tab, w.rng_len, (uint32_t)n };
     int flags = 0;
-    int64_t base = c_begin;                                       // first window; chunk 0 enters exactly at B0
-    int sw_eff = SW;
-    bool warm = chunk > 0;
-    if (warm) base = c_begin - SW;
+    const int entry_off = entries[(size_t)set * n_chunks + chunk];    // chunk 0 enters exactly at B0 (offset 0)
+    if (entry_off < 0) flags |= 2;                                // an earlier chunk's map had no answer: serial kernel
+    int64_t base = c_begin + max(entry_off, 0);
+    int sw_eff = (int)min((int64_t)SW, c_end - base);
     if (c_end + SW + SW_TAIL + 64 >= w.rng_len) flags |= 1;       // the table must cover the chunk and its look-ahead
     int n_ok_total = 0, n_nodes_total = 0, head = 0, run = 0;
     bool seen_ok = false;
-    int64_t entry = c_begin, exit_pos = c_begin;
+    const int64_t entry = base;
+    int64_t exit_pos = base;
     while (!flags) {
         __syncthreads();
         for (int j = threadIdx.x; j < SW + SW_TAIL; j += SMP_THREADS) {
             const int64_t pp = base + j;
             s_draw[j] = pp < w.rng_len ? (int32_t)(w.rng_tab[pp] % (uint32_t)n) : -1;
         }
-        if (threadIdx.x == 0) { s_last = 0; s_first_ok = SW; s_last_ok = -1; s_bad = 0; s_xmin = 1 << 30; s_xmax = -1; }
+        if (threadIdx.x == 0) { s_last = 0; s_first_ok = SW; s_last_ok = -1; s_bad = 0; }
         __syncthreads();
         auto get = [&](int64_t pos) -> int {
             const int64_t j = pos - base;
@@ -339,7 +437,7 @@ ransac_sample_chunk_kernel(RansacWork w, int round_base, int n_chunks, ChunkOut*
             info[o] = e;
             const int c = e & 0x7fff;
             jump[0][o] = (uint16_t)((o >= sw_eff || c == 0 || o + c >= sw_eff) ? SW : o + c);
-            reach[o] = warm ? (o < CH_STARTS ? 1 : 0) : (o == 0 ? 1 : 0);
+            reach[o] = o == 0 ? 1 : 0;
         }
         __syncthreads();
         int cur = 0;
@@ -354,25 +452,6 @@ ransac_sample_chunk_kernel(RansacWork w, int round_base, int n_chunks, ChunkOut*
             }
             __syncthreads();
             cur ^= 1;
-        }
-        if (warm) {
-            // where do the marked chains leave the window?  (a chain node leaves when o + consumed >= SW)
-            #pragma unroll
-            for (int k = 0; k < SW_PER_THREAD; k++) {
-                const int o = threadIdx.x * SW_PER_THREAD + k;
-                if (reach[o]) {
-                    const int c = info[o] & 0x7fff;
-                    if (c == 0) atomicExch(&s_bad, 1);
-                    else if (o + c >= SW) { atomicMin(&s_xmin, o + c - SW); atomicMax(&s_xmax, o + c - SW); }
-                }
-            }
-            __syncthreads();
-            if (s_bad == 1) { flags |= 1; break; }
-            if (s_xmin != s_xmax || s_xmax < 0) { flags |= 2; break; }     // the marked chains did not meet: serial kernel
-            entry = c_begin + s_xmin;
-            base = entry; warm = false;
-            sw_eff = (int)min((int64_t)SW, c_end - base);
-            continue;
         }
         // rank the chain nodes (blocked layout, so ranks follow stream order)
         int n_reach = 0, n_ok = 0, mask_r = 0, mask_ok = 0;
@@ -491,7 +570,11 @@ __global__ void ransac_sample_stitch_kernel(RansacWork w, int round_base, int ro
             iter += o[c].n_ok; expect = o[c].exit;
         }
     }
-    if (unsafe) { serial_flag[set] = 1; for (int c = 0; c < n_chunks; c++) off[c] = -1; return; }
+    if (unsafe) {
+        serial_flag[set] = 1; if (w.chunk_serial_count) atomicAdd(w.chunk_serial_count, 1);
+        for (int c = 0; c < n_chunks; c++) off[c] = -1;
+        return;
+    }
     if (!done && !finished) { flags |= 1; finished = true; }     // the chunks (= the draw table) ended before the round did
     w.n_samples[set] = iter;
     if (flags) { w.status_flags[set] = flags; if (w.err_flag) atomicOr(w.err_flag, flags); }
@@ -1298,13 +1381,16 @@ ransac_finish_kernel(RansacWork w)
 }
 
 // layout of the chunked sampler's scratch inside one allocation; returns the total size
-int64_t ransac_chunk_scratch_bytes(int n_sets, int n_chunks, size_t* outs, size_t* lists, size_t* offsets, size_t* serial)
+int64_t ransac_chunk_scratch_bytes(int n_sets, int n_chunks, size_t* outs, size_t* lists, size_t* offsets, size_t* serial,
+                                   size_t* maps, size_t* entries)
 {
     size_t o = 0;
     *outs = o;    o += (size_t)n_sets * n_chunks * sizeof(ChunkOut);
     *lists = o;   o += (size_t)n_sets * n_chunks * CH_LIST * sizeof(int32_t);
     *offsets = o; o += (size_t)n_sets * n_chunks * sizeof(int32_t);
-    *serial = o;  o += (size_t)n_sets * sizeof(int) + 64;
+    *entries = o; o += (size_t)n_sets * n_chunks * sizeof(int32_t);
+    *serial = o;  o += ((size_t)n_sets * sizeof(int) + 63) / 64 * 64;
+    *maps = o;    o += (size_t)n_sets * n_chunks * CH_K + 64;
     return (int64_t)o;
 }
 int ransac_chunks_for_table(int64_t rng_len)
@@ -1348,13 +1434,16 @@ int launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events,
         if (rb == 0 && w.chunk_outs && w.n_chunks > 1 && (int64_t)len >= CHUNKED_MIN_ITERS) {
             // a huge single round (the no-early-stop throughput mode): cut every set's draw stream into chunks
             ChunkOut* outs = static_cast<ChunkOut*>(w.chunk_outs);
-            ransac_sample_chunk_kernel<<<dim3((unsigned)w.n_chunks, (unsigned)w.n_sets), SMP_THREADS, 0, st>>>(w, rb, w.n_chunks, outs, w.chunk_lists);
+            ransac_sample_map_kernel<<<dim3((unsigned)w.n_chunks, (unsigned)w.n_sets), SMP_THREADS, 0, st>>>(w, rb, w.n_chunks, w.chunk_maps);
+            ransac_sample_entry_kernel<<<w.n_sets, 256, 0, st>>>(w.n_chunks, w.chunk_maps, w.chunk_entries);
+            ransac_sample_chunk_kernel<<<dim3((unsigned)w.n_chunks, (unsigned)w.n_sets), SMP_THREADS, 0, st>>>(w, rb, w.n_chunks, w.chunk_entries,
+                                                                                                              outs, w.chunk_lists);
             ransac_sample_stitch_kernel<<<(w.n_sets + 63) / 64, 64, 0, st>>>(w, rb, rb + len, w.n_chunks, outs, w.chunk_lists,
                                                                             w.chunk_offsets, w.chunk_serial);
             ransac_sample_scatter_kernel<<<dim3((unsigned)w.n_chunks, (unsigned)w.n_sets), 256, 0, st>>>(w, rb + len, w.n_chunks, outs,
                                                                                                      w.chunk_lists, w.chunk_offsets);
             ransac_sample_kernel<<<w.n_sets, SMP_THREADS, 0, st>>>(w, rb, rb + len, w.chunk_serial);   // sets the stitch rejected
-            launches += 3;
+            launches += 5;
         } else
             ransac_sample_kernel<<<w.n_sets, SMP_THREADS, 0, st>>>(w, rb, rb + len, nullptr);
         const bool timed = hyp_events != nullptr && round < 16;

@@ -218,6 +218,10 @@ int  cvg_dev_merge_top2(cvg_ctx* ctx, void* stream, const float* dist_parts_dev,
 int  cvg_last_match_path(const cvg_ctx* ctx);
 /* Rows of the last path-3 call that the re-rank could not prove and the exact fallback kernel redid. */
 int  cvg_last_match_fallback_rows(const cvg_ctx* ctx);
+/* Verify calls with CVG_RANSAC_NO_EARLY_STOP and max_iters >= 32768 cut every set's cv::RNG draw stream into
+ * chunks walked by many CTAs (same samples as the serial walk).  Returns how many sets of the last such call
+ * were handed back to the one-CTA-per-set sampler, or -1 if the last verify call did not use the chunked sampler. */
+int  cvg_last_sampler_serial_sets(const cvg_ctx* ctx);
 /* The context's cudaStream_t (all of its GPU work is issued there); lets a harness record its own
  * CUDA events around calls. */
 void* cvg_stream(const cvg_ctx* ctx);

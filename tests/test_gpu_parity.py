@@ -325,9 +325,10 @@ def test_find_homography_batch_shapes_thread_kernel(ctx, api, oracle):
 
 
 def test_chunked_sampler_huge_single_round(ctx, api, oracle):
-    """max_iters >= 32768 without early stop: the draw stream is walked by many CTAs at once (chunks whose entry is
-    found by letting 64 marked chains meet, accepted only if exit(c-1) == entry(c)).  The result must be the serial
-    loop's: at 4-5 % inliers the reference's adaptive niters never drops below max_iters, so its loop is exhaustive."""
+    """max_iters >= 32768 without early stop: the draw stream is walked by many CTAs at once (per-chunk entry -> exit
+    maps composed in order give every chunk its true entry; accepted only if exit(c-1) == entry(c)).  The result must
+    be the serial loop's: at 4-5 % inliers the reference's adaptive niters never drops below max_iters, so its loop is
+    exhaustive.  last_sampler_serial_sets says how many sets the chunked sampler gave up on: none here."""
     rng = np.random.default_rng(6100)
     srcs, dsts, offs, refs = [], [], [0], []
     for n, rho in ((600, 0.05), (300, 0.04), (4, 1.0), (2000, 0.03), (7, 0.6)):
@@ -336,6 +337,7 @@ def test_chunked_sampler_huge_single_round(ctx, api, oracle):
     iters = 70000
     out = ctx.find_homography_batch(np.concatenate(srcs), np.concatenate(dsts), offs, max_iters=iters,
                                     flags=api.RANSAC_NO_EARLY_STOP | api.RANSAC_NO_REFINE)
+    assert ctx.last_sampler_serial_sets == 0
     for k, (s, d) in enumerate(zip(srcs, dsts)):
         a, b = offs[k], offs[k + 1]
         if len(s) == 4:
@@ -349,6 +351,15 @@ def test_chunked_sampler_huge_single_round(ctx, api, oracle):
         assert np.array_equal(out["H"][k], ref["H"]), k
         refs.append(k)
     assert len(refs) >= 3
+    # many correspondences: nearly every attempt consumes exactly four draws, chains of different phase never meet
+    s8, d8, _ = synth.correspondences(rng, 8192, 0.02)
+    ref = oracle.ransac_stage(s8, d8, max_iters=40000)
+    assert ref["info"]["iters_run"] == 40000
+    H, mask = ctx.find_homography(s8, d8, max_iters=40000, flags=api.RANSAC_NO_EARLY_STOP | api.RANSAC_NO_REFINE)
+    assert ctx.last_sampler_serial_sets == 0
+    assert np.array_equal(mask, ref["mask"]) and np.array_equal(H, ref["H"])
+    H, mask = ctx.find_homography(s8, d8, max_iters=2000)
+    assert ctx.last_sampler_serial_sets == -1
     # a high-rejection set (most attempts fail checkSubset): long failure runs, the draw table is regrown
     n = 200
     src, dst, _ = synth.correspondences(rng, n, 0.5)

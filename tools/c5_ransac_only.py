@@ -7,7 +7,7 @@ n_hyp = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 src, dst, _ = synth.correspondences(np.random.default_rng(5002), 8192, 0.3)
 ctx = api.Context(0)
 ctx.set_timing(True)
-for rep in range(3):
+for rep in range(int(sys.argv[2]) if len(sys.argv) > 2 else 3):
     t0 = time.perf_counter()
     H, mask = ctx.find_homography(src, dst, max_iters=n_hyp, flags=api.RANSAC_NO_EARLY_STOP | api.RANSAC_NO_REFINE)
     dt = time.perf_counter() - t0
