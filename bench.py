@@ -13,9 +13,10 @@ the way the reference batches it (one model view vs. many test images, src/Tests
   e2e   : pairs/s through the public host-buffer API: every step uploads its B scene sets from pinned
           host memory (cvg_scenes_upload_async, step k+1's upload overlapping step k's compute), runs
           cvg_detect_scenes and reads the per-pair results back
-  roofline : the dominant kernel of the step (RANSAC hypothesis kernel: 16 B per scored (hypothesis, correspondence)
-             against the HBM copy bandwidth); roofline_match: the tcgen05 match kernel, 2*Nq*Nt*128 flop per pair
-             against the measured cuBLAS bf16 rate — both from CUDA events around the kernels inside the timed steps
+  roofline : the tcgen05 match kernel, the largest kernel of the step that has a roofline (2*Nq*Nt*128 flop per pair
+             against the measured cuBLAS bf16 rate); roofline_score: the inlier-counting kernel, 16 B per scored
+             (hypothesis, correspondence) against the HBM copy bandwidth; solve_stage: the 4-point DLT kernel (fp64 Jacobi,
+             latency-bound, hypotheses/s) — all from CUDA events around the kernels inside the timed steps
   cpu_baseline : cv2 4.13.0 (the reference's own arithmetic) on this host's cores, bounded sample
 
 `--impl reference` times the reference's CPU implementation (cv2 BFMatcher.knnMatch + findHomography, all
@@ -275,6 +276,7 @@ def run_cvgraft(args):
     # ---- value: scene sets resident in HBM --------------------------------------------------------
     resident = [ctx.upload_scenes(d, k, o) for d, k, o in batches]
     match_ms, ransac_ms, hyp_ms, hyp_launches, scored, accepted = [], [], [], [], [], 0
+    score_ms = []
 
     def step_resident(k):
         nonlocal accepted
@@ -282,6 +284,7 @@ def run_cvgraft(args):
         t = ctx.last_timing()
         match_ms.append(t["match_ms"]); ransac_ms.append(t["ransac_ms"])
         hyp_ms.append(t["hyp_ms"]); hyp_launches.append(t["hyp_launches"]); scored.append(t["scored_points"])
+        score_ms.append(t["score_ms"])
         accepted += int((res["status"] == 0).sum())
 
     # Phase 1 — ONE context, calls back to back (every call synchronous): the kernels run alone, so the CUDA-event
@@ -289,6 +292,7 @@ def run_cvgraft(args):
     for k in range(args.warmup):
         step_resident(k)
     match_ms.clear(); ransac_ms.clear(); hyp_ms.clear(); hyp_launches.clear(); scored.clear(); accepted = 0
+    score_ms.clear()
     ms_single = timed(step_resident, args.steps)
     value_single = world * B * args.steps / (ms_single * 1e-3)
 
@@ -469,7 +473,7 @@ def run_cvgraft(args):
             with open(tpath) as f:
                 tj = json.load(f)
             traffic = tj.get("match_tc_kernel", {}).get("dram_bytes_per_pair", 0) * B or None
-            hj = tj.get("ransac_hyp_t_kernel", {})
+            hj = tj.get("ransac_score_kernel", {})
             if hj.get("measured_at_sets_per_launch") == B:
                 hyp_traffic = hj.get("dram_bytes_per_launch")
         flops = 2.0 * NQ * NT * DIM * B
@@ -492,34 +496,46 @@ def run_cvgraft(args):
                 "real_dataset": real,
                 "gpu_launches": int(launches),
                 "clocks": clk,
-                # dominant kernel of the step by device time: the RANSAC hypothesis kernel (DLT solve + scoring).
-                # SURVEY 8d: scoring is a streaming scan, 16 B per (hypothesis, correspondence), HBM roofline.
-                "roofline": {"kernel": "ransac_hyp_t_kernel (4-pt DLT + inlier scoring, one hypothesis per thread; one launch per RANSAC round, "
-                                       "rounds past the adaptive stop exit early)", "bound": "hbm",
-                             "achieved": 16.0 * sum(scored) / max(sum(hyp_ms) * 1e-3, 1e-12) / 1e9, "peak": peaks["hbm"],
-                             "unit": "GB/s",
-                             "frac": 16.0 * sum(scored) / max(sum(hyp_ms) * 1e-3, 1e-12) / 1e9 / peaks["hbm"],
-                             "peak_source": peaks["source"] + " (copy bandwidth)",
-                             "kernel_ms_per_launch": sum(hyp_ms) / max(sum(hyp_launches), 1),
-                             "launches_per_step": sum(hyp_launches) / args.steps,
-                             "algorithmic_bytes_per_launch": 16.0 * sum(scored) / max(sum(hyp_launches), 1),
-                             "share_of_step": sum(hyp_ms) / ms_single, "traffic": hyp_traffic,
+                # The largest kernel of the step that has a roofline: the tcgen05 match kernel (tensor bound).  The refit/LM
+                # kernel (ransac_finish_kernel) has a longer single launch when the kernels run alone, but it is 64 CTAs of
+                # serial fp64 eigen-solves — latency, no roofline; with C contexts it hides under the other batches' kernels.
+                "roofline": {"kernel": "match_tc_kernel (tcgen05)", "bound": "tensor", "achieved": achieved,
+                             "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
+                             "peak_burst": peaks["bf16_burst"], "frac_of_burst": achieved / peaks["bf16_burst"],
+                             "peak_source": peaks["source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
+                             "kernel_ms_per_launch": kms, "launches_per_step": 1, "algorithmic_flops_per_launch": flops,
+                             "share_of_step": sum(match_ms) / ms_single, "traffic": traffic,
                              "timed_region": "single-context pass (value_single_context): with several contexts in flight "
                                              "kernels of different batches overlap and a launch duration is no longer a "
-                                             "utilisation figure",
-                             "note": "bound in practice by the fp64 Jacobi of the 4-point DLT (one 9x9 eigen-solve per "
-                                     "hypothesis, ~140 dependent rotations of ~1000 instructions), not by bandwidth: each CTA "
-                                     "stages its sets' correspondences once in shared memory, so DRAM traffic is far below "
-                                     "the algorithmic 16 B per (hypothesis, correspondence)"},
-                "roofline_match": {"kernel": "match_tc_kernel (tcgen05)", "bound": "tensor", "achieved": achieved,
-                                   "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
-                                   "peak_burst": peaks["bf16_burst"], "frac_of_burst": achieved / peaks["bf16_burst"],
-                                   "peak_source": peaks["source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
-                                   "kernel_ms_per_launch": kms, "algorithmic_flops_per_launch": flops,
-                                   "share_of_step": sum(match_ms) / ms_single, "traffic": traffic},
+                                             "utilisation figure"},
+                # SURVEY 8d: scoring is a streaming scan, 16 B per (hypothesis, correspondence), HBM roofline.
+                "roofline_score": {"kernel": "ransac_score_kernel (inlier counting of a round's models, one hypothesis per thread, "
+                                             "correspondences staged in shared memory; one launch per RANSAC round)", "bound": "hbm",
+                                   "achieved": 16.0 * sum(scored) / max(sum(score_ms) * 1e-3, 1e-12) / 1e9, "peak": peaks["hbm"],
+                                   "unit": "GB/s",
+                                   "frac": 16.0 * sum(scored) / max(sum(score_ms) * 1e-3, 1e-12) / 1e9 / peaks["hbm"],
+                                   "peak_source": peaks["source"] + " (copy bandwidth)",
+                                   "kernel_ms_per_launch": sum(score_ms) / max(sum(hyp_launches), 1),
+                                   "launches_per_step": sum(hyp_launches) / args.steps,
+                                   "algorithmic_bytes_per_launch": 16.0 * sum(scored) / max(sum(hyp_launches), 1),
+                                   "share_of_step": sum(score_ms) / ms_single, "traffic": hyp_traffic,
+                                   "fp32_issue_frac": 28.0 * sum(scored) / max(sum(score_ms) * 1e-3, 1e-12)
+                                                      / (148 * 128 * (clk.get("sm_mhz") or 1965.0) * 1e6),
+                                   "note": "frac can exceed 1: a CTA reads its slice of the correspondences from HBM/L2 once and "
+                                           "scores 256 hypotheses against it from shared memory, so the algorithmic 16 B per "
+                                           "(hypothesis, correspondence) is not DRAM traffic; the real ceiling is the fp32 issue "
+                                           "rate (28 non-FMA instructions per pair, fp32_issue_frac)"},
+                "solve_stage": {"kernel": "ransac_hyp_t_kernel (4-point DLT: bit-exact fp64 9x9 Jacobi, one hypothesis per thread; "
+                                          "one launch per RANSAC round, rounds past the adaptive stop exit early)",
+                                "ms_per_step": statistics.mean(hyp_ms), "launches_per_step": sum(hyp_launches) / args.steps,
+                                "share_of_step": sum(hyp_ms) / ms_single,
+                                "note": "latency-bound (~140 dependent rotations per matrix, 7 warps per SM: the matrix state fills "
+                                        "shared memory); no bandwidth or tensor roofline applies"},
                 "value_single_context": {"value": value_single, "unit": UNIT, "ms_per_step": ms_single / args.steps,
                                          "note": "one context, synchronous calls back to back: the timed region of the rooflines"},
-                "stage_ms_per_step": {"match_kernel": kms, "verify": statistics.mean(ransac_ms), "verify_hyp_kernels": statistics.mean(hyp_ms)},
+                "stage_ms_per_step": {"match_kernel": kms, "verify": statistics.mean(ransac_ms), "verify_solve_kernels": statistics.mean(hyp_ms),
+                                      "verify_score_kernels": statistics.mean(score_ms),
+                                      "verify_rest(sampler, select, refit/LM finish, gates)": statistics.mean(ransac_ms) - statistics.mean(hyp_ms) - statistics.mean(score_ms)},
                 "accepted_pairs": accepted_multi}
         if world == 1 and not args.no_cpu:
             os.sched_setaffinity(0, all_cpus)           # the CPU baseline gets every core of the box

@@ -205,6 +205,12 @@ class Context:
     def launch_count(self):
         return int(self.lib.cvg_launch_count(self.handle))
 
+    def selftest(self, which=0):
+        """Device self test `which` (include/cvgraft.h); returns the number of mismatches (0 = pass)."""
+        n = C.c_uint64(0)
+        self._check(self.lib.cvg_selftest(self.handle, int(which), C.byref(n)))
+        return int(n.value)
+
     def set_timing(self, on=True):
         self._check(self.lib.cvg_set_timing(self.handle, int(on)))
 
@@ -213,7 +219,9 @@ class Context:
         self.lib.cvg_last_timing(self.handle, C.byref(a), C.byref(b), C.byref(c))
         h, n, p = C.c_float(), C.c_int(), C.c_uint64()
         self.lib.cvg_last_hyp_stats(self.handle, C.byref(h), C.byref(n), C.byref(p))
-        return {"match_ms": a.value, "ransac_ms": b.value, "total_ms": c.value,
+        sc = C.c_float()
+        self.lib.cvg_last_score_ms(self.handle, C.byref(sc))
+        return {"match_ms": a.value, "ransac_ms": b.value, "total_ms": c.value, "score_ms": sc.value,
                 "hyp_ms": h.value, "hyp_launches": n.value, "scored_points": p.value}
 
     # ---- verify stage --------------------------------------------------------------------------

@@ -121,14 +121,15 @@ struct cvg_ctx {
     int last_match_path = 0; int64_t launches = 0;
     int timing = 0; float t_match = 0, t_ransac = 0, t_total = 0;
     cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
-    cudaEvent_t hyp_ev[32] = {};                       // brackets of the hypothesis kernel, per round
-    int hyp_rounds = 0; float t_hyp = 0; int hyp_launches = 0; unsigned long long scored_pts = 0;
+    cudaEvent_t hyp_ev[48] = {};                       // [2r], [2r+1]: solve kernel of round r; [32 + r]: after its score kernel
+    int hyp_rounds = 0; float t_hyp = 0, t_score = 0; int hyp_launches = 0; unsigned long long scored_pts = 0;
     unsigned long long* d_scored = nullptr;
     // scratch
     DevBuf q_f32, q_b, q_blo, q_aug, q_norm;           // raw-query path
     DevBuf t_f32, t_b, t_blo, t_aug, t_kpt, t_kptoff, t_segtab;  // per-call train path
     DevBuf units, dir, parts, idx, dist, accept;
     DevBuf parts4, segdev, fb;                         // candidate path: Top4 records, segment table, unproven rows
+    DevBuf hypH;                                       // fp32 models of the current round(s), read by ransac_score_kernel
     DevBuf chunk;                                      // chunked sampler scratch (huge no-early-stop rounds)
     DevBuf plan_units, plan_dir;                       // match plan of the fused path, cached by (model set, scene shapes)
     bool last_chunked = false;                         // the last verify call used the chunked sampler (d_flags[17] = sets it handed back)
@@ -207,7 +208,7 @@ int cvg_create(cvg_ctx** out, int device, unsigned flags)
     CU_CHECK(cudaMalloc(&c->d_flags, 64 * sizeof(int)));
     CU_CHECK(cudaMemset(c->d_flags, 0, 64 * sizeof(int)));
     for (int i = 0; i < 6; i++) CU_CHECK(cudaEventCreate(&c->ev[i]));
-    for (int i = 0; i < 32; i++) CU_CHECK(cudaEventCreate(&c->hyp_ev[i]));
+    for (int i = 0; i < 48; i++) CU_CHECK(cudaEventCreate(&c->hyp_ev[i]));
     CU_CHECK(cudaMalloc(&c->d_scored, 8));
     CU_CHECK(cudaMemset(c->d_scored, 0, 8));
     c->stage_cap = 4u << 20;
@@ -228,7 +229,7 @@ void cvg_destroy(cvg_ctx* c)
     cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     DevBuf* bufs[] = { &c->q_f32, &c->q_b, &c->q_blo, &c->q_aug, &c->q_norm, &c->t_f32, &c->t_b, &c->t_blo, &c->t_aug, &c->t_segtab, &c->t_kpt, &c->t_kptoff,
-                       &c->units, &c->dir, &c->parts, &c->parts4, &c->segdev, &c->fb, &c->plan_units, &c->plan_dir, &c->chunk, &c->idx, &c->dist, &c->accept, &c->pts, &c->starts, &c->counts_n,
+                       &c->units, &c->dir, &c->parts, &c->parts4, &c->segdev, &c->fb, &c->plan_units, &c->plan_dir, &c->chunk, &c->hypH, &c->idx, &c->dist, &c->accept, &c->pts, &c->starts, &c->counts_n,
                        &c->sample_pos, &c->n_samples, &c->counts, &c->best_iter, &c->best_count, &c->iters_run, &c->niters_cur, &c->smp_state, &c->sel,
                        &c->H, &c->mask, &c->rmask, &c->found, &c->sflags, &c->results, &c->inl_xy, &c->inl_cnt,
                        &c->scales, &c->src, &c->dst };
@@ -237,7 +238,7 @@ void cvg_destroy(cvg_ctx* c)
     if (c->d_flags) cudaFree(c->d_flags);
     if (c->d_rng) cudaFree(c->d_rng);
     for (int i = 0; i < 6; i++) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-    for (int i = 0; i < 32; i++) if (c->hyp_ev[i]) cudaEventDestroy(c->hyp_ev[i]);
+    for (int i = 0; i < 48; i++) if (c->hyp_ev[i]) cudaEventDestroy(c->hyp_ev[i]);
     if (c->d_scored) cudaFree(c->d_scored);
     if (c->stage_h) cudaFreeHost(c->stage_h);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -276,6 +277,24 @@ int cvg_last_hyp_stats(const cvg_ctx* c, float* hyp_ms, int* hyp_launches, uint6
     if (!c) return CVG_ERR_INVALID;
     if (hyp_ms) *hyp_ms = c->t_hyp; if (hyp_launches) *hyp_launches = c->hyp_launches;
     if (scored_points) *scored_points = c->scored_pts;
+    return CVG_OK;
+}
+int cvg_selftest(cvg_ctx* c, int which, uint64_t* mismatches)
+{
+    if (!c || !mismatches || which != 0) return set_err(CVG_ERR_INVALID, "cvg_selftest: bad argument");
+    CU_CHECK(cudaSetDevice(c->device));
+    CU_CHECK(cudaMemsetAsync(c->d_scored, 0, 8, c->stream));
+    c->launches += launch_selftest_rcp(c->d_scored, c->stream);
+    unsigned long long n = 0;
+    CU_CHECK(cudaMemcpyAsync(&n, c->d_scored, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(cudaStreamSynchronize(c->stream));
+    *mismatches = n;
+    return CVG_OK;
+}
+int cvg_last_score_ms(const cvg_ctx* c, float* score_ms)
+{
+    if (!c || !score_ms) return CVG_ERR_INVALID;
+    *score_ms = c->t_score;
     return CVG_OK;
 }
 int64_t cvg_launch_count(const cvg_ctx* c) { return c ? c->launches : 0; }
@@ -507,6 +526,8 @@ static int run_ransac(cvg_ctx* c, const float4* d_pts, const int64_t* d_starts, 
     const int mi = std::max(p->max_iters, 1);
     CU_CHECK(c->sample_pos.ensure((size_t)n_sets * mi * 4));
     CU_CHECK(c->counts.ensure((size_t)n_sets * mi * 4));
+    static const bool split_score = !(getenv("CVG_FUSED_SCORE") && atoi(getenv("CVG_FUSED_SCORE")));   // A/B: 1 = score inside the solve kernel
+    if (split_score) CU_CHECK(c->hypH.ensure((size_t)n_sets * mi * 32));
     CU_CHECK(c->n_samples.ensure((size_t)n_sets * 4));
     CU_CHECK(c->best_iter.ensure((size_t)n_sets * 4));
     CU_CHECK(c->best_count.ensure((size_t)n_sets * 4));
@@ -527,6 +548,7 @@ static int run_ransac(cvg_ctx* c, const float4* d_pts, const int64_t* d_starts, 
     w.conf = p->confidence; w.flags = p->flags;
     w.rng_tab = c->d_rng; w.rng_len = c->rng_len;
     w.sample_pos = c->sample_pos.as<int32_t>(); w.n_samples = c->n_samples.as<int32_t>();
+    w.hyp_H = split_score ? c->hypH.as<float>() : nullptr;
     w.counts = c->counts.as<int32_t>(); w.best_iter = c->best_iter.as<int32_t>();
     w.best_count = c->best_count.as<int32_t>(); w.iters_run = c->iters_run.as<int32_t>();
     w.niters_cur = c->niters_cur.as<int32_t>();
@@ -877,8 +899,11 @@ static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, Tra
     }
     c->last_match_path = path == 0 ? path_from_device_word(flag) : path;
     if (c->timing) {
-        c->t_hyp = 0;
-        for (int r = 0; r < c->hyp_rounds; r++) { float t = 0; cudaEventElapsedTime(&t, c->hyp_ev[2 * r], c->hyp_ev[2 * r + 1]); c->t_hyp += t; }
+        c->t_hyp = 0; c->t_score = 0;
+        for (int r = 0; r < c->hyp_rounds; r++) {
+            float t = 0; cudaEventElapsedTime(&t, c->hyp_ev[2 * r], c->hyp_ev[2 * r + 1]); c->t_hyp += t;
+            t = 0; cudaEventElapsedTime(&t, c->hyp_ev[2 * r + 1], c->hyp_ev[32 + r]); c->t_score += t;
+        }
         c->hyp_launches = c->hyp_rounds;
         cudaMemcpy(&c->scored_pts, c->d_scored, 8, cudaMemcpyDeviceToHost);
         cudaEventElapsedTime(&c->t_match, c->ev[3], c->ev[4]);      // the match kernel(s) alone

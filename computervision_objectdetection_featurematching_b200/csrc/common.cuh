@@ -118,6 +118,7 @@ struct RansacWork {
     int32_t* niters_cur;        // [P] adaptive niters after the rounds scanned so far
     int64_t* smp_state;         // [P, 2] sampler state between rounds: next draw position, failure run (-1 = finished)
     unsigned long long* scored_pts;   // device counter: sum over scored hypotheses of n (or NULL)
+    float* hyp_H;               // [P, max_iters, 8] fp32 models for ransac_score_kernel, or NULL = score inside the solve kernel
     int32_t* sel;               // [total] compacted inlier indices
     // outputs
     double* H;                  // [P, 9]
@@ -133,7 +134,9 @@ struct RansacWork {
 int64_t ransac_chunk_scratch_bytes(int n_sets, int n_chunks, size_t* outs, size_t* lists, size_t* offsets, size_t* serial,
                                    size_t* maps, size_t* entries);
 int ransac_chunks_for_table(int64_t rng_len);
-// returns the number of kernel launches; hyp_events (optional, 32 events) bracket the hypothesis kernel of each round
+int launch_selftest_rcp(unsigned long long* d_mismatches, cudaStream_t st);
+// returns the number of kernel launches; hyp_events (optional, 48 events): [2r], [2r+1] bracket the solve kernel of round r,
+// [32 + r] follows its score kernel
 int  launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events = nullptr, int* n_hyp_rounds = nullptr);
 
 // detect glue (ransac.cu)

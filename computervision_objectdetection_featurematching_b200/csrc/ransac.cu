@@ -818,6 +818,17 @@ ransac_hyp_t_kernel(RansacWork w, int round_base, int round_len)
         #pragma unroll
         for (int i = 0; i < 8; i++) Hf[i] = valid ? (float)H[i] : 0.f;
     }
+    if (w.hyp_H) {
+        // split mode: the model goes to HBM (32 B), ransac_score_kernel counts its inliers at full occupancy
+        if (live) {
+            float4* dst = reinterpret_cast<float4*>(w.hyp_H + ((size_t)set * w.max_iters + iter) * 8);
+            dst[0] = make_float4(Hf[0], Hf[1], Hf[2], Hf[3]);
+            dst[1] = make_float4(Hf[4], Hf[5], Hf[6], Hf[7]);
+            w.counts[(size_t)set * w.max_iters + iter] = valid ? 0 : -1;
+            if (w.scored_pts && valid) atomicAdd(w.scored_pts, (unsigned long long)n);
+        }
+        return;
+    }
     // ---- scoring: the matrix state is dead, the CTA's shared memory becomes a staging buffer for the
     //      correspondences of the (one or two, rarely more) sets its hypotheses belong to ----
     constexpr int STAGE_PTS = HYPT_SMEM / 16;                   // 14 112 correspondences
@@ -846,6 +857,59 @@ ransac_hyp_t_kernel(RansacWork w, int round_base, int round_len)
     if (live) {
         w.counts[(size_t)set * w.max_iters + iter] = valid ? cnt : -1;
         if (w.scored_pts && valid) atomicAdd(w.scored_pts, (unsigned long long)n);
+    }
+}
+
+// Scoring of the models ransac_hyp_t_kernel left in hyp_H: one hypothesis per thread, a CTA = SCORE_THREADS
+// consecutive iterations of ONE set x one slice of its correspondences (blockIdx.z), staged in shared memory and read
+// as warp-uniform float4 broadcasts.  The solve kernel holds 7 warps per SM (its matrix state fills shared memory);
+// here a CTA needs 32 KB, so the fp32 pipe sees 48+ warps.  Slices add their counts with atomicAdd (integer: order-free).
+constexpr int SCORE_THREADS = 256;
+constexpr int SCORE_STAGE = 2048;
+__global__ void __launch_bounds__(SCORE_THREADS)
+ransac_score_kernel(RansacWork w, int round_base, int round_len, int n_slices)
+{
+    __shared__ float4 stage[SCORE_STAGE];
+    const int set = blockIdx.y;
+    const int r = blockIdx.x * SCORE_THREADS + threadIdx.x;
+    const int iter = round_base + r;
+    const int n = w.counts_n[set];
+    const size_t slot = (size_t)set * w.max_iters + iter;
+    bool live = r < round_len && iter < w.n_samples[set] && iter < w.niters_cur[set];
+    if (live) live = w.counts[slot] >= 0;                        // -1: degenerate sample, no model
+    if (!__syncthreads_or(live)) return;
+    float Hf[8];
+    if (live) {
+        const float4* src = reinterpret_cast<const float4*>(w.hyp_H + slot * 8);
+        const float4 a = src[0], b = src[1];
+        Hf[0] = a.x; Hf[1] = a.y; Hf[2] = a.z; Hf[3] = a.w; Hf[4] = b.x; Hf[5] = b.y; Hf[6] = b.z; Hf[7] = b.w;
+    } else {
+        #pragma unroll
+        for (int i = 0; i < 8; i++) Hf[i] = 0.f;
+    }
+    const int per = (n + n_slices - 1) / n_slices;
+    const int p0 = min(n, (int)blockIdx.z * per), p1 = min(n, p0 + per);
+    const float4* __restrict__ ps = w.pts + w.starts[set];
+    const float thr2 = w.thr2;
+    int cnt = 0;
+    for (int base = p0; base < p1; base += SCORE_STAGE) {
+        const int m = min(SCORE_STAGE, p1 - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < m; i += SCORE_THREADS) stage[i] = ps[base + i];
+        __syncthreads();
+        if (live) {
+            int i = 0;
+            #pragma unroll 2
+            for (; i + 4 <= m; i += 4)
+                cnt += count_inliers4(Hf, stage[i], stage[i + 1], stage[i + 2], stage[i + 3], thr2);
+            for (; i < m; i++) {
+                const float4 q = stage[i];
+                cnt += reproj_err(Hf, q.x, q.y, q.z, q.w) <= thr2 ? 1 : 0;     // NaN -> not an inlier
+            }
+        }
+    }
+    if (live && cnt) {
+        if (n_slices == 1) w.counts[slot] = cnt; else atomicAdd(&w.counts[slot], cnt);
     }
 }
 
@@ -1399,6 +1463,28 @@ int ransac_chunks_for_table(int64_t rng_len)
     return c < 0 ? 0 : (c > 1000000 ? 1000000 : (int)c);
 }
 
+// ---- self test 0: rcp_rn_fastpath == __frcp_rn on every float of the fast range (both signs) ----------------
+__global__ void selftest_rcp_kernel(unsigned long long* mismatches)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    // |x| in [2^-126, 2^126): bit patterns 0x00800000 .. 0x7E7FFFFF, and the same with the sign bit
+    for (uint64_t b = 0x00800000ull + blockIdx.x * blockDim.x + threadIdx.x; b < 0x7E800000ull; b += stride) {
+        #pragma unroll
+        for (uint32_t sgn = 0; sgn < 2; sgn++) {
+            const float x = __uint_as_float((uint32_t)b | (sgn << 31));
+            if (__float_as_uint(rcp_rn_fastpath(x)) != __float_as_uint(__frcp_rn(x))) bad++;
+            if (__float_as_uint(__frcp_rn(x)) != __float_as_uint(__fdiv_rn(1.f, x))) bad++;
+        }
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+int launch_selftest_rcp(unsigned long long* d_mismatches, cudaStream_t st)
+{
+    selftest_rcp_kernel<<<148 * 16, 256, 0, st>>>(d_mismatches);
+    return 1;
+}
+
 int launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events, int* n_hyp_rounds)
 {
     if (n_hyp_rounds) *n_hyp_rounds = 0;
@@ -1468,6 +1554,16 @@ int launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events,
             ransac_hyp_t_kernel<<<(unsigned)blocks, HYPT_THREADS, HYPT_SMEM, st>>>(w, rb, len);
         }
         if (timed) { cudaEventRecord(hyp_events[2 * round + 1], st); *n_hyp_rounds = round + 1; }
+        if (mode == 4 && w.hyp_H) {
+            // slices of the correspondences so that the launch holds >= ~6 CTAs per SM (or one slice per 512 points)
+            const int tiles = (len + SCORE_THREADS - 1) / SCORE_THREADS;
+            const int64_t ctas = (int64_t)tiles * w.n_sets;
+            int n_slices = (int)std::min<int64_t>(std::max<int64_t>(1, ((int64_t)n_sms * 6 + ctas - 1) / ctas), std::max(1, w.max_n / 512));
+            n_slices = std::max(1, std::min(n_slices, 64));
+            ransac_score_kernel<<<dim3((unsigned)tiles, (unsigned)w.n_sets, (unsigned)n_slices), SCORE_THREADS, 0, st>>>(w, rb, len, n_slices);
+            launches += 1;
+        }
+        if (timed) cudaEventRecord(hyp_events[32 + round], st);
         if (w.flags & CVG_RANSAC_NO_EARLY_STOP)
             ransac_select_all_kernel<<<w.n_sets, SELP_THREADS, 0, st>>>(w, rb, len);
         else

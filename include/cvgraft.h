@@ -236,6 +236,12 @@ int  cvg_last_timing(const cvg_ctx* ctx, float* match_ms, float* ransac_ms, floa
  * kernel launches, their number, and the number of (hypothesis, correspondence) pairs they scored —
  * 16 bytes each is the algorithmic traffic of the scoring. */
 int  cvg_last_hyp_stats(const cvg_ctx* ctx, float* hyp_ms, int* hyp_launches, uint64_t* scored_points);
+/* hyp_ms above covers the solve kernel (4-point DLT, one launch per round); the inlier counting of those models runs in
+ * ransac_score_kernel, one launch per round as well: its summed device time in the last fused call. */
+int  cvg_last_score_ms(const cvg_ctx* ctx, float* score_ms);
+/* Device self tests.  which = 0: the reciprocal the scoring kernel writes out by hand (MUFU.RCP + one Newton step) against
+ * __frcp_rn and against 1.f / x on EVERY float with 2^-126 <= |x| < 2^126; *mismatches must come back 0. */
+int  cvg_selftest(cvg_ctx* ctx, int which, uint64_t* mismatches);
 
 #ifdef __cplusplus
 }

@@ -324,6 +324,12 @@ def test_find_homography_batch_shapes_thread_kernel(ctx, api, oracle):
                 assert np.allclose(out["H"][k], ref["H"], rtol=1e-9, atol=1e-12), (case["max_iters"], k, n)
 
 
+def test_selftest_reciprocal_exhaustive(ctx):
+    """The scoring kernel's hand-written reciprocal (MUFU.RCP + one Newton step, four at a time behind one range test)
+    against __frcp_rn and 1.f / x on every float with 2^-126 <= |x| < 2^126: 0 mismatches of 2 x 4.2e9 comparisons."""
+    assert ctx.selftest(0) == 0
+
+
 def test_chunked_sampler_huge_single_round(ctx, api, oracle):
     """max_iters >= 32768 without early stop: the draw stream is walked by many CTAs at once (per-chunk entry -> exit
     maps composed in order give every chunk its true entry; accepted only if exit(c-1) == entry(c)).  The result must

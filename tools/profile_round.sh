@@ -15,6 +15,8 @@ ncu --set full --clock-control none --import-source on -k regex:match_tc -s 1 -c
     python tools/gpu_prof_match.py 64 > $out/${tag}_ncu_match.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:ransac_hyp_t -s 4 -c 1 -o $out/${tag}_prof_hyp \
     python tools/gpu_prof_match.py 64 > $out/${tag}_ncu_hyp.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:ransac_score -s 4 -c 1 -o $out/${tag}_prof_score \
+    python tools/gpu_prof_match.py 64 > $out/${tag}_ncu_score.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:ransac_finish -s 1 -c 1 -o $out/${tag}_prof_finish \
     python tools/gpu_prof_match.py 64 > $out/${tag}_ncu_finish.log 2>&1
 cat $out/${tag}_bench_n1.json; cat $out/${tag}_bench_reference_n1.json
