@@ -20,6 +20,7 @@ ACCEPT, LT4_MATCHES, H_EMPTY, LT4_INLIERS, DET_REJECT = range(5)
 RANSAC_NO_EARLY_STOP = 1
 RANSAC_NO_REFINE = 2
 FORCE_EXACT_MATCH = 1
+MATCH_PAIR_MODE = 2
 PATH_TENSOR, PATH_EXACT, PATH_TENSOR_RERANK = 1, 2, 3   # cvg_last_match_path
 
 PAIR_DTYPE = np.dtype([("status", "<i4"), ("n_good", "<i4"), ("n_inliers", "<i4"), ("ransac_iters", "<i4"),

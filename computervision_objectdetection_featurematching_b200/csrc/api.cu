@@ -415,29 +415,43 @@ static void build_plan(const QuerySide& q, const TrainSet& ts, int n_sms, std::v
         if (cost < best_cost - 1e-9) { best_cost = cost; best_ch = ch; }
     }
     units.clear(); dir.assign((size_t)ts.n_segs * n_rb, MergeEntry{ 0, 0 });
+    // With an even number of row blocks the list is made of PAIRS: units (2p, 2p + 1) are row blocks (2i, 2i + 1) against
+    // the same train tiles — what the cta_group::2 form of the match kernel needs (launch_match_tc, paired); any other
+    // consumer sees an ordinary unit list.  Partial slots stay consecutive per (segment, row block) for the merge.
+    const int group = (n_rb % 2 == 0) ? 2 : 1;
     int slot = 0;
     for (int s = 0; s < ts.n_segs; s++) {
         const SegInfo& g = ts.segs[s];
         const int n_chunks = (g.ct + best_ch - 1) / best_ch;
-        for (int rb = 0; rb < n_rb; rb++) {
-            dir[(size_t)s * n_rb + rb] = MergeEntry{ slot, n_chunks };
+        const int slot0 = slot;
+        for (int rb = 0; rb < n_rb; rb++) dir[(size_t)s * n_rb + rb] = MergeEntry{ slot0 + rb * n_chunks, n_chunks };
+        slot += n_rb * n_chunks;
+        for (int rb0 = 0; rb0 < n_rb; rb0 += group) {
             for (int ck = 0; ck < n_chunks; ck++) {
                 // spread tiles evenly over the chunks of this segment
                 const int t0 = (int)((int64_t)g.ct * ck / n_chunks), t1 = (int)((int64_t)g.ct * (ck + 1) / n_chunks);
-                MatchUnit u;
-                u.q_row0 = q.row_begin + rb * TILE_M;
-                u.t_row0 = (int32_t)(g.pad_row0 + (int64_t)t0 * TILE_N);
-                u.n_tiles = t1 - t0;
-                u.t_local0 = t0 * TILE_N;
-                u.part_slot = slot++;
-                u.seg_cols = g.rows;
-                u.t_row0_f32 = (int32_t)(g.f32_row0 + (int64_t)t0 * TILE_N);
-                u.pad1 = 0;
-                units.push_back(u);
+                for (int rb = rb0; rb < rb0 + group; rb++) {
+                    MatchUnit u;
+                    u.q_row0 = q.row_begin + rb * TILE_M;
+                    u.t_row0 = (int32_t)(g.pad_row0 + (int64_t)t0 * TILE_N);
+                    u.n_tiles = t1 - t0;
+                    u.t_local0 = t0 * TILE_N;
+                    u.part_slot = slot0 + rb * n_chunks + ck;
+                    u.seg_cols = g.rows;
+                    u.t_row0_f32 = (int32_t)(g.f32_row0 + (int64_t)t0 * TILE_N);
+                    u.pad1 = 0;
+                    units.push_back(u);
+                }
             }
         }
     }
-    std::stable_sort(units.begin(), units.end(), [](const MatchUnit& a, const MatchUnit& b) { return a.n_tiles > b.n_tiles; });
+    // largest first, groups kept together
+    std::vector<int> order(units.size() / group);
+    for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return units[(size_t)a * group].n_tiles > units[(size_t)b * group].n_tiles; });
+    std::vector<MatchUnit> sorted; sorted.reserve(units.size());
+    for (int gi : order) for (int k = 0; k < group; k++) sorted.push_back(units[(size_t)gi * group + k]);
+    units.swap(sorted);
 }
 
 // Match paths.  Host-side hints / cvg_last_match_path: 1 = tensor cores, exact (integer descriptors), 2 = exact fp32
@@ -475,7 +489,8 @@ static int launch_match(cvg_ctx* c, const QuerySide& q, const TrainSet& ts, cons
         TcOperands op{ q.d_b, q.d_aug, q.d_norm, q.n_pad, ts.d_b, ts.d_aug, (int)ts.rows_pad_total, q.d_blo, ts.d_blo };
         char err[256];
         if (want_int) {
-            if (launch_match_tc(op, d_units, n_units, d_parts, 2, gate, 0, c->d_flags + 8, c->n_sms, c->stream, err, sizeof err))
+            if (launch_match_tc(op, d_units, n_units, d_parts, 2, gate, 0, c->d_flags + 8, c->n_sms, c->stream, err, sizeof err,
+                                (tc_pair_mode_enabled() || (c->flags & CVG_MATCH_PAIR_MODE)) && n_rb % 2 == 0))
                 return set_err(CVG_ERR_CUDA, "%s", err);
             c->launches++;
         }

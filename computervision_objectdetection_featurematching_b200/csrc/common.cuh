@@ -76,9 +76,12 @@ struct TcOperands {
 int  tc_init(char* err, size_t errlen);     // resolves cuTensorMapEncodeTiled; 0 = ok
 // candidates = 2: exact top-2 (Top2 parts[n_units][128]); 4: candidate records (Top4 parts[n_units][4][128]).
 // gate_flag (device, may be NULL): the kernel runs only if *gate_flag == gate_want.
+// paired: the unit list is made of pairs (2p, 2p + 1) with the same train tiles (build_plan with an even number of row
+// blocks): the exact form then runs as clusters of two CTAs with cta_group::2 MMAs.
 int  launch_match_tc(const TcOperands& op, const MatchUnit* units, int n_units, void* parts, int candidates,
                      const int* gate_flag, int gate_want, int* dbg, int n_sms,
-                     cudaStream_t st, char* err, size_t errlen);
+                     cudaStream_t st, char* err, size_t errlen, bool paired = false);
+bool tc_pair_mode_enabled();                 // CVG_TC_PAIR=1: pair mode for every context of the process (A/B runs); else per context flag
 
 // merge.cu (in match_exact.cu)
 void launch_merge(const Top2* parts, const MergeEntry* dir, int n_segments, int n_rowblocks, int n_query,

@@ -36,6 +36,14 @@ constexpr uint32_t A_BYTES = 2 * A_ATOM_BYTES + A_AUG_BYTES;      //            
 constexpr int B_STAGES = 4;                                       // half-K stages
 constexpr uint32_t B_ATOM_BYTES = TILE_N * 128;                   // 256 rows x 64 bf16          32 KB
 constexpr uint32_t B_AUG_BYTES = TILE_N * KAUG * 2;               //                              8 KB
+// Pair mode (cta_group::2): two CTAs of a cluster run ONE M256 N256 MMA on two 128-row query tiles against the same
+// train tiles.  Each CTA holds its own A tile and HALF of every B stage (128 train rows x 64 K = 16 KB), so a CTA pulls
+// 36 KB instead of 72 KB per tile out of L2 — the single-CTA kernel is bound by L2 -> SM bandwidth (148 x 72 KB per
+// 1.2 us tile = 17 TB/s wanted) — and the same 128 KB ring holds 8 stages (4 tiles of prefetch instead of 2).
+constexpr int B_STAGES_PAIR = 8;
+constexpr uint32_t B_HALF_BYTES = B_ATOM_BYTES / 2;               // 128 rows x 64 bf16          16 KB
+constexpr uint32_t B_AUG_HALF_BYTES = B_AUG_BYTES / 2;            //                              4 KB
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;                       // shared::cluster address of the pair's even CTA
 constexpr uint32_t OFF_A = 0;
 constexpr uint32_t OFF_B = 2 * A_BYTES;                           //  72 KB
 constexpr uint32_t OFF_BAUG = OFF_B + B_STAGES * B_ATOM_BYTES;    // 200 KB
@@ -92,6 +100,39 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// pair mode: the load lands in this CTA's shared memory, its bytes are counted on the LEADER CTA's barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(dst), "l"(map), "r"(bar & PEER_MASK), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(bar & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar)       // arrives on the barrier at this offset in BOTH CTAs
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar)
@@ -132,6 +173,7 @@ __device__ __forceinline__ uint64_t desc_sw32(uint32_t saddr)
 // instruction descriptor, kind::f16: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1),
 // both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+constexpr uint32_t TC_IDESC_PAIR = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE_N >> 3) << 17) | ((uint32_t)((2 * TILE_M) >> 4) << 24);
 
 // Running top-2 (largest acc') of one query row over 32 more train columns.  `f` is the row's filter: no
 // column with a value <= f can be one of the row's two best (f >= the warp's own second best b2, and it is
@@ -225,12 +267,14 @@ __device__ __forceinline__ void top4_scan32(const uint32_t* r, int c0, float (&b
     }
 }
 
-struct TcMaps { CUtensorMap q, qaug, t, taug, qlo, tlo; };
+struct TcMaps { CUtensorMap q, qaug, t, taug, qlo, tlo, th, taugh; };   // th / taugh: 128-row boxes of the train operand (pair mode)
 
 // KP = 2: exact top-2 per row (integer descriptors), partial records Top2 with distances.
 // KP = 4: four candidates per row and column part (non-integer descriptors), partial records Top4 with raw
 //         accumulator values, slot (part_slot * 4 + column part).
-template <int KP>
+// PAIR: launched as clusters of two CTAs (cta_group::2); unit 2p + r belongs to CTA r of the cluster that owns pair p, and
+//       both units of a pair name the same train tiles.
+template <int KP, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ qnorm,
                 const MatchUnit* __restrict__ units, int n_units, void* __restrict__ parts_out,
@@ -240,7 +284,17 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
     // scanning it, bit 1 = the producer re-arms ring stages without issuing the B loads
     if (gate_flag && *gate_flag != gate_want) return;
     constexpr bool SPLIT = KP == 4;                  // hi/lo split operands (non-integer descriptors)
+    static_assert(!(SPLIT && PAIR), "pair mode serves the exact (integer descriptor) form only");
     constexpr int N_STAGES_PER_TILE = SPLIT ? 4 : 2;
+    constexpr int NB = PAIR ? B_STAGES_PAIR : B_STAGES;                   // ring stages
+    constexpr uint32_t STAGE_BYTES = PAIR ? B_HALF_BYTES : B_ATOM_BYTES;  // bytes of a ring stage in THIS CTA
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    // persistent loop: worker w of n_workers takes list entries w, w + n_workers, ...; an entry is a unit, or a pair of units
+    const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int n_entries = PAIR ? n_units / 2 : n_units;
+    auto unit_of = [&](int e) { return PAIR ? 2 * e + (int)cta_rank : e; };
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -251,27 +305,36 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
     const uint32_t bar0 = smem_base + OFF_BAR;
     // barrier slots (8 bytes each)
     const uint32_t a_full = bar0, a_empty = bar0 + 16, t_full = bar0 + 32, t_empty = bar0 + 48;
-    const uint32_t b_full = bar0 + 64, b_empty = bar0 + 64 + 8 * B_STAGES;
-    const uint32_t g_full = bar0 + 64 + 16 * B_STAGES, g_empty = g_full + 16;      // augmentation ring (2 stages)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 64 + 16 * B_STAGES + 48);
+    const uint32_t b_full = bar0 + 64, b_empty = bar0 + 64 + 8 * NB;
+    constexpr int NG = PAIR ? 4 : 2;                                                // augmentation ring stages (pair: 4 KB each, as deep as the B ring)
+    constexpr uint32_t G_BYTES = PAIR ? B_AUG_HALF_BYTES : B_AUG_BYTES;
+    const uint32_t g_full = bar0 + 64 + 16 * NB, g_empty = g_full + 8 * NG;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 64 + 16 * NB + 16 * NG + 16);
+    static_assert(64 + 16 * B_STAGES_PAIR + 16 * 4 + 16 + 8 <= 512, "barrier area");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; i++) {
             mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1);
-            mbar_init(t_full + 8 * i, 1); mbar_init(t_empty + 8 * i, TC_EPI_WARPS);
-            mbar_init(g_full + 8 * i, 1); mbar_init(g_empty + 8 * i, 1);
+            mbar_init(t_full + 8 * i, 1); mbar_init(t_empty + 8 * i, (PAIR ? 2 : 1) * TC_EPI_WARPS);   // pair: both CTAs' epilogues arrive on the leader's
         }
-        for (int i = 0; i < B_STAGES; i++) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
+        for (int i = 0; i < NG; i++) { mbar_init(g_full + 8 * i, 1); mbar_init(g_empty + 8 * i, 1); }
+        for (int i = 0; i < NB; i++) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_slot)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {                            // the same warp of both CTAs
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_slot)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();          // the peer's barriers are initialised before anything is sent to them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -279,8 +342,8 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
         // ===================== TMA producer =====================
         if (lane == 0) {
             uint32_t ua = 0, bs = 0, tcnt = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ua++) {
-                const MatchUnit un = units[u];
+            for (int e = worker; e < n_entries; e += n_workers, ua++) {
+                const MatchUnit un = units[unit_of(e)];
                 // KP == 2: A tile (queries) double-buffered.  KP == 4 (split operands): one buffer holding the hi and lo
                 // halves of 2q — [hi k 0-63][hi k 64-127][lo k 0-63][lo k 64-127][aug] = 68 KB in the same 72 KB region.
                 const uint32_t ab = SPLIT ? 0u : (ua & 1);
@@ -293,6 +356,12 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                     tma_load_2d(sa + 2 * A_ATOM_BYTES, &maps.qlo, 0, un.q_row0, a_full);
                     tma_load_2d(sa + 3 * A_ATOM_BYTES, &maps.qlo, 64, un.q_row0, a_full);
                     tma_load_2d(sa + 4 * A_ATOM_BYTES, &maps.qaug, 0, un.q_row0, a_full);
+                } else if constexpr (PAIR) {
+                    // both CTAs load their own query tile; the bytes of both are counted on the leader's barrier
+                    if (leader) mbar_expect_tx(a_full + 8 * ab, 2 * A_BYTES);
+                    tma_load_2d_pair(sa, &maps.q, 0, un.q_row0, a_full + 8 * ab);
+                    tma_load_2d_pair(sa + A_ATOM_BYTES, &maps.q, 64, un.q_row0, a_full + 8 * ab);
+                    tma_load_2d_pair(sa + 2 * A_ATOM_BYTES, &maps.qaug, 0, un.q_row0, a_full + 8 * ab);
                 } else {
                     mbar_expect_tx(a_full + 8 * ab, A_BYTES);
                     tma_load_2d(sa, &maps.q, 0, un.q_row0, a_full + 8 * ab);
@@ -305,26 +374,51 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                     // of its lo part (stages 2, 3)
                     #pragma unroll 1
                     for (int h = 0; h < N_STAGES_PER_TILE; h++, bs++) {
-                        const uint32_t s = bs % B_STAGES;
-                        mbar_wait(b_empty + 8 * s, ((bs / B_STAGES) & 1) ^ 1, dbg, 2);
+                        const uint32_t s = bs % NB;
+                        mbar_wait(b_empty + 8 * s, ((bs / NB) & 1) ^ 1, dbg, 2);
+                        if constexpr (PAIR) {
+                            // this CTA's half of the stage: train rows [row + 128 r, +128) — accumulator columns 128 r ..
+                            if ((exp_mode & 2) && bs >= NB) { if (leader) mbar_arrive(b_full + 8 * s); continue; }
+                            if (leader) mbar_expect_tx(b_full + 8 * s, 2 * B_HALF_BYTES);
+                            tma_load_2d_pair(smem_base + OFF_B + s * B_HALF_BYTES, &maps.th, 64 * (h & 1), row + (int)cta_rank * (TILE_N / 2),
+                                             b_full + 8 * s);
+                            continue;
+                        }
                         if (!SPLIT && (exp_mode & 2) && bs >= B_STAGES) { mbar_arrive(b_full + 8 * s); continue; }
                         mbar_expect_tx(b_full + 8 * s, B_ATOM_BYTES);
                         tma_load_2d(smem_base + OFF_B + s * B_ATOM_BYTES, (SPLIT && h >= 2) ? &maps.tlo : &maps.t, 64 * (h & 1), row,
                                     b_full + 8 * s);
                     }
-                    const uint32_t g = tcnt & 1;
-                    mbar_wait(g_empty + 8 * g, ((tcnt >> 1) & 1) ^ 1, dbg, 7);
+                    const uint32_t g = tcnt % NG;
+                    mbar_wait(g_empty + 8 * g, ((tcnt / NG) & 1) ^ 1, dbg, 7);
+                    if constexpr (PAIR) {
+                        if (leader) mbar_expect_tx(g_full + 8 * g, 2 * B_AUG_HALF_BYTES);
+                        tma_load_2d_pair(smem_base + OFF_BAUG + g * G_BYTES, &maps.taugh, 0, row + (int)cta_rank * (TILE_N / 2), g_full + 8 * g);
+                        continue;
+                    }
                     mbar_expect_tx(g_full + 8 * g, B_AUG_BYTES);
                     tma_load_2d(smem_base + OFF_BAUG + g * B_AUG_BYTES, &maps.taug, 0, row, g_full + 8 * g);
                 }
             }
+            if constexpr (PAIR) {
+                // tail: the leader's last commits are multicast to this CTA's barriers as well; wait for the release of
+                // every slot's last use so that nothing is still on its way here when the CTA exits
+                for (int k = 0; k < NB; k++, bs++) mbar_wait(b_empty + 8 * (bs % NB), ((bs / NB) & 1) ^ 1, dbg, 12);
+                for (int k = 0; k < NG; k++, tcnt++) mbar_wait(g_empty + 8 * (tcnt % NG), ((tcnt / NG) & 1) ^ 1, dbg, 13);
+                for (int k = 0; k < 2; k++, ua++) mbar_wait(a_empty + 8 * (ua & 1), ((ua >> 1) & 1) ^ 1, dbg, 14);
+            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (lane == 0 && leader) {                   // pair mode: the leader CTA issues for both
             uint32_t ua = 0, bs = 0, tc = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ua++) {
-                const int n_tiles = units[u].n_tiles;
+            auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t accumulate) {
+                if constexpr (PAIR) tc_mma_bf16_pair(d, da, db, TC_IDESC_PAIR, accumulate);
+                else tc_mma_bf16(d, da, db, TC_IDESC, accumulate);
+            };
+            auto commit = [&](uint32_t bar) { if constexpr (PAIR) tc_commit_pair(bar); else tc_commit(bar); };
+            for (int e = worker; e < n_entries; e += n_workers, ua++) {
+                const int n_tiles = units[unit_of(e)].n_tiles;
                 const uint32_t ab = SPLIT ? 0u : (ua & 1);
                 mbar_wait(a_full + 8 * ab, SPLIT ? (ua & 1) : ((ua >> 1) & 1), dbg, 3);
                 const uint32_t sa = smem_base + OFF_A + ab * A_BYTES;
@@ -334,10 +428,10 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                     const uint32_t d_tmem = tmem_base + acc * TILE_N;
                     #pragma unroll 1
                     for (int h = 0; h < N_STAGES_PER_TILE; h++, bs++) {
-                        const uint32_t s = bs % B_STAGES;
-                        mbar_wait(b_full + 8 * s, (bs / B_STAGES) & 1, dbg, 4);
+                        const uint32_t s = bs % NB;
+                        mbar_wait(b_full + 8 * s, (bs / NB) & 1, dbg, 4);
                         tc_fence_after();
-                        const uint32_t sb = smem_base + OFF_B + s * B_ATOM_BYTES;
+                        const uint32_t sb = smem_base + OFF_B + s * STAGE_BYTES;
                         #pragma unroll
                         for (int k = 0; k < 4; k++) {
                             const uint32_t koff = (uint32_t)k * 32u;             // 16 bf16 = 32 B inside the swizzle atom
@@ -348,22 +442,22 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                                 tc_mma_bf16(d_tmem, desc_sw128(sa + kh * A_ATOM_BYTES + koff), db, TC_IDESC, (h | k) ? 1u : 0u);
                                 if (h < 2) tc_mma_bf16(d_tmem, desc_sw128(sa + (2 + kh) * A_ATOM_BYTES + koff), db, TC_IDESC, 1u);
                             } else {
-                                tc_mma_bf16(d_tmem, desc_sw128(sa + h * A_ATOM_BYTES + koff), db, TC_IDESC, (h | k) ? 1u : 0u);
+                                mma(d_tmem, desc_sw128(sa + h * A_ATOM_BYTES + koff), db, (h | k) ? 1u : 0u);
                             }
                         }
-                        tc_commit(b_empty + 8 * s);      // ring stage reusable once these MMAs retire
+                        commit(b_empty + 8 * s);         // ring stage reusable once these MMAs retire
                     }
                     {
-                        const uint32_t g = tc & 1;
-                        mbar_wait(g_full + 8 * g, (tc >> 1) & 1, dbg, 8);
+                        const uint32_t g = tc % NG;
+                        mbar_wait(g_full + 8 * g, (tc / NG) & 1, dbg, 8);
                         tc_fence_after();
-                        tc_mma_bf16(d_tmem, desc_sw32(sa + (SPLIT ? 4 : 2) * A_ATOM_BYTES),
-                                    desc_sw32(smem_base + OFF_BAUG + g * B_AUG_BYTES), TC_IDESC, 1u);
-                        tc_commit(g_empty + 8 * g);
+                        mma(d_tmem, desc_sw32(sa + (SPLIT ? 4 : 2) * A_ATOM_BYTES),
+                            desc_sw32(smem_base + OFF_BAUG + g * G_BYTES), 1u);
+                        commit(g_empty + 8 * g);
                     }
-                    tc_commit(t_full + 8 * acc);         // accumulator ready for the epilogue
+                    commit(t_full + 8 * acc);            // accumulator ready for the epilogue (of both CTAs)
                 }
-                tc_commit(a_empty + 8 * ab);
+                commit(a_empty + 8 * ab);
             }
         }
     } else {
@@ -384,10 +478,13 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
         asm volatile("bar.sync 1, %0;" :: "n"(32 * TC_EPI_WARPS) : "memory");
         if constexpr (KP == 2) {
             uint32_t tc = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const MatchUnit un = units[u];
+            for (int e = worker; e < n_entries; e += n_workers) {
+                const MatchUnit un = units[unit_of(e)];
                 float b1 = -INFINITY, b2 = -INFINITY, f = -INFINITY;
                 int i1 = -1, i2 = -1;
+                // Measured and rejected: two groups of 8 warps taking alternate tiles (128 columns per warp): 1.21 ms instead
+                // of 1.10 ms per 64 pairs — the epilogue is bound by its instruction stream (~250 per warp and tile, four
+                // warps per scheduler), not by the latency of one tile's chain.
                 for (int t = 0; t < un.n_tiles; t++, tc++) {
                     const uint32_t acc = tc & 1;
                     mbar_wait(t_full + 8 * acc, (tc >> 1) & 1, dbg, 6);
@@ -413,13 +510,19 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                         tc_ld32(tbase, ra);                           // two loads in flight before the wait
                         tc_ld32(tbase + 32, rb);
                         tc_wait_ld();
+                        // the warp's 64 columns are in registers: the accumulator goes back to the MMA issuer BEFORE the
+                        // scan, so the next-but-one tile's MMAs overlap it (1.14 -> 1.10 ms per 64 pairs)
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) { if constexpr (PAIR) mbar_arrive_leader(t_empty + 8 * acc); else mbar_arrive(t_empty + 8 * acc); }
                         top2_scan32(ra, col_base, b1, i1, b2, i2, f);
                         top2_scan32(rb, col_base + 32, b1, i1, b2, i2, f);
                         share_store(my_share, b1, b2);
+                    } else {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) { if constexpr (PAIR) mbar_arrive_leader(t_empty + 8 * acc); else mbar_arrive(t_empty + 8 * acc); }
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(t_empty + 8 * acc);
                 }
                 // ---- unit flush: merge the four column parts, convert to distances, write the partial ----
                 share_store(my_share, -INFINITY, -INFINITY);     // reset before the barriers below
@@ -456,8 +559,8 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
             }
         } else {
             uint32_t tc = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const MatchUnit un = units[u];
+            for (int e = worker; e < n_entries; e += n_workers) {
+                const MatchUnit un = units[unit_of(e)];
                 float b[4] = { -INFINITY, -INFINITY, -INFINITY, -INFINITY }, f = -INFINITY;
                 int ix[4] = { -1, -1, -1, -1 };
                 for (int t = 0; t < un.n_tiles; t++, tc++) {
@@ -489,7 +592,7 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(t_empty + 8 * acc);
+                    if (lane == 0) { if constexpr (PAIR) mbar_arrive_leader(t_empty + 8 * acc); else mbar_arrive(t_empty + 8 * acc); }
                 }
                 // ---- unit flush: every column part writes its own candidate record ----
                 share_store(my_share, -INFINITY, -INFINITY);
@@ -502,10 +605,12 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();          // both epilogues are done with TMEM, both producers have seen their tails
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base) : "memory");
+        if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" :: "r"(tmem_base) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem_base) : "memory");
     }
 }
 
@@ -526,9 +631,11 @@ int tc_init(char* err, size_t errlen)
         return 1;
     }
     g_encode = (EncodeTiledFn)fn;
-    e = cudaFuncSetAttribute(match_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+    e = cudaFuncSetAttribute(match_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(match_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+        e = cudaFuncSetAttribute(match_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(match_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
     if (e != cudaSuccess) {
         snprintf(err, errlen, "cudaFuncSetAttribute(match_tc_kernel): %s", cudaGetErrorString(e));
         g_encode = nullptr;
@@ -554,8 +661,18 @@ static int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint32_t co
     return 0;
 }
 
+static bool dbg_print_clusters() { return getenv("CVG_DEBUG") != nullptr; }
+
+bool tc_pair_mode_enabled()
+{
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("CVG_TC_PAIR"); on = e ? (atoi(e) != 0) : 0; }
+    return on != 0;
+}
+
 int launch_match_tc(const TcOperands& op, const MatchUnit* units, int n_units, void* parts, int candidates,
-                    const int* gate_flag, int gate_want, int* dbg, int n_sms, cudaStream_t st, char* err, size_t errlen)
+                    const int* gate_flag, int gate_want, int* dbg, int n_sms, cudaStream_t st, char* err, size_t errlen,
+                    bool paired)
 {
     if (n_units <= 0) return 0;
     if (tc_init(err, errlen)) return 1;
@@ -564,6 +681,8 @@ int launch_match_tc(const TcOperands& op, const MatchUnit* units, int n_units, v
     if (make_map(&maps.qaug, op.Qaug, op.nq_pad, KAUG, KAUG, TILE_M, CU_TENSOR_MAP_SWIZZLE_32B, err, errlen)) return 1;
     if (make_map(&maps.t, op.Tb, op.nt_pad, DIM, 64, TILE_N, CU_TENSOR_MAP_SWIZZLE_128B, err, errlen)) return 1;
     if (make_map(&maps.taug, op.Taug, op.nt_pad, KAUG, KAUG, TILE_N, CU_TENSOR_MAP_SWIZZLE_32B, err, errlen)) return 1;
+    if (make_map(&maps.th, op.Tb, op.nt_pad, DIM, 64, TILE_N / 2, CU_TENSOR_MAP_SWIZZLE_128B, err, errlen)) return 1;
+    if (make_map(&maps.taugh, op.Taug, op.nt_pad, KAUG, KAUG, TILE_N / 2, CU_TENSOR_MAP_SWIZZLE_32B, err, errlen)) return 1;
     maps.qlo = maps.q; maps.tlo = maps.t;
     if (candidates == 4) {
         if (!op.Qlo || !op.Tlo) { snprintf(err, errlen, "candidate path needs the lo operand halves"); return 1; }
@@ -574,9 +693,35 @@ int launch_match_tc(const TcOperands& op, const MatchUnit* units, int n_units, v
     static int exp_mode = -1;
     if (exp_mode < 0) { const char* e = getenv("CVG_TC_EXP"); exp_mode = e ? atoi(e) : 0; }
     if (candidates == 4)
-        match_tc_kernel<4><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, op.qnorm, units, n_units, parts, gate_flag, gate_want, dbg, exp_mode);
-    else
-        match_tc_kernel<2><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, op.qnorm, units, n_units, parts, gate_flag, gate_want, dbg, exp_mode);
+        match_tc_kernel<4, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, op.qnorm, units, n_units, parts, gate_flag, gate_want, dbg, exp_mode);
+    else if (paired && (n_units % 2) == 0 && n_sms >= 2) {
+        // clusters of two CTAs (cta_group::2): consecutive units (2p, 2p + 1) share their train tiles
+        const int n_pairs = n_units / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * (n_sms / 2))); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = TC_SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        // The persistent loop deals entries to clusters statically, so every cluster of the grid must be resident at once:
+        // a GPC with an odd number of free SMs leaves one without a partner, and a second wave would double the time.
+        static int max_clusters = -1;
+        if (max_clusters < 0) {
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, match_tc_kernel<2, true>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = n_sms / 2; }
+            max_clusters = n < n_sms / 2 ? n : n_sms / 2;
+            if (getenv("CVG_TC_PAIR_CLUSTERS")) max_clusters = atoi(getenv("CVG_TC_PAIR_CLUSTERS"));
+            if (dbg_print_clusters()) fprintf(stderr, "cvgraft: match pair mode runs %d clusters of 2 CTAs (%d SMs)\n", max_clusters, n_sms);
+        }
+        const int clusters = n_pairs < max_clusters ? n_pairs : max_clusters;
+        cfg.gridDim = dim3((unsigned)(2 * clusters));
+        cudaError_t le = cudaLaunchKernelEx(&cfg, match_tc_kernel<2, true>, maps, op.qnorm, units, n_units, parts, gate_flag, gate_want, dbg, exp_mode);
+        if (le != cudaSuccess) {
+            snprintf(err, errlen, "match_tc_kernel (pair mode) launch: %s", cudaGetErrorString(le));
+            return 1;
+        }
+    } else
+        match_tc_kernel<2, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, op.qnorm, units, n_units, parts, gate_flag, gate_want, dbg, exp_mode);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(err, errlen, "match_tc_kernel launch: %s", cudaGetErrorString(e));

@@ -60,6 +60,9 @@ enum {
 
 /* cvg_create flags */
 #define CVG_FORCE_EXACT_MATCH 1u    /* always use the fp32 SIMT match kernel (debug / A-B tests)     */
+#define CVG_MATCH_PAIR_MODE   2u    /* exact tensor-core match as clusters of two CTAs (tcgen05      */
+                                    /* cta_group::2, M = 256): same results; measured slower than    */
+                                    /* the one-CTA form on B200, kept for A-B runs   */
 
 typedef struct cvg_ctx cvg_ctx;
 typedef struct cvg_models cvg_models;   /* resident model-view descriptor set                        */

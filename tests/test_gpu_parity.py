@@ -128,6 +128,25 @@ def test_match_both_paths_agree(ctx, ctx_exact, api):
         assert np.array_equal(x, y)
 
 
+def test_match_pair_mode_cta_group_2(api, oracle):
+    """The cta_group::2 form of the match kernel (clusters of two CTAs, one M256 N256 MMA on two query tiles, each CTA
+    holding half of every train stage; opt-in, CVG_MATCH_PAIR_MODE) gives the one-CTA form's results bit for bit:
+    even number of query row blocks -> pairs; odd -> the one-CTA kernel serves the call."""
+    rng = np.random.default_rng(4242)
+    with api.Context(0, api.MATCH_PAIR_MODE) as cp, api.Context(0) as c1:
+        for nq, nt in ((512, 3000), (1024, 700), (256, 255), (2048, 8192), (384, 1000)):
+            q = synth.sift_like(rng, nq); t = synth.sift_like(rng, nt)
+            t[rng.permutation(nt)[: nt // 3]] = q[rng.integers(0, nq, size=nt // 3)]       # exact duplicates: ties
+            a = cp.match_knn2(q, t); b = c1.match_knn2(q, t)
+            assert cp.last_match_path == api.PATH_TENSOR
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y), (nq, nt)
+        q = synth.sift_like(rng, 640); t = synth.sift_like(rng, 2100)
+        oi, od = oracle.knn2(q, t, nthreads=4)
+        i, d, acc = cp.match_knn2(q, t)
+        assert np.array_equal(i, oi) and np.array_equal(d, od) and np.array_equal(acc, oracle.ratio(oi, od))
+
+
 def test_match_tiny_train_sets(ctx, gsynth):
     q, t = gsynth["knn_int_q"][:9], gsynth["knn_int_t"]
     for nt in (1, 2):
