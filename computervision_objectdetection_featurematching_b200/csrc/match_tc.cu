@@ -16,6 +16,12 @@
 //                                load), running top-2 per row kept in registers across the unit, four
 //                                warps per TMEM lane quarter (64 columns each), merged at unit end
 // Pipelines: a_full/a_empty, b_full/b_empty (TMA <-> MMA), t_full/t_empty (MMA <-> epilogue).
+//
+// Pair mode (template PAIR, opt-in: CVG_MATCH_PAIR_MODE): the same kernel as clusters of two CTAs around
+// tcgen05.mma.cta_group::2 (M256 N256 K16): each CTA holds its own query tile and half of every train stage, TMA loads
+// are counted on the leader CTA's barriers, the leader issues the MMAs and multicasts its commits to both CTAs, both
+// epilogues scan their own TMEM and arrive on the leader's barrier.  Bit-equal results; measured slower on B200
+// (DESIGN.md 4.1), so the one-CTA form stays the default.
 #include "common.cuh"
 #include <cuda.h>
 #include <string.h>

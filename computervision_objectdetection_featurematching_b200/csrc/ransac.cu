@@ -10,15 +10,18 @@
 //                        per-call seed is a constant table in HBM, so the attempt starting at any draw
 //                        position p can be evaluated independently; a block evaluates a window of 2048
 //                        positions in parallel and recovers the chain p -> p + consumed(p) by pointer jumping.
-//   2. hypothesis kernel — 4-point normalised DLT (9x9 Jacobi, fp64, no FMA) + fp32 scoring of all
-//                        correspondences, in rounds sized to one full wave.  ransac_hyp_t_kernel (default): one
-//                        hypothesis per thread, matrix state element-major in shared memory (jacobi_thread.cuh),
-//                        scoring from correspondences staged in the same shared memory.  Bit-identical variants
-//                        for few hypotheses / A-B runs: one warp per hypothesis (jacobi_warp.cuh), four per warp,
-//                        and the generic serial routine (CVG_HYP_MODE = 1, 2, 3).
-//   3. select kernel   — the sequential "good > max(best,3)" / RANSACUpdateNumIters scan, one warp per
+//                        One huge round (no early stop, >= 32768 iterations) is cut into chunks walked by many CTAs
+//                        (1b below: per-chunk entry -> exit maps composed in order).
+//   2. solve kernel    — 4-point normalised DLT (9x9 Jacobi, fp64, no FMA), in rounds sized to one full wave.
+//                        ransac_hyp_t_kernel (default): one hypothesis per thread, matrix state element-major in
+//                        shared memory (jacobi_thread.cuh); it leaves the fp32 model in HBM.  Bit-identical variants
+//                        for few hypotheses / A-B runs that also score: one warp per hypothesis (jacobi_warp.cuh),
+//                        four per warp, and the generic serial routine (CVG_HYP_MODE = 1, 2, 3).
+//   3. score kernel    — ransac_score_kernel: fp32 inlier counting of a round's models at full occupancy, the
+//                        correspondences staged in shared memory, four points per reciprocal range test.
+//   4. select kernel   — the sequential "good > max(best,3)" / RANSACUpdateNumIters scan, one warp per
 //                        set, so the winner is the hypothesis the serial loop would have kept.
-//   4. finish kernel   — winner's inlier mask, DLT refit on the inliers, 9-parameter LM (10 iterations),
+//   5. finish kernel   — winner's inlier mask, DLT refit on the inliers, 9-parameter LM (10 iterations),
 //                        mask recomputed from the refined H.  Sets with <= EXACT_MAX_INLIERS inliers use
 //                        OpenCV's exact summation order (bit-exact H); larger sets use block reductions.
 #include "common.cuh"
