@@ -41,6 +41,10 @@ sys.path.insert(0, ROOT)
 
 from computervision_objectdetection_featurematching_b200 import synth  # noqa: E402
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout when the
+# box sets NCCL_DEBUG), so file descriptor 1 is pointed at stderr for everything but the result line.
+_RESULT_OUT = sys.stdout                 # main() swaps the descriptors; importing this module (tools/) does not
+
 METRIC = "image-pairs/s (BF-L2 kNN + RANSAC H)"
 UNIT = "pairs/s"
 NQ = NT = 8192
@@ -224,7 +228,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
                              "sample": f"{pairs_per_step} pairs per step, knnMatch on {threads} threads, findHomography calls of the step on a {threads}-thread pool"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 def run_cvgraft(args):
@@ -548,7 +552,7 @@ def run_cvgraft(args):
             line["cpu_baseline"] = {"value": n / t_cpu, "unit": UNIT, "cores": threads, "kind": kind,
                                     "sample": f"{n} pairs of the same workload (cv2 knnMatch on {threads} threads, "
                                               f"findHomography calls on a {threads}-thread pool)"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_RESULT_OUT, flush=True)
     for m_, c_ in zip(cmodels, ctxs):
         m_.free(); c_.close()
     if world > 1:
@@ -556,6 +560,10 @@ def run_cvgraft(args):
 
 
 def main():
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
