@@ -1015,7 +1015,7 @@ __device__ void block_sum(double* vals, double* s_part /*[4*K]*/, double* s_out 
     if (threadIdx.x < K) {
         double v = s_part[threadIdx.x];
         #pragma unroll
-        for (int q = 1; q < RS_THREADS / 32; q++) v = v + s_part[q * K + threadIdx.x];
+        for (int q = 1; q < (int)(blockDim.x >> 5); q++) v = v + s_part[q * K + threadIdx.x];
         s_out[threadIdx.x] = v;
     }
     __syncthreads();
@@ -1049,7 +1049,7 @@ __device__ double lm_eval_block(const float4* __restrict__ pts, const int32_t* _
     for (int k = 0; k < 56; k++) acc[k] = 0;
     double rm = 0;
     const bool wantJ = A != nullptr;
-    for (int i = threadIdx.x; i < count; i += RS_THREADS) {
+    for (int i = threadIdx.x; i < count; i += (int)blockDim.x) {
         const float4 q = pts[sel[i]];
         double r0, r1, J0[9], J1[9];
         refine_row(h, q.x, q.y, q.z, q.w, r0, r1, wantJ ? J0 : nullptr, wantJ ? J1 : nullptr);
@@ -1094,7 +1094,7 @@ __device__ double lm_eval_exact(const float4* __restrict__ pts, const int32_t* _
 {
     const int tid = threadIdx.x;
     const int rows = 2 * count;
-    for (int i = tid; i < count; i += RS_THREADS) {
+    for (int i = tid; i < count; i += (int)blockDim.x) {
         const float4 q = pts[sel[i]];
         double r0, r1, J0[9], J1[9];
         refine_row(h, q.x, q.y, q.z, q.w, r0, r1, wantJ ? J0 : nullptr, wantJ ? J1 : nullptr);
@@ -1112,8 +1112,8 @@ __device__ double lm_eval_exact(const float4* __restrict__ pts, const int32_t* _
         double s = 0;
         for (int row = 0; row < rows; row++) s += sh.J[row * 9 + j] * sh.J[row * 9 + k];
         sh.out[tid] = s;
-    } else if (wantJ && tid >= 64 && tid < 73) {          // J^T r entry
-        const int j = tid - 64;
+    } else if (wantJ && tid >= 45 && tid < 54) {          // J^T r entry (56 sums on the first 56 threads: any block of >= 64 works)
+        const int j = tid - 45;
         double s;
         if (rows < 100) {
             double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
@@ -1129,11 +1129,11 @@ __device__ double lm_eval_exact(const float4* __restrict__ pts, const int32_t* _
             for (int k = 0; k < rows; k++) s += sh.J[k * 9 + j] * sh.r[k];
         }
         sh.out[45 + j] = s;
-    } else if (tid == 96) {                               // |r|^2 in cv::norm's order
+    } else if (tid == 54) {                               // |r|^2 in cv::norm's order
         NormL2SqrAcc na; na.init();
         for (int k = 0; k < rows; k++) na.push(sh.r[k]);
         sh.out[54] = na.finish();
-    } else if (tid == 97) {
+    } else if (tid == 55) {
         double rm = 0;
         for (int k = 0; k < rows; k++) { const double q = fabs(sh.r[k]); if (q > rm) rm = q; }
         sh.out[55] = rm;
@@ -1213,7 +1213,7 @@ ransac_finish_kernel(RansacWork w)
     const int tid = threadIdx.x;
 
     auto fail = [&]() {
-        for (int i = tid; i < n; i += RS_THREADS) { mask[i] = 0; if (rmask) rmask[i] = 0; }
+        for (int i = tid; i < n; i += (int)blockDim.x) { mask[i] = 0; if (rmask) rmask[i] = 0; }
         if (tid < 9) Hout[tid] = 0.0;
         if (tid == 0) w.found[set] = 0;
     };
@@ -1257,7 +1257,7 @@ ransac_finish_kernel(RansacWork w)
     #pragma unroll
     for (int i = 0; i < 8; i++) Hf[i] = sh.Hf[i];
     const int lane = tid & 31, wid = tid >> 5;
-    for (int base = 0; base < n; base += RS_THREADS) {       // ordered compaction of inlier indices
+    for (int base = 0; base < n; base += (int)blockDim.x) {   // ordered compaction of inlier indices
         const int i = base + tid;
         bool in = false;
         if (i < n) {
@@ -1273,7 +1273,7 @@ ransac_finish_kernel(RansacWork w)
         for (int k = 0; k < wid; k++) off += sh.warp_cnt[k];
         if (in) sel[off + __popc(bal & ((1u << lane) - 1))] = i;
         __syncthreads();
-        if (tid == 0) { int t = 0; for (int k = 0; k < RS_THREADS / 32; k++) t += sh.warp_cnt[k]; sh.base_cnt += t; }
+        if (tid == 0) { int t = 0; for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += sh.warp_cnt[k]; sh.base_cnt += t; }
         __syncthreads();
     }
     const int n_inl = sh.base_cnt;
@@ -1311,14 +1311,14 @@ ransac_finish_kernel(RansacWork w)
             smx = sh.sums[4]; smy = sh.sums[5]; sMx = sh.sums[6]; sMy = sh.sums[7];
         } else {
             double s[4] = { 0, 0, 0, 0 };
-            for (int i = tid; i < n_inl; i += RS_THREADS) {
+            for (int i = tid; i < n_inl; i += (int)blockDim.x) {
                 const float4 q = pts[sel[i]];
                 s[0] += q.z; s[1] += q.w; s[2] += q.x; s[3] += q.y;
             }
             block_sum<4>(s, sh.part, sh.out);
             cmx = s[0] / n_inl; cmy = s[1] / n_inl; cMx = s[2] / n_inl; cMy = s[3] / n_inl;
             s[0] = s[1] = s[2] = s[3] = 0;
-            for (int i = tid; i < n_inl; i += RS_THREADS) {
+            for (int i = tid; i < n_inl; i += (int)blockDim.x) {
                 const float4 q = pts[sel[i]];
                 s[0] += fabs(q.z - cmx); s[1] += fabs(q.w - cmy); s[2] += fabs(q.x - cMx); s[3] += fabs(q.y - cMy);
             }
@@ -1350,7 +1350,7 @@ ransac_finish_kernel(RansacWork w)
                 double L[45];
                 #pragma unroll
                 for (int k = 0; k < 45; k++) L[k] = 0;
-                for (int i = tid; i < n_inl; i += RS_THREADS) {
+                for (int i = tid; i < n_inl; i += (int)blockDim.x) {
                     const float4 q = pts[sel[i]];
                     const double x = (q.z - cmx) * smx, y = (q.w - cmy) * smy;
                     const double X = (q.x - cMx) * sMx, Y = (q.y - cMy) * sMy;
@@ -1436,12 +1436,12 @@ ransac_finish_kernel(RansacWork w)
         // B.9: returned mask = err(H_final) <= thr^2 over ALL correspondences
         #pragma unroll
         for (int i = 0; i < 8; i++) Hf[i] = (float)sh.H[i];
-        for (int i = tid; i < n; i += RS_THREADS) {
+        for (int i = tid; i < n; i += (int)blockDim.x) {
             const float4 q = pts[i];
             mask[i] = reproj_err(Hf, q.x, q.y, q.z, q.w) <= w.thr2 ? 1 : 0;
         }
     } else {
-        for (int i = tid; i < n; i += RS_THREADS) mask[i] = 0;
+        for (int i = tid; i < n; i += (int)blockDim.x) mask[i] = 0;
     }
     if (tid < 9) Hout[tid] = sh.H[tid];
     if (tid == 0) w.found[set] = 1;
@@ -1513,6 +1513,12 @@ int launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events,
     if (!(w.flags & CVG_RANSAC_NO_EARLY_STOP)) {
         const int64_t wave = (int64_t)n_sms * HYPT_THREADS * HYPT_CTAS_PER_SM;
         int64_t fill = wave / w.n_sets / 32 * 32;              // rounded down: n_sets x round_len must not spill into a second wave
+        if (fill < 256) {
+            // many sets: a round of 256 iterations is several waves; make it a whole number of them (13 350 real pairs in
+            // calls of 445 sets: 288 iterations = 3.9 waves and 7 rounds instead of 256 = 3.4 waves — 4 wave times — and 8)
+            const int64_t k = (256 * (int64_t)w.n_sets + wave - 1) / wave;
+            fill = k * wave / w.n_sets / 32 * 32;
+        }
         round_len = (int)std::min<int64_t>(std::max<int64_t>(256, fill), w.max_iters);
         if (round_env > 0) round_len = std::min(round_env, w.max_iters);
     }
@@ -1573,7 +1579,11 @@ int launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events,
             ransac_select_kernel<<<(w.n_sets + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(w, rb, len);
         launches += 3;
     }
-    ransac_finish_kernel<<<w.n_sets, RS_THREADS, 0, st>>>(w);
+    // Sets of a few dozen correspondences (the real dataset: 445 sets per call, n <= 127) take the exact path, which is
+    // warp 0's serial eigen-solves plus 56 single-thread sums: with 64 threads per CTA four CTAs fit an SM (206 registers)
+    // and the call's sets run in one wave instead of two.  Every loop of the kernel strides by blockDim.x.
+    const int finish_threads = w.max_n <= 512 ? 64 : RS_THREADS;
+    ransac_finish_kernel<<<w.n_sets, finish_threads, 0, st>>>(w);
     return launches;
 }
 
