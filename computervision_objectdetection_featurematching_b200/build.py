@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libcvgraft.so")
 SOURCES = ["api.cu", "prep.cu", "match_exact.cu", "match_tc.cu", "ransac.cu"]
-HEADERS = ["common.cuh", "homography_math.cuh", "jacobi_warp.cuh", os.path.join("..", "..", "include", "cvgraft.h")]
+HEADERS = ["common.cuh", "homography_math.cuh", "jacobi_warp.cuh", "jacobi_thread.cuh", os.path.join("..", "..", "include", "cvgraft.h")]
 # -fmad=false: the verify stage and the exact match kernel must not contract a*b+c (OpenCV's baseline
 # build has no FMA); the few fused operations OpenCV does perform are explicit fma() calls.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-fmad=false", "-lineinfo",
