@@ -574,7 +574,7 @@ static int run_ransac(cvg_ctx* c, const float4* d_pts, const int64_t* d_starts, 
     w.chunk_outs = nullptr; w.chunk_lists = nullptr; w.chunk_offsets = nullptr; w.chunk_serial = nullptr; w.n_chunks = 0;
     w.chunk_maps = nullptr; w.chunk_entries = nullptr; w.chunk_serial_count = nullptr;
     c->last_chunked = false;
-    if ((p->flags & CVG_RANSAC_NO_EARLY_STOP) && mi >= 32768) {
+    if ((p->flags & CVG_RANSAC_NO_EARLY_STOP) && mi >= 32768 && n_sets <= 65535) {     // sets ride on gridDim.y of the chunk kernels
         // one huge round: the draw stream of every set is walked by many CTAs at once (ransac_sample_chunk_kernel)
         const int n_chunks = ransac_chunks_for_table(c->rng_len);
         size_t o_outs, o_lists, o_off, o_ser, o_maps, o_ent;

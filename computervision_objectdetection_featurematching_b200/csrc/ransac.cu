@@ -870,11 +870,11 @@ ransac_hyp_t_kernel(RansacWork w, int round_base, int round_len)
 constexpr int SCORE_THREADS = 256;
 constexpr int SCORE_STAGE = 2048;
 __global__ void __launch_bounds__(SCORE_THREADS)
-ransac_score_kernel(RansacWork w, int round_base, int round_len, int n_slices)
+ransac_score_kernel(RansacWork w, int round_base, int round_len, int n_slices, int tiles)
 {
     __shared__ float4 stage[SCORE_STAGE];
-    const int set = blockIdx.y;
-    const int r = blockIdx.x * SCORE_THREADS + threadIdx.x;
+    const int set = (int)(blockIdx.x / (unsigned)tiles);         // sets on x: no 65535 limit on their number
+    const int r = (int)(blockIdx.x % (unsigned)tiles) * SCORE_THREADS + threadIdx.x;
     const int iter = round_base + r;
     const int n = w.counts_n[set];
     const size_t slot = (size_t)set * w.max_iters + iter;
@@ -1569,7 +1569,7 @@ int launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events,
             const int64_t ctas = (int64_t)tiles * w.n_sets;
             int n_slices = (int)std::min<int64_t>(std::max<int64_t>(1, ((int64_t)n_sms * 6 + ctas - 1) / ctas), std::max(1, w.max_n / 512));
             n_slices = std::max(1, std::min(n_slices, 64));
-            ransac_score_kernel<<<dim3((unsigned)tiles, (unsigned)w.n_sets, (unsigned)n_slices), SCORE_THREADS, 0, st>>>(w, rb, len, n_slices);
+            ransac_score_kernel<<<dim3((unsigned)ctas, 1, (unsigned)n_slices), SCORE_THREADS, 0, st>>>(w, rb, len, n_slices, tiles);
             launches += 1;
         }
         if (timed) cudaEventRecord(hyp_events[32 + round], st);

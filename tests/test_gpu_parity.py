@@ -343,6 +343,28 @@ def test_find_homography_batch_shapes_thread_kernel(ctx, api, oracle):
                 assert np.allclose(out["H"][k], ref["H"], rtol=1e-9, atol=1e-12), (case["max_iters"], k, n)
 
 
+def test_find_homography_batch_more_sets_than_a_grid_dimension(ctx, oracle):
+    """70 000 sets in one call (more than gridDim.y can hold): every kernel of the verify stage indexes sets on x.  The
+    same 40 correspondence sets repeated; every copy must give the first copy's result, the first 40 the oracle's."""
+    rng = np.random.default_rng(9090)
+    base = [synth.correspondences(rng, int(n), 0.6)[:2] for n in rng.integers(6, 14, size=40)]
+    reps = 1750
+    srcs = [b[0] for b in base] * reps; dsts = [b[1] for b in base] * reps
+    offs = np.concatenate([[0], np.cumsum([len(s) for s in srcs])])
+    out = ctx.find_homography_batch(np.concatenate(srcs), np.concatenate(dsts), offs, max_iters=300)
+    per = offs[40]
+    m0 = out["mask"][:per]
+    assert np.array_equal(out["mask"].reshape(reps, per), np.broadcast_to(m0, (reps, per)))
+    assert np.array_equal(out["H"].reshape(reps, 40, 9), np.broadcast_to(out["H"][:40].reshape(40, 9), (reps, 40, 9)))
+    assert np.array_equal(out["found"].reshape(reps, 40), np.broadcast_to(out["found"][:40], (reps, 40)))
+    for k in range(40):
+        ref = oracle.find_homography(base[k][0], base[k][1], max_iters=300)
+        assert out["found"][k] == ref["found"], k
+        if ref["found"]:
+            assert np.array_equal(out["mask"][offs[k]:offs[k + 1]], ref["mask"]), k
+            assert np.allclose(out["H"][k], ref["H"], rtol=1e-9, atol=1e-12), k
+
+
 def test_selftest_reciprocal_exhaustive(ctx):
     """The scoring kernel's hand-written reciprocal (MUFU.RCP + one Newton step, four at a time behind one range test)
     against __frcp_rn and 1.f / x on every float with 2^-126 <= |x| < 2^126: 0 mismatches of 2 x 4.2e9 comparisons."""
