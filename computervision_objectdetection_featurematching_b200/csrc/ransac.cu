@@ -828,7 +828,12 @@ ransac_hyp_t_kernel(RansacWork w, int round_base, int round_len)
             dst[0] = make_float4(Hf[0], Hf[1], Hf[2], Hf[3]);
             dst[1] = make_float4(Hf[4], Hf[5], Hf[6], Hf[7]);
             w.counts[(size_t)set * w.max_iters + iter] = valid ? 0 : -1;
-            if (w.scored_pts && valid) atomicAdd(w.scored_pts, (unsigned long long)n);
+        }
+        if (w.scored_pts) {                                  // statistics (timing enabled only): one atomic per warp, not per thread
+            unsigned long long v = (live && valid) ? (unsigned long long)n : 0ull;
+            #pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0 && v) atomicAdd(w.scored_pts, v);
         }
         return;
     }
