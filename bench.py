@@ -7,17 +7,22 @@ descriptors is matched against B scene descriptor sets of 8192 rows each and eac
 verified with a 2000-iteration RANSAC homography — BASELINE config 3 (8k x 8k + 2000-iter RANSAC), batched
 the way the reference batches it (one model view vs. many test images, src/TestsDetector.cpp:58).
 
-  value : pairs/s with the scene sets already resident in HBM (cvg_detect_scenes), whole job over N GPUs; C contexts
-          per GPU on C host threads (the library's concurrency model), so that one batch's latency-bound refit/LM
-          kernel overlaps the other batches' match and hypothesis kernels; value_single_context = one context
-  e2e   : pairs/s through the public host-buffer API: every step uploads its B scene sets from pinned
-          host memory (cvg_scenes_upload_async, step k+1's upload overlapping step k's compute), runs
-          cvg_detect_scenes and reads the per-pair results back
+ONE context per GPU, driven by ONE host thread, in every number below.
+
+  value : pairs/s with the scene sets already resident in HBM, whole job over N GPUs; the thread keeps `--depth` calls in
+          flight (cvg_detect_scenes_submit / cvg_job_wait), so that one call's latency-bound refit/LM kernel runs under the
+          next calls' match and hypothesis kernels.  value_single_context = synchronous calls back to back (each split over
+          the context's lanes); value_serial = one lane, every kernel alone on the GPU (timed region of the rooflines)
+  e2e   : pairs/s through the public host-buffer API: every step uploads its B scene sets from pinned host memory
+          (cvg_scenes_upload_async), runs the fused call and reads back the per-pair results AND the inlier scene points
   roofline : the tcgen05 match kernel, the largest kernel of the step that has a roofline (2*Nq*Nt*128 flop per pair
-             against the measured cuBLAS bf16 rate); roofline_score: the inlier-counting kernel, 16 B per scored
-             (hypothesis, correspondence) against the HBM copy bandwidth; solve_stage: the 4-point DLT kernel (fp64 Jacobi,
-             latency-bound, hypotheses/s) — all from CUDA events around the kernels inside the timed steps
+             against the measured burst cuBLAS bf16 rate); roofline_score: the inlier-counting kernel against the fp32 issue
+             rate (its SURVEY-8d HBM figure is kept as algorithmic_gbs); solve_stage: the 4-point DLT kernel (fp64 Jacobi,
+             latency-bound) — all from CUDA events around the kernels inside the serial timed steps
   cpu_baseline : cv2 4.13.0 (the reference's own arithmetic) on this host's cores, bounded sample
+  c4, c5_match (N >= 2 only, outside the timed regions above): BASELINE config 4 (4096 pairs of 4096 x 4096, pair p -> GPU
+             p mod N) and config 5's match (262 144 queries x 131 072 train rows per GPU, train-tile sharded, ONE NCCL
+             all-gather + top-2 merge), each with an inline parity check against the CPU oracle
 
 `--impl reference` times the reference's CPU implementation (cv2 BFMatcher.knnMatch + findHomography, all
 host threads; the C oracle port if cv2 is unavailable) on the same workload, metric and unit.
@@ -206,6 +211,10 @@ def cpu_pairs(q, qk, batch, n_pairs, threads, first=0):
         return time.perf_counter() - t0, "port"
 
 
+WORKLOAD = ("c3: 1 resident model view x 8192 desc vs scenes of 8192 desc (128-D, SIFT-like), ratio 0.9, "
+            "RANSAC 2000 iters thr 5.0 conf 0.995")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -223,12 +232,150 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "c3: 1 model view x 8192 desc vs scenes of 8192 desc, ratio 0.9, RANSAC 2000 iters",
-                       "pairs_per_step": pairs_per_step},
+            "config": {"workload": WORKLOAD, "pairs_per_step": pairs_per_step},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
                              "sample": f"{pairs_per_step} pairs per step, knnMatch on {threads} threads, findHomography calls of the step on a {threads}-thread pool"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=_RESULT_OUT, flush=True)
+
+
+# ---- BASELINE config 5 (match): train-tile sharded kNN with ONE exchange step over NCCL, inline parity ------------------
+def run_c5_match(ctx, dev, rank, world, dist, all_max, barrier):
+    """262 144 queries x (131 072 x world) train rows: every rank holds one train tile (the tile size of SURVEY 8d; the full
+    1 048 576-row set at 8 GPUs) and the replicated queries; local top-2 (cvg_dev_match_top2), all-gather of 16 B per query and
+    rank over NCCL, merge (cvg_dev_merge_top2).  Rank 0 regenerates every tile and checks 512 sampled queries against the
+    CPU oracle over the WHOLE train set (reference src/TestsDetector.cpp:59-72)."""
+    import torch
+    from computervision_objectdetection_featurematching_b200 import sharding
+    NQ, TILE = 262144, 131072
+    NT = TILE * world
+    q = synth.sift_like(np.random.default_rng(5000), NQ)           # replicated queries (same seed everywhere)
+
+    def make_tile(r):
+        rng = np.random.default_rng(5001 + r)
+        t = synth.sift_like(rng, TILE)
+        k = NQ // 16                                               # planted noisy copies of some queries in every tile
+        rq = rng.permutation(NQ)[:k]; rt = rng.permutation(TILE)[:k]
+        t[rt] = np.clip(q[rq] + np.round(rng.normal(0, 12.0, size=(k, 128))).astype(np.float32), 0, 255)
+        return t
+
+    t_mine = make_tile(rank)
+    qd = torch.from_numpy(q).to(dev); td = torch.from_numpy(t_mine).to(dev)
+    base = rank * TILE
+    stream = torch.cuda.current_stream(dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    d_loc = torch.empty((NQ, 2), dtype=torch.float32, device=dev); i_loc = torch.empty((NQ, 2), dtype=torch.int32, device=dev)
+    d_all = torch.empty((world, NQ, 2), dtype=torch.float32, device=dev); i_all = torch.empty((world, NQ, 2), dtype=torch.int32, device=dev)
+    idx = torch.empty((NQ, 2), dtype=torch.int32, device=dev); dd = torch.empty((NQ, 2), dtype=torch.float32, device=dev)
+    acc = torch.empty((NQ,), dtype=torch.uint8, device=dev)
+
+    def once():
+        ev[0].record(stream)
+        ctx.dev_match_top2(qd.data_ptr(), NQ, td.data_ptr(), TILE, base, d_loc.data_ptr(), i_loc.data_ptr(), stream=stream.cuda_stream)
+        ev[1].record(stream)
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_loc)               # the one exchange step of the path
+            dist.all_gather_into_tensor(i_all, i_loc)
+        else:
+            d_all[0].copy_(d_loc); i_all[0].copy_(i_loc)
+        ev[2].record(stream)
+        ctx.dev_merge_top2(d_all.data_ptr(), i_all.data_ptr(), world, NQ, 0.9, idx.data_ptr(), dd.data_ptr(), acc.data_ptr(),
+                           stream=stream.cuda_stream)
+        ev[3].record(stream)
+        ev[3].synchronize()
+        return ev[0].elapsed_time(ev[3]), ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])
+
+    for _ in range(3):
+        once()
+    barrier()
+    reps = [once() for _ in range(5)]
+    ms = all_max(min(r[0] for r in reps))
+    best = min(reps, key=lambda r: r[0])
+    out = {"nq": NQ, "nt": NT, "tile_rows_per_gpu": TILE, "ms": ms, "match_pflops": 2.0 * NQ * NT * 128 / (ms * 1e-3) / 1e15,
+           "local_match_ms": all_max(best[1]), "all_gather_us": 1e3 * all_max(best[2]), "merge_us": 1e3 * all_max(best[3]),
+           "all_gather_share": best[2] / best[0],
+           "bytes_gathered_per_gpu": int(16 * NQ * world), "accepted": int(acc.sum().item()),
+           "note": "weak form of BASELINE config 5: 131 072 train rows per GPU (the full 262 144 x 1 048 576 at 8 GPUs); timed region = "
+                   "operand prep + local top-2 + NCCL all-gather + merge, best of 5 after 3 warm-ups, max over ranks"}
+    if rank == 0:
+        from oracle import cvoracle as o
+        t0 = time.time()
+        t_all = np.concatenate([t_mine] + [make_tile(r) for r in range(1, world)])
+        rows = np.random.default_rng(5999).permutation(NQ)[:512]
+        oi, od = o.knn2(q[rows], t_all, nthreads=os.cpu_count())
+        gi = idx.cpu().numpy()[rows]; gd = dd.cpu().numpy()[rows]; ga = acc.cpu().numpy()[rows]
+        out["checked_queries"] = 512
+        out["parity"] = bool(np.array_equal(gi, oi) and np.array_equal(gd, od) and np.array_equal(ga, o.ratio(oi, od)))
+        out["oracle_s"] = time.time() - t0
+    del qd, td, d_all, i_all
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---- BASELINE config 4: 4096 pairs of 4096 x 4096, pair p -> GPU p mod N, no data-path collective ------------------------
+def run_c4(ctx, api, dev, rank, world, all_max, barrier):
+    import torch
+    N4, B, POOL = 4096, 64, 2
+    n_pairs = 4096
+    rngq = np.random.default_rng(4000)
+    q = synth.sift_like(rngq, N4); qk = rngq.uniform([0, 0], [640, 480], size=(N4, 2)).astype(np.float32)
+    models = ctx.upload_models(q, qk, [0, N4], [0])
+
+    def make_pair(p):
+        """Scene p: planted copies of half the view's descriptors, 30 % of them on a homography."""
+        rng = np.random.default_rng(4001 + p)
+        t = synth.sift_like(rng, N4); tk = rng.uniform([0, 0], [640, 480], size=(N4, 2)).astype(np.float32)
+        k = N4 // 2
+        rq = rng.permutation(N4)[:k]; rt = rng.permutation(N4)[:k]
+        t[rt] = np.clip(q[rq] + np.round(rng.normal(0, 12.0, size=(k, 128))).astype(np.float32), 0, 255)
+        H = synth.random_homography(rng)
+        geo = rng.random(k) < 0.3
+        pp = np.c_[qk[rq[geo]], np.ones(int(geo.sum()))] @ H.T
+        tk[rt[geo]] = (pp[:, :2] / pp[:, 2:3] + rng.normal(0, 0.7, size=(int(geo.sum()), 2))).astype(np.float32)
+        return t, tk
+
+    mine = list(range(rank, n_pairs, world))                      # pair p -> GPU p mod N (SURVEY 8d)
+    pool = []
+    for b in range(POOL):                                         # POOL x B distinct scenes per rank, cycled over its pairs
+        ps = mine[b * B:(b + 1) * B]
+        ts, ks = zip(*[make_pair(p) for p in ps])
+        pool.append(ctx.upload_scenes(np.concatenate(ts), np.concatenate(ks), np.arange(B + 1, dtype=np.int64) * N4))
+    steps = len(mine) // B
+    first = ctx.detect_scenes_inliers(models, pool[0])[0].copy()
+    barrier()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    jobs = []; accepted = 0
+    for s in range(steps):                                         # one host thread, three calls in flight
+        jobs.append(ctx.submit_scenes(models, pool[s % POOL]))
+        if len(jobs) == 3:
+            accepted += int((jobs.pop(0).wait()[0]["status"] == 0).sum())
+    for j in jobs:
+        accepted += int((j.wait()[0]["status"] == 0).sum())
+    e1.record(stream); e1.synchronize()
+    ms = all_max(e0.elapsed_time(e1))
+    out = {"pairs": steps * B * world, "nq": N4, "nt": N4, "ms": ms, "pairs_per_s": steps * B * world / (ms * 1e-3),
+           "match_tflops_equiv": 2.0 * N4 * N4 * 128 * steps * B * world / (ms * 1e-3) / 1e12, "accepted_rank0": accepted,
+           "note": f"pair p -> GPU p mod N; every rank cycles {POOL * B} distinct resident scenes over its {steps * B} pairs; "
+                   "kNN + ratio + 2000-iteration RANSAC + refit per pair, inlier points returned; no data-path collective"}
+    if rank == 0:
+        from oracle import cvoracle as o
+        ok = True
+        for j in range(2):
+            t, tk = make_pair(mine[j])
+            oi, od = o.knn2(q, t, nthreads=os.cpu_count()); oa = o.ratio(oi, od).astype(bool)
+            ref = o.find_homography(qk[oa], tk[oi[oa, 0]])
+            r = first[j, 0]
+            ok = ok and int(r["n_good"]) == int(oa.sum()) and (int(r["status"]) != api.H_EMPTY) == ref["found"] \
+                and int(r["ransac_iters"]) == ref["info"]["iters_run"] \
+                and (not ref["found"] or abs(int(r["n_inliers"]) - int(ref["mask"].sum())) <= 2)
+        out["parity"] = bool(ok)
+        out["parity_note"] = "first 2 pairs of rank 0 against the CPU oracle: matches kept, H found, RANSAC iterations, inlier count (<= 2 flips above 128 inliers)"
+    for sc in pool:
+        sc.free()
+    models.free()
+    return out
 
 
 def run_cvgraft(args):
@@ -241,18 +388,18 @@ def run_cvgraft(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libcvgraft has no CPU fallback")
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     all_cpus = os.sched_getaffinity(0)
     numa = bind_to_gpu_numa_node(torch.cuda.get_device_properties(local))
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    B, R = args.pairs, args.batches
+        dist.init_process_group("nccl", device_id=dev)
+    B, R, DEPTH = args.pairs, args.batches, max(1, args.depth)
     clocks = ClockSampler(local); clocks.start()
     q, qk, batches = make_workload(3000 + rank, B, R, args.desc)
-    ctx = api.Context(local)
-    ctx.set_timing(True)
+    ctx = api.Context(local)                             # ONE context, driven by this one host thread
     models = ctx.upload_models(q, qk, [0, NQ], [0])
     params = api.detect_params()
-    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     def barrier():
         torch.cuda.synchronize()
@@ -260,127 +407,111 @@ def run_cvgraft(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        """K steps bracketed by barrier + synchronize, device time by CUDA events on the context's stream."""
+    def all_max(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def timed(loop, steps):
+        """K steps bracketed by barrier + synchronize; device time between two CUDA events on the context's stream: the
+        first is recorded on the idle GPU before the first call, the second after the last call's results are on the host
+        (every call / job wait returns only when its GPU work is complete, whichever internal stream ran it)."""
         barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for k in range(steps):
-            fn(k)
+        loop(steps)
         e1.record(stream)
         e1.synchronize()
         ms = e0.elapsed_time(e1)
         barrier()
-        if world > 1:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return all_max(ms)
 
-    # ---- value: scene sets resident in HBM --------------------------------------------------------
     resident = [ctx.upload_scenes(d, k, o) for d, k, o in batches]
-    match_ms, ransac_ms, hyp_ms, hyp_launches, scored, accepted = [], [], [], [], [], 0
-    score_ms = []
 
-    def step_resident(k):
-        nonlocal accepted
-        res = ctx.detect_scenes(models, resident[k % R], params=params)
-        t = ctx.last_timing()
-        match_ms.append(t["match_ms"]); ransac_ms.append(t["ransac_ms"])
-        hyp_ms.append(t["hyp_ms"]); hyp_launches.append(t["hyp_launches"]); scored.append(t["scored_points"])
-        score_ms.append(t["score_ms"])
-        accepted += int((res["status"] == 0).sum())
+    # ---- phase 1: strictly serial (one lane), kernels alone — the timed region the rooflines are computed from ----------
+    ctx.set_lanes(1); ctx.set_timing(True)
+    match_ms, ransac_ms, hyp_ms, hyp_launches, scored, score_ms = [], [], [], [], [], []
 
-    # Phase 1 — ONE context, calls back to back (every call synchronous): the kernels run alone, so the CUDA-event
-    # durations of this timed region are what the rooflines below are computed from.
-    for k in range(args.warmup):
-        step_resident(k)
-    match_ms.clear(); ransac_ms.clear(); hyp_ms.clear(); hyp_launches.clear(); scored.clear(); accepted = 0
-    score_ms.clear()
-    ms_single = timed(step_resident, args.steps)
-    value_single = world * B * args.steps / (ms_single * 1e-3)
+    def loop_serial(steps, record=True):
+        for k in range(steps):
+            ctx.detect_scenes(models, resident[k % R], params=params)
+            if record:
+                t = ctx.last_timing()
+                match_ms.append(t["match_ms"]); ransac_ms.append(t["ransac_ms"]); hyp_ms.append(t["hyp_ms"])
+                hyp_launches.append(t["hyp_launches"]); scored.append(t["scored_points"]); score_ms.append(t["score_ms"])
 
-    # Phase 2 (headline) — C contexts on C host threads, the library's concurrency model (a context is not re-entrant;
-    # callers wanting concurrency create one per thread, include/cvgraft.h): the GPU overlaps one batch's latency-bound
-    # refit/LM kernel with the other batches' match and hypothesis kernels.  K steps in total, one step = one batch.
-    import threading
-    C = max(1, args.contexts)
-    ctxs = [ctx] + [api.Context(local) for _ in range(C - 1)]
-    cmodels = [models] + [c.upload_models(q, qk, [0, NQ], [0]) for c in ctxs[1:]]
-    cres = [resident] + [[c.upload_scenes(d, k, o) for d, k, o in batches] for c in ctxs[1:]]
-    cstreams = [torch.cuda.ExternalStream(c.stream, device=torch.device("cuda", local)) for c in ctxs]
+    loop_serial(args.warmup, record=False)
+    ms_serial = timed(loop_serial, args.steps)
     ctx.set_timing(False)
-    acc_multi = [0] * C
 
-    def run_multi(step_fn, steps):
-        """steps in total, dealt round-robin to the C contexts; device time from the first start to the last end."""
-        per = [steps // C + (1 if i < steps % C else 0) for i in range(C)]
-        barrier()
-        e0 = torch.cuda.Event(enable_timing=True); e0.record(cstreams[0])
-        ends = [torch.cuda.Event(enable_timing=True) for _ in range(C)]
+    # ---- phase 2: synchronous calls, each split over the context's lanes (what a caller of the blocking API gets) -------
+    ctx.set_lanes(0)
 
-        def work(i):
-            torch.cuda.set_device(local)
-            for k in range(per[i]):
-                step_fn(i, k, per[i])
-            ends[i].record(cstreams[i])
-        th = [threading.Thread(target=work, args=(i,)) for i in range(C)]
-        [t.start() for t in th]; [t.join() for t in th]
-        for e in ends:
-            e.synchronize()
-        ms = max(e0.elapsed_time(e) for e in ends)
-        barrier()
-        if world > 1:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+    def loop_sync(steps):
+        for k in range(steps):
+            ctx.detect_scenes(models, resident[k % R], params=params)
 
-    def step_resident_multi(i, k, last):
-        res = ctxs[i].detect_scenes(cmodels[i], cres[i][k % R], params=params)
-        acc_multi[i] += int((res["status"] == 0).sum())
+    loop_sync(args.warmup)
+    ms_sync = timed(loop_sync, args.steps)
+
+    # ---- phase 3 (headline `value`): the same thread keeps DEPTH calls in flight (cvg_detect_scenes_submit / cvg_job_wait)
+    accepted = 0
+
+    def loop_pipe(steps):
+        nonlocal accepted
+        jobs = []
+        for k in range(steps):
+            jobs.append(ctx.submit_scenes(models, resident[k % R], params=params, want_inliers=False))
+            if len(jobs) > DEPTH - 1:
+                accepted += int((jobs.pop(0).wait()[0]["status"] == 0).sum())
+        for j in jobs:
+            accepted += int((j.wait()[0]["status"] == 0).sum())
 
     tw0 = time.time()                                  # clock samples: from the warm-up on (the timed region is short)
-    run_multi(step_resident_multi, max(C, args.warmup))
-    acc_multi = [0] * C
-    l0 = sum(c.launch_count for c in ctxs)
-    ms_total = run_multi(step_resident_multi, args.steps)
-    launches = sum(c.launch_count for c in ctxs) - l0
+    loop_pipe(max(args.warmup, DEPTH))
+    accepted = 0
+    l0 = ctx.launch_count
+    ms_total = timed(loop_pipe, args.steps)
+    launches = ctx.launch_count - l0
     clocks.mark(tw0, time.time())
     value = world * B * args.steps / (ms_total * 1e-3)
-    accepted_multi = sum(acc_multi)
-    for rs in cres:
-        for sc in rs:
-            sc.free()
+    for sc in resident:
+        sc.free()
 
-    # ---- e2e: host buffers in, results out, every step -------------------------------------------
+    # ---- e2e: host buffers in; per-pair results, inlier masks' points and offsets out, every step -----------------------
     pinned = []
     for d, k, o in batches:
         pd = torch.from_numpy(d).pin_memory(); pk = torch.from_numpy(k).pin_memory()
         pinned.append((pd.numpy(), pk.numpy(), o, pd, pk))
     h2d = int(batches[0][0].nbytes + batches[0][1].nbytes + batches[0][2].nbytes)
-    d2h = int(B * api.PAIR_DTYPE.itemsize)
+    d2h_seen = []
 
-    # Streaming caller (the reference walks a list of test images, src/Output.cpp:27-47): the upload of step k+1 is
-    # enqueued on the context's copy stream before step k is run, so copy and compute overlap.  Every step's inputs
-    # cross PCIe inside the timed region (the first upload is not overlapped) and every step's results come back.
-    inflight = [dict() for _ in range(C)]
+    def loop_e2e_with(upload):
+        """Streaming caller (the reference walks a list of test images, src/Output.cpp:27-47): every step's inputs cross PCIe
+        inside the timed region (upload of step k+1.. enqueued while step k computes), and every step's per-pair results
+        AND inlier points (what src/TestsDetector.cpp:87-94 hands to the consumer) come back to the host."""
+        def loop(steps):
+            inflight = []
+            for k in range(steps):
+                sc = upload(k % R)
+                inflight.append((sc, ctx.submit_scenes(models, sc, params=params, want_inliers=True)))
+                if len(inflight) > DEPTH - 1:
+                    sc0, j0 = inflight.pop(0)
+                    res, xy, off = j0.wait(); sc0.free()
+                    d2h_seen.append(res.nbytes + xy.nbytes + off.nbytes)
+            for sc0, j0 in inflight:
+                res, xy, off = j0.wait(); sc0.free()
+                d2h_seen.append(res.nbytes + xy.nbytes + off.nbytes)
+        return loop
 
-    def step_e2e(i, k, last):
-        c = ctxs[i]; fl = inflight[i]
-        if k not in fl:
-            d, kk, o, _, _ = pinned[(k * C + i) % R]
-            fl[k] = c.upload_scenes_async(d, kk, o)
-        if k + 1 < last:
-            d, kk, o, _, _ = pinned[((k + 1) * C + i) % R]
-            fl[k + 1] = c.upload_scenes_async(d, kk, o)
-        sc = fl.pop(k)
-        c.detect_scenes(cmodels[i], sc, params=params)
-        sc.free()
-
+    loop_e2e = loop_e2e_with(lambda j: ctx.upload_scenes_async(pinned[j][0], pinned[j][1], pinned[j][2]))
     tw0 = time.time()
-    run_multi(step_e2e, max(2 * C, args.warmup))
-    ms_e2e = run_multi(step_e2e, args.steps)
+    loop_e2e(max(args.warmup, 2 * DEPTH))
+    d2h_seen.clear()
+    ms_e2e = timed(loop_e2e, args.steps)
+    d2h = int(statistics.mean(d2h_seen))
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
     clocks.mark(tw0, time.time())
     clk = clocks.stop()
@@ -392,31 +523,37 @@ def run_cvgraft(args):
         for d, k, o in batches:
             p8 = torch.from_numpy(d.astype(np.uint8)).pin_memory()
             pinned8.append((p8.numpy(), p8))
-        for fl in inflight:
-            fl.clear()
-
-        def step_u8(i, k, last):
-            c = ctxs[i]; fl = inflight[i]
-            if k not in fl:
-                j = (k * C + i) % R
-                fl[k] = c.upload_scenes_u8_async(pinned8[j][0], pinned[j][1], pinned[j][2])
-            if k + 1 < last:
-                j = ((k + 1) * C + i) % R
-                fl[k + 1] = c.upload_scenes_u8_async(pinned8[j][0], pinned[j][1], pinned[j][2])
-            sc = fl.pop(k)
-            c.detect_scenes(cmodels[i], sc, params=params)
-            sc.free()
-
-        run_multi(step_u8, max(2 * C, args.warmup))
-        ms_u8 = run_multi(step_u8, args.steps)
+        loop_u8 = loop_e2e_with(lambda j: ctx.upload_scenes_u8_async(pinned8[j][0], pinned[j][1], pinned[j][2]))
+        loop_u8(max(args.warmup, 2 * DEPTH))
+        ms_u8 = timed(loop_u8, args.steps)
         e2e_u8 = {"value": world * B * args.steps / (ms_u8 * 1e-3), "unit": UNIT, "ms_per_step": ms_u8 / args.steps,
                   "h2d_bytes_per_step": int(batches[0][0].size + batches[0][1].nbytes + batches[0][2].nbytes),
                   "note": "uint8 descriptor rows in pinned host memory (cvg_scenes_upload_u8_async); not the headline"}
 
+    # ---- single 8k x 8k pair: the match kernel's launch alone (SURVEY 8d target: <= 20.8 us) -----------------------------
+    single_pair_us = None
+    if not args.no_extras:
+        d, k, o = batches[0]
+        one = ctx.upload_scenes(d[:NT], k[:NT], o[:2])
+        ctx.set_lanes(1); ctx.set_timing(True)
+        ts = []
+        for _ in range(6):
+            ctx.detect_scenes(models, one, params=params)
+            ts.append(ctx.last_timing()["match_ms"])
+        ctx.set_timing(False); ctx.set_lanes(0)
+        one.free()
+        single_pair_us = 1e3 * min(ts[1:])
+
+    # ---- N >= 2: BASELINE configs 4 and 5 on the same ranks, outside the c3 timed regions --------------------------------
+    c4 = c5 = None
+    if world > 1 and args.desc == "sift" and not args.no_multi:
+        c5 = run_c5_match(ctx, dev, rank, world, dist, all_max, barrier)
+        c4 = run_c4(ctx, api, dev, rank, world, all_max, barrier)
+
     # ---- extra key: the reference's own dataset (BASELINE configs 1-2: 30 test images x 5 scales x 89 model views), when
     # the feature cache travelled with the tree (data_cache/, built by __graft_entry__.build() from the reference's
-    # data with cv2 SIFT).  Per test image: one streaming upload of its 5 scaled scenes + one fused call, as the
-    # reference's processAllTestImages loop would issue them (src/Output.cpp:27-47).
+    # data with cv2 SIFT).  Per test image: one streaming upload of its 5 scaled scenes + one fused call, software-pipelined
+    # on this one thread as the reference's processAllTestImages loop allows (src/Output.cpp:27-47 carries no state).
     real = None
     cache = os.path.join(ROOT, "data_cache", "features_full.npz")
     if rank == 0 and args.desc == "sift" and not args.no_extras and os.path.exists(cache):
@@ -425,47 +562,51 @@ def run_cvgraft(args):
             md = Z["model_desc"].astype(np.float32); so = Z["scene_offsets"]; n_img = (len(so) - 1) // 5
             sd = torch.from_numpy(Z["scene_desc"].astype(np.float32)).pin_memory(); sk = torch.from_numpy(Z["scene_kpt"].astype(np.float32)).pin_memory()
             sdn, skn = sd.numpy(), sk.numpy()
-            # own contexts (their buffer pools hold this workload's sizes), C of them on C threads, image i on context
-            # i mod C — test images are independent (src/Output.cpp:27-47 carries no state from one to the next)
-            rctxs = [api.Context(local) for _ in range(C)]
-            rstreams = [torch.cuda.ExternalStream(c.stream, device=torch.device("cuda", local)) for c in rctxs]
-            rmodels = [c.upload_models(md, Z["model_kpt"], Z["view_offsets"], Z["view_model"]) for c in rctxs]
+            rctx = api.Context(local)                      # own context: its buffer pools hold this workload's sizes
+            rstream = torch.cuda.ExternalStream(rctx.stream, device=dev)
+            rmodels = rctx.upload_models(md, Z["model_kpt"], Z["view_offsets"], Z["view_model"])
             sc5 = Z["scales"].astype(np.float32)
 
-            def up(c, i):
+            def up(i):
                 a, b = so[5 * i], so[5 * i + 5]
-                return c.upload_scenes_async(sdn[a:b], skn[a:b], so[5 * i:5 * i + 6] - a)
+                return rctx.upload_scenes_async(sdn[a:b], skn[a:b], so[5 * i:5 * i + 6] - a)
 
-            def whole():
-                hists = [np.zeros(5, np.int64) for _ in range(C)]
-                ends = [torch.cuda.Event(enable_timing=True) for _ in range(C)]
-
-                def work(j):
-                    torch.cuda.set_device(local)
-                    mine = list(range(j, n_img, C))
-                    nxt = up(rctxs[j], mine[0]) if mine else None
-                    for t, i in enumerate(mine):
-                        cur = nxt; nxt = up(rctxs[j], mine[t + 1]) if t + 1 < len(mine) else None
-                        res, _, _ = rctxs[j].detect_scenes_inliers(rmodels[j], cur, scales=sc5, params=params)
-                        cur.free()
-                        hists[j] += np.bincount(res["status"].ravel(), minlength=5)[:5]
-                    ends[j].record(rstreams[j])
+            def whole(pipelined):
+                hist = np.zeros(5, np.int64)
                 torch.cuda.synchronize()
-                r0 = torch.cuda.Event(enable_timing=True); r0.record(rstreams[0])
-                th = [threading.Thread(target=work, args=(j,)) for j in range(C)]
-                [t.start() for t in th]; [t.join() for t in th]
-                for e in ends:
-                    e.synchronize()
-                return sum(hists), max(r0.elapsed_time(e) for e in ends)
-            whole()                                        # warm-up pass: allocations, lazy kernel loading
-            hist, ms_real = whole()
-            n_views = rmodels[0].n_views
+                r0 = torch.cuda.Event(enable_timing=True); r1 = torch.cuda.Event(enable_timing=True); r0.record(rstream)
+                if pipelined:
+                    fl = []
+                    for i in range(n_img):
+                        sc = up(i)
+                        fl.append((sc, rctx.submit_scenes(rmodels, sc, scales=sc5, params=params)))
+                        if len(fl) > DEPTH - 1:
+                            sc0, j0 = fl.pop(0); res = j0.wait()[0]; sc0.free()
+                            hist += np.bincount(res["status"].ravel(), minlength=5)[:5]
+                    for sc0, j0 in fl:
+                        res = j0.wait()[0]; sc0.free()
+                        hist += np.bincount(res["status"].ravel(), minlength=5)[:5]
+                else:
+                    nxt = up(0)
+                    for i in range(n_img):
+                        cur = nxt; nxt = up(i + 1) if i + 1 < n_img else None
+                        res = rctx.detect_scenes_inliers(rmodels, cur, scales=sc5, params=params)[0]
+                        cur.free()
+                        hist += np.bincount(res["status"].ravel(), minlength=5)[:5]
+                r1.record(rstream); r1.synchronize()
+                return hist, r0.elapsed_time(r1)
+            whole(True); whole(False)                      # warm-up passes: allocations, lazy kernel loading
+            hist, ms_real = whole(True)
+            hist_s, ms_real_sync = whole(False)
+            n_views = rmodels.n_views
             real = {"pairs": int(n_img * 5 * n_views), "images": int(n_img), "seconds": ms_real * 1e-3,
-                    "pairs_per_s": n_img * 5 * n_views / (ms_real * 1e-3), "contexts": C,
+                    "pairs_per_s": n_img * 5 * n_views / (ms_real * 1e-3), "contexts": 1, "host_threads": 1,
+                    "seconds_sync_calls": ms_real_sync * 1e-3,
                     "gate_histogram[accept,<4 matches,H empty,<4 inliers,det]": [int(v) for v in hist],
-                    "note": "host buffers in, per-pair results + inlier points out, one call per test image"}
-            for m_, c_ in zip(rmodels, rctxs):
-                m_.free(); c_.close()
+                    "gate_histogram_sync_equal": bool(np.array_equal(hist, hist_s)),
+                    "note": f"host buffers in, per-pair results + inlier points out, one call per test image, {DEPTH} images in "
+                            "flight from one thread (seconds) / strictly synchronous calls (seconds_sync_calls)"}
+            rmodels.free(); rctx.close()
         except Exception as e:                             # the cache is optional
             real = {"unavailable": str(e)[:200]}
 
@@ -483,64 +624,73 @@ def run_cvgraft(args):
         flops = 2.0 * NQ * NT * DIM * B
         kms = statistics.mean(match_ms)
         achieved = flops / (kms * 1e-3) / 1e12
+        sm_hz = (clk.get("sm_mhz") or 1965.0) * 1e6
+        score_s = max(sum(score_ms) * 1e-3, 1e-12)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16 operands (exact for u8 descriptors) / f32 accumulate; f64+f32 verify", "data": "synthetic",
-                "config": {"workload": "c3: 1 resident model view x 8192 desc vs B scenes x 8192 desc, ratio 0.9, "
-                                       "RANSAC 2000 iters thr 5.0 conf 0.995", "pairs_per_step_per_gpu": B,
+                "config": {"workload": WORKLOAD, "pairs_per_step_per_gpu": B,
                            "descriptors": "fp32, integer-valued 0..255 (SIFT-like)" if args.desc == "sift" else
                                           "fp32, non-integer (candidate + fp32 re-rank match path)",
                            "match_path": ctx.last_match_path,
                            "scene_batches_rotated": R, "parallelism": f"pair-sharded x{world}, no data-path collective",
-                           "contexts_per_gpu": C, "host_numa_node": numa,
+                           "contexts_per_gpu": 1, "host_threads_per_gpu": 1, "calls_in_flight": DEPTH, "host_numa_node": numa,
                            "l2": f"{R} rotating batches, {R * B * NT * DIM * 2 / 2**20:.0f} MiB of bf16 operands > 126 MB L2"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_e2e / args.steps},
+                        "ms_per_step": ms_e2e / args.steps,
+                        "returns": "per-pair status/counts/H/det + inlier scene points + offsets (cvg_detect_scenes_submit with inlier buffers)"},
                 "e2e_u8": e2e_u8,
                 "real_dataset": real,
                 "gpu_launches": int(launches),
                 "clocks": clk,
                 # The largest kernel of the step that has a roofline: the tcgen05 match kernel (tensor bound).  The refit/LM
                 # kernel (ransac_finish_kernel) has a longer single launch when the kernels run alone, but it is 64 CTAs of
-                # serial fp64 eigen-solves — latency, no roofline; with C contexts it hides under the other batches' kernels.
+                # serial fp64 eigen-solves — latency, no roofline; with calls in flight it hides under the other calls' kernels.
                 "roofline": {"kernel": "match_tc_kernel (tcgen05)", "bound": "tensor", "achieved": achieved,
-                             "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
-                             "peak_burst": peaks["bf16_burst"], "frac_of_burst": achieved / peaks["bf16_burst"],
-                             "peak_source": peaks["source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
+                             "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_burst"],
+                             "peak_sustained": peaks["bf16_sustained"], "frac_of_sustained": achieved / peaks["bf16_sustained"],
+                             "peak_source": peaks["source"] + " (burst cuBLAS bf16: the timed region is tens of ms at full clocks)",
                              "kernel_ms_per_launch": kms, "launches_per_step": 1, "algorithmic_flops_per_launch": flops,
-                             "share_of_step": sum(match_ms) / ms_single, "traffic": traffic,
-                             "timed_region": "single-context pass (value_single_context): with several contexts in flight "
-                                             "kernels of different batches overlap and a launch duration is no longer a "
-                                             "utilisation figure"},
-                # scoring is a streaming scan, 16 B per (hypothesis, correspondence), HBM roofline.
+                             "share_of_step": sum(match_ms) / ms_serial, "traffic": traffic,
+                             "single_pair_us": single_pair_us,
+                             "timed_region": "serial pass (one lane, synchronous calls): with several calls in flight kernels of "
+                                             "different batches overlap and a launch duration is no longer a utilisation figure"},
+                # SURVEY 8d quotes scoring against HBM (16 B per (hypothesis, correspondence)); the set is shared-memory resident,
+                # so that figure is reported as algorithmic_gbs and the utilisation is the fp32 issue fraction.
                 "roofline_score": {"kernel": "ransac_score_kernel (inlier counting of a round's models, one hypothesis per thread, "
-                                             "correspondences staged in shared memory; one launch per RANSAC round)", "bound": "hbm",
-                                   "achieved": 16.0 * sum(scored) / max(sum(score_ms) * 1e-3, 1e-12) / 1e9, "peak": peaks["hbm"],
-                                   "unit": "GB/s",
-                                   "frac": 16.0 * sum(scored) / max(sum(score_ms) * 1e-3, 1e-12) / 1e9 / peaks["hbm"],
-                                   "peak_source": peaks["source"] + " (copy bandwidth)",
+                                             "correspondences staged in shared memory; one launch per RANSAC round)",
+                                   "bound": "fp32_issue",
+                                   "achieved": 28.0 * sum(scored) / score_s / 1e12, "peak": 148 * 128 * sm_hz / 1e12,
+                                   "unit": "T non-FMA fp32 instr/s (28 per (hypothesis, correspondence))",
+                                   "frac": 28.0 * sum(scored) / score_s / (148 * 128 * sm_hz),
+                                   "algorithmic_gbs": 16.0 * sum(scored) / score_s / 1e9, "hbm_peak_gbs": peaks["hbm"],
                                    "kernel_ms_per_launch": sum(score_ms) / max(sum(hyp_launches), 1),
                                    "launches_per_step": sum(hyp_launches) / args.steps,
                                    "algorithmic_bytes_per_launch": 16.0 * sum(scored) / max(sum(hyp_launches), 1),
-                                   "share_of_step": sum(score_ms) / ms_single, "traffic": hyp_traffic,
-                                   "fp32_issue_frac": 28.0 * sum(scored) / max(sum(score_ms) * 1e-3, 1e-12)
-                                                      / (148 * 128 * (clk.get("sm_mhz") or 1965.0) * 1e6),
-                                   "note": "frac can exceed 1: a CTA reads its slice of the correspondences from HBM/L2 once and "
-                                           "scores 256 hypotheses against it from shared memory, so the algorithmic 16 B per "
-                                           "(hypothesis, correspondence) is not DRAM traffic; the real ceiling is the fp32 issue "
-                                           "rate (28 non-FMA instructions per pair, fp32_issue_frac)"},
+                                   "share_of_step": sum(score_ms) / ms_serial, "traffic": hyp_traffic,
+                                   "note": "a CTA reads its slice of the correspondences from HBM/L2 once and scores 256 hypotheses "
+                                           "against it from shared memory: algorithmic_gbs exceeds the HBM peak by construction"},
                 "solve_stage": {"kernel": "ransac_hyp_t_kernel (4-point DLT: bit-exact fp64 9x9 Jacobi, one hypothesis per thread; "
                                           "one launch per RANSAC round, rounds past the adaptive stop exit early)",
                                 "ms_per_step": statistics.mean(hyp_ms), "launches_per_step": sum(hyp_launches) / args.steps,
-                                "share_of_step": sum(hyp_ms) / ms_single,
-                                "note": "latency-bound (~140 dependent rotations per matrix, 7 warps per SM: the matrix state fills "
-                                        "shared memory); no bandwidth or tensor roofline applies"},
-                "value_single_context": {"value": value_single, "unit": UNIT, "ms_per_step": ms_single / args.steps,
-                                         "note": "one context, synchronous calls back to back: the timed region of the rooflines"},
+                                "share_of_step": sum(hyp_ms) / ms_serial,
+                                "note": "latency-bound (~140 dependent rotations per matrix); no bandwidth or tensor roofline applies"},
+                # one context, one host thread in all three: serial (one lane; the rooflines' timed region), synchronous calls
+                # split over the context's lanes, and the headline (calls_in_flight submitted ahead)
+                "value_single_context": {"value": world * B * args.steps / (ms_sync * 1e-3), "unit": UNIT,
+                                         "ms_per_step": ms_sync / args.steps,
+                                         "note": "one context, one host thread, SYNCHRONOUS calls back to back, each split into sub-batches "
+                                                 "over the context's lanes"},
+                "value_serial": {"value": world * B * args.steps / (ms_serial * 1e-3), "unit": UNIT, "ms_per_step": ms_serial / args.steps,
+                                 "note": "one lane: every kernel alone on the GPU (timed region of the rooflines)"},
                 "stage_ms_per_step": {"match_kernel": kms, "verify": statistics.mean(ransac_ms), "verify_solve_kernels": statistics.mean(hyp_ms),
                                       "verify_score_kernels": statistics.mean(score_ms),
                                       "verify_rest(sampler, select, refit/LM finish, gates)": statistics.mean(ransac_ms) - statistics.mean(hyp_ms) - statistics.mean(score_ms)},
-                "accepted_pairs": accepted_multi}
+                "accepted_pairs": accepted}
+        if c4 is not None:
+            line["c4"] = c4
+        if c5 is not None:
+            line["c5_match"] = c5
         if world == 1 and not args.no_cpu:
             os.sched_setaffinity(0, all_cpus)           # the CPU baseline gets every core of the box
             threads = os.cpu_count() or 1
@@ -553,9 +703,9 @@ def run_cvgraft(args):
                                     "sample": f"{n} pairs of the same workload (cv2 knnMatch on {threads} threads, "
                                               f"findHomography calls on a {threads}-thread pool)"}
         print(json.dumps(line), file=_RESULT_OUT, flush=True)
-    for m_, c_ in zip(cmodels, ctxs):
-        m_.free(); c_.close()
+    models.free(); ctx.close()
     if world > 1:
+        barrier()
         dist.destroy_process_group()
 
 
@@ -573,8 +723,9 @@ def main():
     ap.add_argument("--batches", type=int, default=4, help="distinct scene batches rotated over the steps")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--contexts", type=int, default=3,
-                    help="contexts (= host threads, streams) per GPU for the headline value / e2e; 1 = strictly serial calls")
+    ap.add_argument("--depth", type=int, default=3,
+                    help="calls the one host thread keeps in flight on the one context (cvg_detect_scenes_submit / cvg_job_wait)")
+    ap.add_argument("--no-multi", action="store_true", help="N >= 2: skip the c4 / c5_match keys")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra keys (e2e_u8, real_dataset): launch-list runs")
     ap.add_argument("--desc", default="sift", choices=["sift", "float"],
                     help="descriptor generator: integer-valued SIFT-like rows (default) or non-integer float rows")

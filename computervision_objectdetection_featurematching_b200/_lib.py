@@ -28,6 +28,14 @@ SYMBOLS = {
     "cvg_ransac_params_default": (None, [C.POINTER(RansacParams)]),
     "cvg_detect_params_default": (None, [C.POINTER(DetectParams)]),
     "cvg_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_uint]),
+    "cvg_create_multi": (C.c_int, [C.POINTER(_P), C.POINTER(C.c_int), C.c_int, C.c_uint]),
+    "cvg_num_devices": (C.c_int, [_P]),
+    "cvg_exchange_kind": (C.c_char_p, [_P]),
+    "cvg_set_lanes": (C.c_int, [_P, C.c_int]),
+    "cvg_detect_scenes_submit": (C.c_int, [_P, _P, _P, _P, C.POINTER(DetectParams), _P, _P, _P, C.POINTER(_P)]),
+    "cvg_job_wait": (C.c_int, [_P, _P]),
+    "cvg_match_knn2_sharded": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_float, _P, _P, _P]),
+    "cvg_last_match_guard_rows": (C.c_int, [_P]),
     "cvg_destroy": (None, [_P]),
     "cvg_last_error": (C.c_char_p, []),
     "cvg_host_alloc": (C.c_void_p, [C.c_size_t]),

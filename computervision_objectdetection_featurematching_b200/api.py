@@ -101,15 +101,53 @@ class Scenes:
             self.handle = None
 
 
+class Job:
+    """A fused call in flight (Context.submit_scenes); wait() returns what detect_scenes_inliers returns."""
+
+    def __init__(self, ctx, handle, res, inl, off, S, V, keep):
+        self.ctx, self.handle, self._res, self._inl, self._off, self._S, self._V, self._keep = ctx, handle, res, inl, off, S, V, keep
+
+    def wait(self):
+        if self.handle is None:
+            raise RuntimeError("job already waited for")
+        h, self.handle = self.handle, None
+        self.ctx._check(self.ctx.lib.cvg_job_wait(self.ctx.handle, h))
+        self._keep = None
+        res = self._res[:self._S * self._V].reshape(self._S, self._V)
+        if self._inl is None:
+            return res, None, None
+        return res, self._inl[:self._off[-1]], self._off
+
+
 class Context:
+    """device: one GPU index (cvg_create), or a list of GPU indices of this host (cvg_create_multi: model set replicated,
+    scene batches dealt to the GPUs by cost, train-tile sharded match with one NCCL all-gather)."""
+
     def __init__(self, device=0, flags=0):
         self.lib = _lib.load()
         h = C.c_void_p()
-        rc = self.lib.cvg_create(C.byref(h), device, flags)
+        if isinstance(device, (list, tuple)):
+            devs = (C.c_int * len(device))(*[int(d) for d in device])
+            rc = self.lib.cvg_create_multi(C.byref(h), devs, len(device), flags)
+        else:
+            rc = self.lib.cvg_create(C.byref(h), device, flags)
         if rc:
             raise CvgError(rc, self.lib.cvg_last_error().decode())
         self.handle = h
         self.device = device
+
+    @property
+    def n_devices(self):
+        return int(self.lib.cvg_num_devices(self.handle))
+
+    @property
+    def exchange_kind(self):
+        """How the train-tile shards exchange their partial top-2: 'nccl', 'memcpy' (logical devices on one GPU), 'none'."""
+        return self.lib.cvg_exchange_kind(self.handle).decode()
+
+    def set_lanes(self, n):
+        """Sub-batches of one synchronous fused call / jobs in flight (1 = strictly serial on the caller's thread, 0 = default)."""
+        self._check(self.lib.cvg_set_lanes(self.handle, int(n)))
 
     def close(self):
         if self.handle:
@@ -191,6 +229,11 @@ class Context:
     def last_match_fallback_rows(self):
         """Rows of the last candidate-path call that were redone by the exact fallback kernel."""
         return int(self.lib.cvg_last_match_fallback_rows(self.handle))
+
+    @property
+    def last_match_guard_rows(self):
+        """Rows of the last tensor-path call whose second distance reached 2048 and were redone exactly."""
+        return int(self.lib.cvg_last_match_guard_rows(self.handle))
 
     @property
     def last_sampler_serial_sets(self):
@@ -294,6 +337,29 @@ class Context:
         self._check(self.lib.cvg_detect_scenes_inliers(self.handle, models.handle, scenes.handle, _ptr(sc), C.byref(p),
                                                        _ptr(res), _ptr(inl), _ptr(off)))
         return res[:S * V].reshape(S, V), inl[:off[-1]], off
+
+    def submit_scenes(self, models, scenes, scales=None, params=None, want_inliers=True):
+        """Asynchronous detect_scenes_inliers: returns a Job at once (cvg_detect_scenes_submit); Job.wait() gives the results.
+        A single-threaded caller keeps two or three jobs in flight to overlap them on the GPU."""
+        p = params if params is not None else detect_params()
+        S, V = scenes.n_scenes, models.n_views
+        res = np.zeros(max(S * V, 1), PAIR_DTYPE)
+        sc = np.ascontiguousarray(scales, np.float32) if scales is not None else None
+        inl = np.zeros((max(S * models.n_rows, 1), 2), np.float32) if want_inliers else None
+        off = np.zeros(S * V + 1, np.int64) if want_inliers else None
+        h = C.c_void_p()
+        self._check(self.lib.cvg_detect_scenes_submit(self.handle, models.handle, scenes.handle, _ptr(sc), C.byref(p),
+                                                      _ptr(res), _ptr(inl), _ptr(off), C.byref(h)))
+        return Job(self, h, res, inl, off, S, V, keep=(models, scenes, sc, p))
+
+    def match_knn2_sharded(self, query, train, ratio=0.9):
+        """Train-tile sharded knnMatch over the GPUs of a multi-device context (one all-gather + merge)."""
+        q = _f32(query, 128); t = _f32(train, 128)
+        nq = q.shape[0]
+        idx = np.full((nq, 2), -1, np.int32); dist = np.zeros((nq, 2), np.float32); acc = np.zeros(nq, np.uint8)
+        self._check(self.lib.cvg_match_knn2_sharded(self.handle, _ptr(q), nq, _ptr(t), t.shape[0], ratio,
+                                                    _ptr(idx), _ptr(dist), _ptr(acc)))
+        return idx, dist, acc
 
     # ---- device-pointer building blocks (multi-GPU train-tile shards) ---------------------------
     def dev_match_top2(self, query_ptr, n_query, train_ptr, n_train, index_base, dist_ptr, idx_ptr, stream=None):

@@ -1,10 +1,8 @@
 // api.cu — the C ABI of libcvgraft (include/cvgraft.h): context, resident model/scene sets and the
 // host-side orchestration of the match and verify kernels.  No CPU fallback exists: every entry point
 // needs a CUDA device and fails loudly otherwise.
-#include "common.cuh"
-#include <algorithm>
-#include <string>
-#include <vector>
+#include "ctx.cuh"
+#include <atomic>
 #include <string.h>
 #include <stdarg.h>
 #include <math.h>
@@ -13,7 +11,7 @@ using namespace cvg;
 
 static thread_local char g_err[512] = "";
 
-static int set_err(int code, const char* fmt, ...)
+int cvg_set_err(int code, const char* fmt, ...)
 {
     va_list ap;
     va_start(ap, fmt);
@@ -21,127 +19,7 @@ static int set_err(int code, const char* fmt, ...)
     va_end(ap);
     return code;
 }
-
-#define CU_CHECK(call)                                                                         \
-    do {                                                                                       \
-        cudaError_t e__ = (call);                                                              \
-        if (e__ != cudaSuccess)                                                                \
-            return set_err(CVG_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
-                           __FILE__, __LINE__);                                                \
-    } while (0)
-
-// grow-only device buffer
-struct DevBuf {
-    void* p = nullptr; size_t cap = 0;
-    cudaError_t ensure(size_t bytes)
-    {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-// Freed device buffers are kept for reuse: cudaMalloc/cudaFree cost milliseconds and serialise the
-// device, which would dominate a streaming caller that uploads a scene batch per step.
-struct BufPool {
-    std::vector<DevBuf> free_list;
-    cudaError_t acquire(DevBuf& b, size_t bytes)
-    {
-        if (b.cap >= bytes) return cudaSuccess;
-        if (b.p) { release(b); }
-        int best = -1;
-        for (int i = 0; i < (int)free_list.size(); i++)
-            if (free_list[i].cap >= bytes && (best < 0 || free_list[i].cap < free_list[best].cap)) best = i;
-        if (best >= 0 && free_list[best].cap <= 2 * bytes + (1 << 20)) {
-            b = free_list[best];
-            free_list.erase(free_list.begin() + best);
-            return cudaSuccess;
-        }
-        return b.ensure(bytes);
-    }
-    void release(DevBuf& b)
-    {
-        if (!b.p) return;
-        if (free_list.size() >= 64) {               // bounded: the buffer that has waited longest goes (sizes of a
-            free_list.front().release();            // streaming caller drift; keeping the smallest ones thrashed)
-            free_list.erase(free_list.begin());
-        }
-        free_list.push_back(b);
-        b.p = nullptr; b.cap = 0;
-    }
-    void clear() { for (DevBuf& b : free_list) b.release(); free_list.clear(); }
-};
-
-struct SegInfo { int rows; int64_t f32_row0; int64_t pad_row0; int ct; };
-
-struct TrainSet {                      // a prepared set of train segments on the device
-    int n_segs = 0;
-    std::vector<SegInfo> segs;
-    int64_t rows_total = 0, rows_pad_total = 0;
-    int max_rows = 0;
-    float* d_f32 = nullptr;            // [rows_total, 128]
-    __nv_bfloat16* d_b = nullptr;      // [rows_pad_total, 128]
-    __nv_bfloat16* d_blo = nullptr;    // [rows_pad_total, 128] lo half of the split operand (zero for integer rows)
-    __nv_bfloat16* d_aug = nullptr;    // [rows_pad_total, 16]
-    float* d_kpt = nullptr;            // [rows_total, 2] or null
-    int64_t* d_kpt_offsets = nullptr;  // [S+1]
-    int nonint = -1;                   // host-known row-kind bits of prep_rows_kernel (-1 unknown: decided on the device)
-    int* d_tnmax = nullptr;            // device word: max ||t||^2 as float bits (error bound of the candidate path)
-};
-
-struct cvg_models {
-    int n_rows = 0, n_pad = 0, n_views = 0;
-    std::vector<int32_t> view_offsets, view_model;
-    float* d_f32 = nullptr; __nv_bfloat16* d_b = nullptr; __nv_bfloat16* d_blo = nullptr; __nv_bfloat16* d_aug = nullptr;
-    float* d_norm = nullptr; float* d_kpt = nullptr; int32_t* d_view_offsets = nullptr;
-    int nonint = 0;
-};
-
-struct cvg_scenes {
-    TrainSet ts;
-    DevBuf f32, b, blo, aug, kpt, kptoff, u8, segtab;
-    int* d_flag = nullptr;             // non-integer flag of this batch (tail of kptoff)
-    cudaEvent_t ready = nullptr;       // set by cvg_scenes_upload_async: upload + conversion finished
-};
-
-struct cvg_ctx {
-    int device = 0; unsigned flags = 0; int n_sms = 148;
-    cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;                // uploads of cvg_scenes_upload_async (overlap with compute)
-    int* d_flags = nullptr;            // [0] train row kinds, [1] query row kinds, [2] match path (0 tensor exact, 1 tensor
-                                       // candidates + re-rank, 2 exact SIMT), [3] raw-query kinds, [4] RNG table short,
-                                       // [5] max ||t||^2 bits, [6] fallback row count, [8..16) kernel debug words, [17] sets the chunked sampler handed to the serial one
-    uint32_t* d_rng = nullptr; int64_t rng_len = 0;
-    int last_match_path = 0; int64_t launches = 0;
-    int timing = 0; float t_match = 0, t_ransac = 0, t_total = 0;
-    cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
-    cudaEvent_t hyp_ev[48] = {};                       // [2r], [2r+1]: solve kernel of round r; [32 + r]: after its score kernel
-    int hyp_rounds = 0; float t_hyp = 0, t_score = 0; int hyp_launches = 0; unsigned long long scored_pts = 0;
-    unsigned long long* d_scored = nullptr;
-    // scratch
-    DevBuf q_f32, q_b, q_blo, q_aug, q_norm;           // raw-query path
-    DevBuf t_f32, t_b, t_blo, t_aug, t_kpt, t_kptoff, t_segtab;  // per-call train path
-    DevBuf units, dir, parts, idx, dist, accept;
-    DevBuf parts4, segdev, fb;                         // candidate path: Top4 records, segment table, unproven rows
-    DevBuf hypH;                                       // fp32 models of the current round(s), read by ransac_score_kernel
-    DevBuf chunk;                                      // chunked sampler scratch (huge no-early-stop rounds)
-    DevBuf plan_units, plan_dir;                       // match plan of the fused path, cached by (model set, scene shapes)
-    bool last_chunked = false;                         // the last verify call used the chunked sampler (d_flags[17] = sets it handed back)
-    const cvg_models* plan_models = nullptr; std::vector<int> plan_shape; int plan_units_n = 0;
-    DevBuf pts, starts, counts_n, sample_pos, n_samples, counts, best_iter, best_count, iters_run, niters_cur, smp_state, sel;
-    DevBuf H, mask, rmask, found, sflags, results, inl_xy, inl_cnt, scales, src, dst;
-    BufPool pool;                                      // recycled buffers of freed scene batches
-    // Small host->device parameter blocks of the fused path go through a mapped pinned staging area read by a
-    // copy kernel, not through cudaMemcpyAsync: the H2D copy engine may be busy for milliseconds with the next
-    // scene batch (cvg_scenes_upload_async) and would hold the compute stream behind it.
-    uint8_t* stage_h = nullptr; uint8_t* stage_d = nullptr; size_t stage_cap = 0, stage_used = 0; bool stage_fallback = false;
-};
+#define set_err cvg_set_err
 
 __global__ void stage_copy_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n16)
 {
@@ -185,7 +63,23 @@ void cvg_detect_params_default(cvg_detect_params* p)
     cvg_ransac_params_default(&p->ransac);
 }
 
-int cvg_create(cvg_ctx** out, int device, unsigned flags)
+}  // extern "C"
+
+// Opt-in attributes (dynamic shared memory) belong to a (function, device) pair: set once per device of the process.
+static int device_init_once(int device, char* err, size_t errlen)
+{
+    static std::mutex mu;
+    static bool done[64] = {};
+    std::lock_guard<std::mutex> g(mu);
+    if (device >= 0 && device < 64 && done[device]) return 0;
+    if (tc_init(err, errlen)) return 1;
+    if (tc_set_device_attrs(err, errlen)) return 1;
+    if (ransac_set_device_attrs(err, errlen)) return 1;
+    if (device >= 0 && device < 64) done[device] = true;
+    return 0;
+}
+
+int eng_create(cvg_ctx** out, int device, unsigned flags)
 {
     if (!out) return set_err(CVG_ERR_INVALID, "cvg_create: out is NULL");
     *out = nullptr;
@@ -201,38 +95,42 @@ int cvg_create(cvg_ctx** out, int device, unsigned flags)
     if (prop.major != 10)
         return set_err(CVG_ERR_CUDA, "cvg_create: device %d is sm_%d%d; libcvgraft is built for sm_100a only",
                        device, prop.major, prop.minor);
+    char err[256];
+    if (device_init_once(device, err, sizeof err)) return set_err(CVG_ERR_CUDA, "%s", err);
     cvg_ctx* c = new cvg_ctx();
     c->device = device; c->flags = flags; c->n_sms = prop.multiProcessorCount;
-    CU_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    CU_CHECK(cudaMalloc(&c->d_flags, 64 * sizeof(int)));
-    CU_CHECK(cudaMemset(c->d_flags, 0, 64 * sizeof(int)));
-    for (int i = 0; i < 6; i++) CU_CHECK(cudaEventCreate(&c->ev[i]));
-    for (int i = 0; i < 48; i++) CU_CHECK(cudaEventCreate(&c->hyp_ev[i]));
-    CU_CHECK(cudaMalloc(&c->d_scored, 8));
-    CU_CHECK(cudaMemset(c->d_scored, 0, 8));
+    int rc = [&]() -> int {
+        CU_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CU_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CU_CHECK(cudaMalloc(&c->d_flags, 64 * sizeof(int)));
+        CU_CHECK(cudaMemset(c->d_flags, 0, 64 * sizeof(int)));
+        for (int i = 0; i < 6; i++) CU_CHECK(cudaEventCreate(&c->ev[i]));
+        for (int i = 0; i < 48; i++) CU_CHECK(cudaEventCreate(&c->hyp_ev[i]));
+        CU_CHECK(cudaMalloc(&c->d_scored, 8));
+        CU_CHECK(cudaMemset(c->d_scored, 0, 8));
+        return CVG_OK;
+    }();
+    if (rc) { eng_destroy(c); return rc; }                  // a half-built engine releases what it got
     c->stage_cap = 4u << 20;
     if (cudaHostAlloc((void**)&c->stage_h, c->stage_cap, cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void**)&c->stage_d, c->stage_h, 0) != cudaSuccess) {
         cudaGetLastError(); c->stage_h = nullptr; c->stage_cap = 0;       // falls back to cudaMemcpyAsync
     }
-    char err[256];
-    if (tc_init(err, sizeof err)) { delete c; return set_err(CVG_ERR_CUDA, "%s", err); }
     *out = c;
     return CVG_OK;
 }
 
-void cvg_destroy(cvg_ctx* c)
+void eng_destroy(cvg_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     DevBuf* bufs[] = { &c->q_f32, &c->q_b, &c->q_blo, &c->q_aug, &c->q_norm, &c->t_f32, &c->t_b, &c->t_blo, &c->t_aug, &c->t_segtab, &c->t_kpt, &c->t_kptoff,
                        &c->units, &c->dir, &c->parts, &c->parts4, &c->segdev, &c->fb, &c->plan_units, &c->plan_dir, &c->chunk, &c->hypH, &c->idx, &c->dist, &c->accept, &c->pts, &c->starts, &c->counts_n,
                        &c->sample_pos, &c->n_samples, &c->counts, &c->best_iter, &c->best_count, &c->iters_run, &c->niters_cur, &c->smp_state, &c->sel,
                        &c->H, &c->mask, &c->rmask, &c->found, &c->sflags, &c->results, &c->inl_xy, &c->inl_cnt,
-                       &c->scales, &c->src, &c->dst };
+                       &c->scales, &c->src, &c->dst, &c->nit };
     for (DevBuf* b : bufs) b->release();
     c->pool.clear();
     if (c->d_flags) cudaFree(c->d_flags);
@@ -246,6 +144,8 @@ void cvg_destroy(cvg_ctx* c)
     delete c;
 }
 
+extern "C" {
+
 void* cvg_host_alloc(size_t bytes)
 {
     void* p = nullptr;
@@ -254,33 +154,44 @@ void* cvg_host_alloc(size_t bytes)
 }
 void cvg_host_free(void* p) { if (p) cudaFreeHost(p); }
 
-int cvg_last_match_path(const cvg_ctx* c) { return c ? c->last_match_path : 0; }
-int cvg_last_match_fallback_rows(const cvg_ctx* c)
+// Introspection reads the engine that served the caller's last direct call: the context itself, or device 0 of a
+// multi-device context (cvg_primary).
+int cvg_last_match_path(const cvg_ctx* c0) { const cvg_ctx* c = cvg_primary(c0); return c ? c->last_match_path : 0; }
+static int read_flag_word(const cvg_ctx* c, int word)
 {
-    if (!c || c->last_match_path != 3) return 0;
     int n = 0;
     cudaSetDevice(c->device);
-    cudaMemcpy(&n, c->d_flags + 6, 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(&n, c->d_flags + word, 4, cudaMemcpyDeviceToHost);
     return n;
 }
-int cvg_last_sampler_serial_sets(const cvg_ctx* c)
+int cvg_last_match_fallback_rows(const cvg_ctx* c0)
 {
-    if (!c || !c->last_chunked) return -1;
-    int n = 0;
-    cudaSetDevice(c->device);
-    cudaMemcpy(&n, c->d_flags + 17, 4, cudaMemcpyDeviceToHost);
-    return n;
+    const cvg_ctx* c = cvg_primary(c0);
+    return (!c || c->last_match_path != 3) ? 0 : read_flag_word(c, 6);
 }
-void* cvg_stream(const cvg_ctx* c) { return c ? (void*)c->stream : nullptr; }
-int cvg_last_hyp_stats(const cvg_ctx* c, float* hyp_ms, int* hyp_launches, uint64_t* scored_points)
+int cvg_last_match_guard_rows(const cvg_ctx* c0)
 {
+    const cvg_ctx* c = cvg_primary(c0);
+    return (!c || c->last_match_path != 1) ? 0 : read_flag_word(c, 7);
+}
+int cvg_last_sampler_serial_sets(const cvg_ctx* c0)
+{
+    const cvg_ctx* c = cvg_primary(c0);
+    return (!c || !c->last_chunked) ? -1 : read_flag_word(c, 17);
+}
+void* cvg_stream(const cvg_ctx* c0) { const cvg_ctx* c = cvg_primary(c0); return c ? (void*)c->stream : nullptr; }
+int cvg_last_hyp_stats(const cvg_ctx* c0, float* hyp_ms, int* hyp_launches, uint64_t* scored_points)
+{
+    const cvg_ctx* c = cvg_primary(c0);
     if (!c) return CVG_ERR_INVALID;
-    if (hyp_ms) *hyp_ms = c->t_hyp; if (hyp_launches) *hyp_launches = c->hyp_launches;
+    if (hyp_ms) *hyp_ms = c->t_hyp;
+    if (hyp_launches) *hyp_launches = c->hyp_launches;
     if (scored_points) *scored_points = c->scored_pts;
     return CVG_OK;
 }
-int cvg_selftest(cvg_ctx* c, int which, uint64_t* mismatches)
+int cvg_selftest(cvg_ctx* c0, int which, uint64_t* mismatches)
 {
+    cvg_ctx* c = cvg_primary(c0);
     if (!c || !mismatches || which != 0) return set_err(CVG_ERR_INVALID, "cvg_selftest: bad argument");
     CU_CHECK(cudaSetDevice(c->device));
     CU_CHECK(cudaMemsetAsync(c->d_scored, 0, 8, c->stream));
@@ -291,18 +202,21 @@ int cvg_selftest(cvg_ctx* c, int which, uint64_t* mismatches)
     *mismatches = n;
     return CVG_OK;
 }
-int cvg_last_score_ms(const cvg_ctx* c, float* score_ms)
+int cvg_last_score_ms(const cvg_ctx* c0, float* score_ms)
 {
+    const cvg_ctx* c = cvg_primary(c0);
     if (!c || !score_ms) return CVG_ERR_INVALID;
     *score_ms = c->t_score;
     return CVG_OK;
 }
-int64_t cvg_launch_count(const cvg_ctx* c) { return c ? c->launches : 0; }
-int cvg_set_timing(cvg_ctx* c, int enabled) { if (!c) return CVG_ERR_INVALID; c->timing = enabled; return CVG_OK; }
-int cvg_last_timing(const cvg_ctx* c, float* m, float* r, float* t)
+int cvg_set_timing(cvg_ctx* c0, int enabled) { cvg_ctx* c = cvg_primary(c0); if (!c) return CVG_ERR_INVALID; c->timing = enabled; return CVG_OK; }
+int cvg_last_timing(const cvg_ctx* c0, float* m, float* r, float* t)
 {
+    const cvg_ctx* c = cvg_primary(c0);
     if (!c) return CVG_ERR_INVALID;
-    if (m) *m = c->t_match; if (r) *r = c->t_ransac; if (t) *t = c->t_total;
+    if (m) *m = c->t_match;
+    if (r) *r = c->t_ransac;
+    if (t) *t = c->t_total;
     return CVG_OK;
 }
 
@@ -470,19 +384,23 @@ static int path_from_device_word(int w) { return w == 0 ? 1 : (w == 1 ? 3 : 2); 
 // gate themselves on d_flags[2]; no host round trip.
 static int launch_match(cvg_ctx* c, const QuerySide& q, const TrainSet& ts, const MatchUnit* d_units, int n_units,
                         const MergeEntry* d_dir, int n_rb, float ratio, int path_hint, Top2* d_parts,
-                        int32_t* d_idx, float* d_dist, uint8_t* d_accept)
+                        int32_t* d_idx, float* d_dist, uint8_t* d_accept, bool guard = true)
 {
     const int nq = q.row_end - q.row_begin;
     const int* gate = path_hint == 0 ? c->d_flags + 2 : nullptr;
     const bool want_int = path_hint == 0 || path_hint == 1, want_cand = path_hint == 0 || path_hint == 3;
     const bool want_simt = path_hint == 0 || path_hint == 2;
-    if (want_cand && n_units > 0) {
-        CU_CHECK(c->parts4.ensure((size_t)n_units * 4 * TILE_M * sizeof(Top4)));
+    // guard: rows of the integer path whose second distance reaches 2048 are redone exactly (merge_kernel); the caller
+    // switches it off when the norms of both sides prove that no distance can get there (SIFT: d <= 1024)
+    guard = guard && want_int && n_units > 0;
+    if ((want_cand || guard) && n_units > 0) {
+        if (want_cand) CU_CHECK(c->parts4.ensure((size_t)n_units * 4 * TILE_M * sizeof(Top4)));
         CU_CHECK(c->segdev.ensure((size_t)ts.n_segs * sizeof(SegDev) + 16));
         CU_CHECK(c->fb.ensure((size_t)ts.n_segs * std::max(nq, 1) * (sizeof(int2) + 16)));   // row list + two key arrays
         std::vector<SegDev> sd((size_t)ts.n_segs);
         for (int s = 0; s < ts.n_segs; s++) sd[(size_t)s] = SegDev{ ts.segs[(size_t)s].f32_row0, ts.segs[(size_t)s].rows, 0 };
         CU_CHECK(h2d_small(c, c->segdev.p, sd.data(), sd.size() * sizeof(SegDev)));
+        if (c->stage_fallback) CU_CHECK(cudaStreamSynchronize(c->stream));    // memcpy fallback: `sd` goes out of scope
     }
     if (c->timing) cudaEventRecord(c->ev[3], c->stream);
     if (n_units > 0) {
@@ -505,14 +423,21 @@ static int launch_match(cvg_ctx* c, const QuerySide& q, const TrainSet& ts, cons
         }
     }
     if (c->timing) cudaEventRecord(c->ev[4], c->stream);
+    const size_t n_rows_all = (size_t)ts.n_segs * std::max(nq, 1);
     if (want_int || want_simt || n_units == 0) {
         // without units (no train rows at all) nothing else writes the results: the merge runs ungated and emits -1
         launch_merge(d_parts, d_dir, ts.n_segs, n_rb, nq, ratio, d_idx, d_dist, d_accept, n_units == 0 ? nullptr : gate, 1,
-                     c->stream);
+                     c->stream, guard ? c->d_flags + 7 : nullptr, guard ? c->fb.as<int2>() : nullptr);
         c->launches++;
+        if (guard) {
+            // ungated: when another path served the call the merge did not run and the list is empty
+            launch_fallback_exact(c->d_flags + 7, c->fb.as<int2>(), reinterpret_cast<unsigned long long*>(c->fb.as<int2>() + n_rows_all),
+                                  c->segdev.as<SegDev>(), ts.n_segs, nq, ts.max_rows, ratio, q.d_f32, q.row_begin, ts.d_f32,
+                                  d_idx, d_dist, d_accept, nullptr, 0, c->n_sms, c->stream);
+            c->launches += 4;
+        }
     }
     if (want_cand && n_units > 0) {
-        const size_t n_rows_all = (size_t)ts.n_segs * std::max(nq, 1);
         launch_merge4_rerank(c->parts4.as<Top4>(), d_dir, c->segdev.as<SegDev>(), ts.n_segs, n_rb, nq, ts.max_rows, ratio, q.d_f32,
                              q.row_begin, ts.d_f32, q.d_norm, ts.d_tnmax ? ts.d_tnmax : c->d_flags + 5, d_idx, d_dist, d_accept,
                              c->d_flags + 6, c->fb.as<int2>(),
@@ -557,6 +482,7 @@ static int run_ransac(cvg_ctx* c, const float4* d_pts, const int64_t* d_starts, 
     if (want_rmask) CU_CHECK(c->rmask.ensure((size_t)std::max<int64_t>(pool_rows, 1)));
     RansacWork w;
     w.pts = d_pts; w.starts = d_starts; w.counts_n = d_counts_n; w.n_sets = n_sets; w.max_n = max_n;
+    w.n_sms = c->n_sms; w.wave_div = std::max(1, c->wave_div);
     w.max_iters = mi;
     const double thr = p->threshold > 0 ? p->threshold : 3.0;        // defaultRANSACReprojThreshold
     w.thr2 = (float)(thr * thr);
@@ -599,7 +525,7 @@ static int run_ransac(cvg_ctx* c, const float4* d_pts, const int64_t* d_starts, 
     return CVG_OK;
 }
 
-static int check_params(const cvg_ransac_params* p)
+int check_params(const cvg_ransac_params* p)
 {
     if (!p || p->size != sizeof(cvg_ransac_params)) return set_err(CVG_ERR_INVALID, "cvg_ransac_params: bad size field");
     if (!(p->confidence > 0 && p->confidence < 1)) return set_err(CVG_ERR_INVALID, "confidence must be in (0,1)");
@@ -617,10 +543,22 @@ static int sync_and_check(cvg_ctx* c)
     return CVG_OK;
 }
 
-extern "C" {
-
 // ---- models ---------------------------------------------------------------------------------------
-int cvg_models_upload(cvg_ctx* c, const float* desc, const float* kpt_xy, const int32_t* view_offsets,
+__global__ void max_norm_kernel(const float* __restrict__ norms, int n, int* __restrict__ out_bits)
+{
+    float m = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float v = norms[i];
+        if (v > m) m = v;                                   // NaN never wins; +inf does (then nothing is "known safe")
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_int(m));   // non-negative floats order like ints
+}
+
+static std::atomic<uint64_t> g_models_uid{ 1 };
+
+int eng_models_upload(cvg_ctx* c, const float* desc, const float* kpt_xy, const int32_t* view_offsets,
                       const int32_t* view_model, int n_views, cvg_models** out)
 {
     if (!c || !out || !view_offsets || n_views < 0) return set_err(CVG_ERR_INVALID, "cvg_models_upload: bad argument");
@@ -631,41 +569,50 @@ int cvg_models_upload(cvg_ctx* c, const float* desc, const float* kpt_xy, const 
     for (int v = 0; v < n_views; v++)
         if (view_offsets[v + 1] < view_offsets[v]) return set_err(CVG_ERR_INVALID, "view_offsets must be non-decreasing");
     cvg_models* m = new cvg_models();
-    m->n_rows = n; m->n_views = n_views;
+    m->n_rows = n; m->n_views = n_views; m->device = c->device; m->uid = g_models_uid.fetch_add(1);
     m->n_pad = round_up(std::max(n, 1), TILE_M) + TILE_M;          // slack: a view's last tile may overrun
     m->view_offsets.assign(view_offsets, view_offsets + n_views + 1);
     if (view_model) m->view_model.assign(view_model, view_model + n_views);
-    CU_CHECK(cudaMalloc(&m->d_f32, (size_t)m->n_pad * DIM * 4));
-    CU_CHECK(cudaMalloc(&m->d_b, (size_t)m->n_pad * DIM * 2));
-    CU_CHECK(cudaMalloc(&m->d_blo, (size_t)m->n_pad * DIM * 2));
-    CU_CHECK(cudaMalloc(&m->d_aug, (size_t)m->n_pad * KAUG * 2));
-    CU_CHECK(cudaMalloc(&m->d_norm, (size_t)m->n_pad * 4));
-    CU_CHECK(cudaMalloc(&m->d_kpt, (size_t)std::max(n, 1) * 8));
-    CU_CHECK(cudaMalloc(&m->d_view_offsets, (size_t)(n_views + 1) * 4));
-    CU_CHECK(cudaMemsetAsync(m->d_f32, 0, (size_t)m->n_pad * DIM * 4, c->stream));
-    if (n > 0) CU_CHECK(cudaMemcpyAsync(m->d_f32, desc, (size_t)n * DIM * 4, cudaMemcpyHostToDevice, c->stream));
-    if (n > 0 && kpt_xy) CU_CHECK(cudaMemcpyAsync(m->d_kpt, kpt_xy, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
-    CU_CHECK(cudaMemcpyAsync(m->d_view_offsets, view_offsets, (size_t)(n_views + 1) * 4, cudaMemcpyHostToDevice, c->stream));
-    CU_CHECK(cudaMemsetAsync(c->d_flags + 1, 0, 4, c->stream));
-    launch_prep_rows(m->d_f32, n, m->n_pad, 0, m->d_b, m->d_blo, m->d_aug, m->d_norm, c->d_flags + 1, nullptr, c->stream);
-    c->launches++;
-    int flag = 0;
-    CU_CHECK(cudaMemcpyAsync(&flag, c->d_flags + 1, 4, cudaMemcpyDeviceToHost, c->stream));
-    CU_CHECK(cudaStreamSynchronize(c->stream));
-    m->nonint = flag;
+    int flag[2] = { 0, 0 };
+    const int rc = [&]() -> int {
+        CU_CHECK(cudaMalloc(&m->d_f32, (size_t)m->n_pad * DIM * 4));
+        CU_CHECK(cudaMalloc(&m->d_b, (size_t)m->n_pad * DIM * 2));
+        CU_CHECK(cudaMalloc(&m->d_blo, (size_t)m->n_pad * DIM * 2));
+        CU_CHECK(cudaMalloc(&m->d_aug, (size_t)m->n_pad * KAUG * 2));
+        CU_CHECK(cudaMalloc(&m->d_norm, (size_t)m->n_pad * 4));
+        CU_CHECK(cudaMalloc(&m->d_kpt, (size_t)std::max(n, 1) * 8));
+        CU_CHECK(cudaMalloc(&m->d_view_offsets, (size_t)(n_views + 1) * 4));
+        CU_CHECK(cudaMemsetAsync(m->d_f32, 0, (size_t)m->n_pad * DIM * 4, c->stream));
+        if (n > 0) CU_CHECK(cudaMemcpyAsync(m->d_f32, desc, (size_t)n * DIM * 4, cudaMemcpyHostToDevice, c->stream));
+        if (n > 0 && kpt_xy) CU_CHECK(cudaMemcpyAsync(m->d_kpt, kpt_xy, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        CU_CHECK(cudaMemcpyAsync(m->d_view_offsets, view_offsets, (size_t)(n_views + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+        CU_CHECK(cudaMemsetAsync(c->d_flags + 1, 0, 4, c->stream));
+        CU_CHECK(cudaMemsetAsync(c->d_flags + 18, 0, 4, c->stream));
+        launch_prep_rows(m->d_f32, n, m->n_pad, 0, m->d_b, m->d_blo, m->d_aug, m->d_norm, c->d_flags + 1, nullptr, c->stream);
+        if (n > 0) max_norm_kernel<<<std::min(64, (n + 255) / 256), 256, 0, c->stream>>>(m->d_norm, n, c->d_flags + 18);
+        c->launches += 2;
+        CU_CHECK(cudaMemcpyAsync(&flag[0], c->d_flags + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+        CU_CHECK(cudaMemcpyAsync(&flag[1], c->d_flags + 18, 4, cudaMemcpyDeviceToHost, c->stream));
+        CU_CHECK(cudaStreamSynchronize(c->stream));
+        return CVG_OK;
+    }();
+    if (rc) { eng_models_free(c, m); return rc; }
+    m->nonint = flag[0];
+    memcpy(&m->max_norm2, &flag[1], 4);
     *out = m;
     return CVG_OK;
 }
 
-void cvg_models_free(cvg_ctx* c, cvg_models* m)
+void eng_models_free(cvg_ctx* c, cvg_models* m)
 {
-    if (c && c->plan_models == m) { c->plan_models = nullptr; c->plan_units_n = 0; }   // a later set may reuse the address
     if (!m) return;
-    if (c) cudaSetDevice(c->device);
+    if (c) cudaSetDevice(c->device); else if (m->device >= 0) cudaSetDevice(m->device);
     cudaFree(m->d_f32); cudaFree(m->d_b); cudaFree(m->d_blo); cudaFree(m->d_aug); cudaFree(m->d_norm); cudaFree(m->d_kpt);
     cudaFree(m->d_view_offsets);
     delete m;
 }
+
+extern "C" {
 
 int cvg_models_num_views(const cvg_models* m) { return m ? m->n_views : 0; }
 int cvg_models_num_rows(const cvg_models* m) { return m ? m->n_rows : 0; }
@@ -721,6 +668,7 @@ extern "C" {
 int cvg_match_knn2(cvg_ctx* c, const cvg_models* m, int view, const float* train, int n_train, float ratio,
                    int32_t* idx, float* dist, uint8_t* accept)
 {
+    c = cvg_primary(c); m = cvg_models_on(m, c);
     if (!c || !m) return set_err(CVG_ERR_INVALID, "cvg_match_knn2: NULL context/models");
     if (view < -1 || view >= m->n_views) return set_err(CVG_ERR_INVALID, "cvg_match_knn2: view %d of %d", view, m->n_views);
     CU_CHECK(cudaSetDevice(c->device));
@@ -732,6 +680,7 @@ int cvg_match_knn2(cvg_ctx* c, const cvg_models* m, int view, const float* train
 int cvg_match_knn2_raw(cvg_ctx* c, const float* query, int n_query, const float* train, int n_train, float ratio,
                        int32_t* idx, float* dist, uint8_t* accept)
 {
+    c = cvg_primary(c);
     if (!c) return set_err(CVG_ERR_INVALID, "cvg_match_knn2_raw: NULL context");
     if (n_query < 0 || (n_query > 0 && !query)) return set_err(CVG_ERR_INVALID, "bad query matrix");
     if (n_query == 0) return CVG_OK;
@@ -758,6 +707,7 @@ int cvg_find_homography_batch(cvg_ctx* c, const float* src_xy, const float* dst_
                               int n_sets, const cvg_ransac_params* p, double* H, uint8_t* mask, int32_t* found,
                               int32_t* iters, uint8_t* ransac_mask)
 {
+    c = cvg_primary(c);
     if (!c || !offsets || n_sets < 0) return set_err(CVG_ERR_INVALID, "cvg_find_homography_batch: bad argument");
     int rc = check_params(p);
     if (rc) return rc;
@@ -826,7 +776,7 @@ int cvg_find_homography(cvg_ctx* c, const float* src_xy, const float* dst_xy, in
 // ---- fused detect over a prepared train set --------------------------------------------------------
 static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, TrainSet& ts, const float* d_scales,
                          const cvg_detect_params* p, cvg_pair_result* per_pair, float* inlier_xy, int32_t* inlier_counts,
-                         bool host_needs_inliers)
+                         bool host_needs_inliers, bool guard = true)
 {
     const int S = ts.n_segs, V = m->n_views, nq = m->n_rows;
     const int P = S * V;
@@ -838,7 +788,7 @@ static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, Tra
     // batches have the same shape (same number of descriptors per scene) reuses the plan already on the device.
     std::vector<int> shape((size_t)S);
     for (int i = 0; i < S; i++) shape[(size_t)i] = ts.segs[(size_t)i].rows;
-    if (c->plan_models == m && c->plan_shape == shape && c->plan_units_n > 0) {
+    if (c->plan_models_uid == m->uid && c->plan_shape == shape && c->plan_units_n > 0) {
         n_units = c->plan_units_n; n_rb = (nq + TILE_M - 1) / TILE_M;
         d_units = c->plan_units.as<MatchUnit>(); d_dir = c->plan_dir.as<MergeEntry>();
     } else {
@@ -851,7 +801,7 @@ static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, Tra
         if (c->stage_fallback) CU_CHECK(cudaStreamSynchronize(c->stream));    // memcpy fallback: host vectors go out of scope
         n_units = (int)units.size();
         d_units = c->plan_units.as<MatchUnit>(); d_dir = c->plan_dir.as<MergeEntry>();
-        c->plan_models = m; c->plan_shape = shape; c->plan_units_n = n_units;
+        c->plan_models_uid = m->uid; c->plan_shape = shape; c->plan_units_n = n_units;
     }
     const size_t rows = (size_t)S * std::max(nq, 1);
     CU_CHECK(c->parts.ensure(std::max<size_t>(n_units, 1) * TILE_M * sizeof(Top2)));
@@ -868,7 +818,7 @@ static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, Tra
         c->launches++;
     }
     int rc = launch_match(c, q, ts, d_units, n_units, d_dir, n_rb, p->ratio, path, c->parts.as<Top2>(),
-                          c->idx.as<int32_t>(), c->dist.as<float>(), c->accept.as<uint8_t>());
+                          c->idx.as<int32_t>(), c->dist.as<float>(), c->accept.as<uint8_t>(), guard);
     if (rc) return rc;
     CompactWork cw;
     cw.n_segments = S; cw.n_views = V; cw.n_query = nq; cw.view_offsets = m->d_view_offsets;
@@ -928,7 +878,7 @@ static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, Tra
     return CVG_OK;
 }
 
-static int check_detect_params(const cvg_detect_params* p)
+int check_detect_params(const cvg_detect_params* p)
 {
     if (!p || p->size != sizeof(cvg_detect_params)) return set_err(CVG_ERR_INVALID, "cvg_detect_params: bad size field");
     return check_params(&p->ransac);
@@ -940,6 +890,7 @@ int cvg_detect_pairs(cvg_ctx* c, const cvg_models* m, const float* scene_desc, c
                      float scale, const cvg_detect_params* p, cvg_pair_result* per_view, float* inlier_scene_xy,
                      int32_t* inlier_offsets)
 {
+    c = cvg_primary(c); m = cvg_models_on(m, c);
     if (!c || !m || !per_view) return set_err(CVG_ERR_INVALID, "cvg_detect_pairs: NULL argument");
     int rc = check_detect_params(p);
     if (rc) return rc;
@@ -994,8 +945,12 @@ __global__ void u8_to_f32_kernel(const uchar4* __restrict__ in, float4* __restri
     }
 }
 
-static int scenes_upload_impl(cvg_ctx* c, const float* desc, const uint8_t* desc_u8, const float* kpt_xy,
-                              const int64_t* offsets, int n_scenes, cvg_scenes** out, bool async)
+}  // extern "C"
+
+// src_row0 (may be NULL): scene s is read from rows [src_row0[s], src_row0[s] + rows of s) of the caller's arrays instead
+// of rows [offsets[s], offsets[s + 1]) — a multi-device context hands every device its own, non-contiguous scenes.
+int eng_scenes_upload(cvg_ctx* c, const float* desc, const uint8_t* desc_u8, const float* kpt_xy,
+                      const int64_t* offsets, int n_scenes, cvg_scenes** out, bool async, const int64_t* src_row0)
 {
     if (!c || !out || !offsets || n_scenes < 0) return set_err(CVG_ERR_INVALID, "cvg_scenes_upload: bad argument");
     *out = nullptr;
@@ -1005,82 +960,83 @@ static int scenes_upload_impl(cvg_ctx* c, const float* desc, const uint8_t* desc
     const int64_t total = offsets[n_scenes];
     if (total > 0 && !desc && !desc_u8) return set_err(CVG_ERR_INVALID, "NULL desc");
     cvg_scenes* sc = new cvg_scenes();
+    sc->n_scenes_total = n_scenes;
+    sc->offsets_copy.assign(offsets, offsets + n_scenes + 1);   // the library's own copy: the caller's array may go away at once
     layout_segments(sc->ts, offsets, n_scenes);
     if (sc->ts.rows_pad_total > 0x7fffff00LL) { delete sc; return set_err(CVG_ERR_LIMIT, "scene batch too large (>2^31 padded rows)"); }
     cudaStream_t st = async ? c->copy_stream : c->stream;
-    CU_CHECK(c->pool.acquire(sc->f32, (size_t)std::max<int64_t>(total, 1) * DIM * 4));
-    CU_CHECK(c->pool.acquire(sc->kpt, (size_t)std::max<int64_t>(total, 1) * 8));
-    CU_CHECK(c->pool.acquire(sc->kptoff, (size_t)(n_scenes + 1) * 8 + 16));
-    sc->ts.d_f32 = sc->f32.as<float>(); sc->ts.d_kpt = sc->kpt.as<float>(); sc->ts.d_kpt_offsets = sc->kptoff.as<int64_t>();
-    sc->d_flag = reinterpret_cast<int*>(sc->kptoff.as<int64_t>() + (n_scenes + 1));
-    sc->ts.d_tnmax = sc->d_flag + 1;
-    if (total > 0 && desc_u8) {                                 // a quarter of the PCIe bytes; widened on the device
-        CU_CHECK(c->pool.acquire(sc->u8, (size_t)total * DIM));
-        CU_CHECK(cudaMemcpyAsync(sc->u8.p, desc_u8, (size_t)total * DIM, cudaMemcpyHostToDevice, st));
-        const size_t n4 = (size_t)total * DIM / 4;
-        u8_to_f32_kernel<<<(unsigned)std::min<size_t>((n4 + 255) / 256, (size_t)c->n_sms * 16), 256, 0, st>>>(
-            sc->u8.as<uchar4>(), reinterpret_cast<float4*>(sc->ts.d_f32), n4);
-        c->launches++;
-    } else if (total > 0) CU_CHECK(cudaMemcpyAsync(sc->ts.d_f32, desc, (size_t)total * DIM * 4, cudaMemcpyHostToDevice, st));
-    if (total > 0 && kpt_xy) CU_CHECK(cudaMemcpyAsync(sc->ts.d_kpt, kpt_xy, (size_t)total * 8, cudaMemcpyHostToDevice, st));
-    else if (total > 0) CU_CHECK(cudaMemsetAsync(sc->ts.d_kpt, 0, (size_t)total * 8, st));
-    CU_CHECK(cudaMemcpyAsync(sc->ts.d_kpt_offsets, offsets, (size_t)(n_scenes + 1) * 8, cudaMemcpyHostToDevice, st));
-    CU_CHECK(cudaMemsetAsync(sc->d_flag, 0, 8, st));
-    int rc = prep_train(c, sc->ts, sc->b, sc->blo, sc->aug, sc->segtab, 0, true, st, sc->d_flag);
-    if (rc) { cvg_scenes_free(c, sc); return rc; }
-    if (async) {
-        // the caller's buffers are read by the copy engine until `ready`; cvg_detect_scenes orders itself after it
-        CU_CHECK(cudaEventCreateWithFlags(&sc->ready, cudaEventDisableTiming));
-        CU_CHECK(cudaEventRecord(sc->ready, st));
-        sc->ts.nonint = -1;                            // the match path is decided on the device from d_flag
-    } else {
-        int flag = 0;
-        CU_CHECK(cudaMemcpyAsync(&flag, sc->d_flag, 4, cudaMemcpyDeviceToHost, st));
-        CU_CHECK(cudaStreamSynchronize(st));
-        sc->ts.nonint = flag;
-    }
+    const int rc = [&]() -> int {
+        CU_CHECK(c->pool.acquire(sc->f32, (size_t)std::max<int64_t>(total, 1) * DIM * 4));
+        CU_CHECK(c->pool.acquire(sc->kpt, (size_t)std::max<int64_t>(total, 1) * 8));
+        CU_CHECK(c->pool.acquire(sc->kptoff, (size_t)(n_scenes + 1) * 8 + 16));
+        sc->ts.d_f32 = sc->f32.as<float>(); sc->ts.d_kpt = sc->kpt.as<float>(); sc->ts.d_kpt_offsets = sc->kptoff.as<int64_t>();
+        sc->d_flag = reinterpret_cast<int*>(sc->kptoff.as<int64_t>() + (n_scenes + 1));
+        sc->ts.d_tnmax = sc->d_flag + 1;
+        // host -> device copies: one per array, or one per scene when the scenes are gathered from all over the caller's arrays
+        auto h2d_rows = [&](void* dst, const void* src, size_t row_bytes) -> int {
+            if (!src_row0) { CU_CHECK(cudaMemcpyAsync(dst, src, (size_t)total * row_bytes, cudaMemcpyHostToDevice, st)); return CVG_OK; }
+            for (int s2 = 0; s2 < n_scenes; s2++) {
+                const size_t rows = (size_t)(offsets[s2 + 1] - offsets[s2]);
+                if (rows) CU_CHECK(cudaMemcpyAsync((uint8_t*)dst + (size_t)offsets[s2] * row_bytes, (const uint8_t*)src + (size_t)src_row0[s2] * row_bytes,
+                                                   rows * row_bytes, cudaMemcpyHostToDevice, st));
+            }
+            return CVG_OK;
+        };
+        if (total > 0 && desc_u8) {                                 // a quarter of the PCIe bytes; widened on the device
+            CU_CHECK(c->pool.acquire(sc->u8, (size_t)total * DIM));
+            int r = h2d_rows(sc->u8.p, desc_u8, DIM);
+            if (r) return r;
+            const size_t n4 = (size_t)total * DIM / 4;
+            u8_to_f32_kernel<<<(unsigned)std::min<size_t>((n4 + 255) / 256, (size_t)c->n_sms * 16), 256, 0, st>>>(
+                sc->u8.as<uchar4>(), reinterpret_cast<float4*>(sc->ts.d_f32), n4);
+            c->launches++;
+        } else if (total > 0) { int r = h2d_rows(sc->ts.d_f32, desc, (size_t)DIM * 4); if (r) return r; }
+        if (total > 0 && kpt_xy) { int r = h2d_rows(sc->ts.d_kpt, kpt_xy, 8); if (r) return r; }
+        else if (total > 0) CU_CHECK(cudaMemsetAsync(sc->ts.d_kpt, 0, (size_t)total * 8, st));
+        CU_CHECK(cudaMemcpyAsync(sc->ts.d_kpt_offsets, sc->offsets_copy.data(), (size_t)(n_scenes + 1) * 8, cudaMemcpyHostToDevice, st));
+        CU_CHECK(cudaMemsetAsync(sc->d_flag, 0, 8, st));
+        int r = prep_train(c, sc->ts, sc->b, sc->blo, sc->aug, sc->segtab, 0, true, st, sc->d_flag);
+        if (r) return r;
+        if (async) {
+            // the caller's buffers are read by the copy engine until `ready`; cvg_detect_scenes orders itself after it
+            CU_CHECK(cudaEventCreateWithFlags(&sc->ready, cudaEventDisableTiming));
+            CU_CHECK(cudaEventRecord(sc->ready, st));
+            sc->ts.nonint = -1;                            // the match path is decided on the device from d_flag
+        } else {
+            int flag[2] = { 0, 0 };                        // row kinds, max ||t||^2 bits
+            CU_CHECK(cudaMemcpyAsync(flag, sc->d_flag, 8, cudaMemcpyDeviceToHost, st));
+            CU_CHECK(cudaStreamSynchronize(st));
+            sc->ts.nonint = flag[0];
+            memcpy(&sc->max_norm2, &flag[1], 4);
+        }
+        return CVG_OK;
+    }();
+    if (rc) { eng_scenes_free(c, sc); return rc; }
     *out = sc;
     return CVG_OK;
 }
 
-int cvg_scenes_upload(cvg_ctx* c, const float* desc, const float* kpt_xy, const int64_t* offsets, int n_scenes,
-                      cvg_scenes** out)
-{
-    return scenes_upload_impl(c, desc, nullptr, kpt_xy, offsets, n_scenes, out, false);
-}
-
-int cvg_scenes_upload_async(cvg_ctx* c, const float* desc, const float* kpt_xy, const int64_t* offsets, int n_scenes,
-                            cvg_scenes** out)
-{
-    return scenes_upload_impl(c, desc, nullptr, kpt_xy, offsets, n_scenes, out, true);
-}
-
-int cvg_scenes_upload_u8_async(cvg_ctx* c, const uint8_t* desc, const float* kpt_xy, const int64_t* offsets, int n_scenes,
-                               cvg_scenes** out)
-{
-    return scenes_upload_impl(c, nullptr, desc, kpt_xy, offsets, n_scenes, out, true);
-}
-
-int cvg_scenes_wait(cvg_ctx* c, cvg_scenes* sc)
+int eng_scenes_wait(cvg_ctx* c, cvg_scenes* sc)
 {
     if (!c || !sc) return set_err(CVG_ERR_INVALID, "cvg_scenes_wait: NULL argument");
     if (!sc->ready) return CVG_OK;
     CU_CHECK(cudaSetDevice(c->device));
     CU_CHECK(cudaEventSynchronize(sc->ready));
     if (sc->ts.nonint < 0) {
-        int flag = 0;
-        CU_CHECK(cudaMemcpy(&flag, sc->d_flag, 4, cudaMemcpyDeviceToHost));
-        sc->ts.nonint = flag;
+        int flag[2] = { 0, 0 };
+        CU_CHECK(cudaMemcpy(flag, sc->d_flag, 8, cudaMemcpyDeviceToHost));
+        sc->ts.nonint = flag[0];
+        memcpy(&sc->max_norm2, &flag[1], 4);
     }
     return CVG_OK;
 }
 
-void cvg_scenes_free(cvg_ctx* c, cvg_scenes* sc)
+void eng_scenes_free(cvg_ctx* c, cvg_scenes* sc)
 {
     if (!sc) return;
+    if (c) cudaSetDevice(c->device);
     if (sc->ready) { cudaEventSynchronize(sc->ready); cudaEventDestroy(sc->ready); sc->ready = nullptr; }
     if (c) {
-        cudaSetDevice(c->device);
         DevBuf* bufs[] = { &sc->f32, &sc->b, &sc->blo, &sc->aug, &sc->kpt, &sc->kptoff, &sc->u8, &sc->segtab };
         for (DevBuf* b : bufs) c->pool.release(*b);
     } else {
@@ -1089,57 +1045,50 @@ void cvg_scenes_free(cvg_ctx* c, cvg_scenes* sc)
     delete sc;
 }
 
-int cvg_detect_scenes_inliers(cvg_ctx* c, const cvg_models* m, const cvg_scenes* scenes, const float* scales,
-                              const cvg_detect_params* p, cvg_pair_result* per_pair, float* inlier_scene_xy,
-                              int64_t* inlier_offsets)
+// Scenes [s0, s1) of a resident batch on engine `c` (the context itself, or one of its lanes: same device, own stream
+// and scratch).  The sub-batch is a VIEW of the batch's train set: same device arrays, a slice of the segment list.
+int eng_detect_range(cvg_ctx* c, const cvg_models* m, cvg_scenes* sc, int s0, int s1, const float* scales,
+                     const cvg_detect_params* p, cvg_pair_result* per_pair, std::vector<float>* pool, std::vector<int32_t>* cnt)
 {
-    if (!c || !m || !scenes || !per_pair) return set_err(CVG_ERR_INVALID, "cvg_detect_scenes: NULL argument");
-    int rc = check_detect_params(p);
-    if (rc) return rc;
+    if (!c || !m || !sc || !per_pair) return set_err(CVG_ERR_INVALID, "cvg_detect_scenes: NULL argument");
+    if (s0 < 0 || s1 > sc->ts.n_segs || s0 > s1) return set_err(CVG_ERR_INVALID, "cvg_detect_scenes: bad scene range");
     CU_CHECK(cudaSetDevice(c->device));
-    cvg_scenes* sc = const_cast<cvg_scenes*>(scenes);
-    const int S = sc->ts.n_segs, V = m->n_views;
-    c->stage_used = 0; c->stage_fallback = false;       // previous call has completed (calls are synchronous)
+    const int S = s1 - s0, V = m->n_views;
+    if (S * V == 0) return CVG_OK;
+    c->stage_used = 0; c->stage_fallback = false;       // the engine's previous call has completed (calls are synchronous)
     if (sc->ready) CU_CHECK(cudaStreamWaitEvent(c->stream, sc->ready, 0));
     const float* d_scales = nullptr;
-    if (scales && S * V > 0) {
+    if (scales) {
         std::vector<float> ps((size_t)S * V);
-        for (int s = 0; s < S; s++) for (int v = 0; v < V; v++) ps[(size_t)s * V + v] = scales[s];
+        for (int s = 0; s < S; s++) for (int v = 0; v < V; v++) ps[(size_t)s * V + v] = scales[s0 + s];
         CU_CHECK(c->scales.ensure(ps.size() * 4 + 16));
         CU_CHECK(h2d_small(c, c->scales.p, ps.data(), ps.size() * 4));
         if (c->stage_fallback) CU_CHECK(cudaStreamSynchronize(c->stream));
         d_scales = c->scales.as<float>();
     }
-    const bool want_inl = inlier_scene_xy != nullptr && inlier_offsets != nullptr;
-    if (!want_inl) return detect_common(c, m, sc, sc->ts, d_scales, p, per_pair, nullptr, nullptr, false);
-    // the device pool has one slot range per (scene, view) at scene * n_rows + view offset; pack it pair after pair
-    const size_t rows = (size_t)S * std::max(m->n_rows, 1);
-    std::vector<float> pool(rows * 2); std::vector<int32_t> cnt((size_t)std::max(S * V, 1));
-    rc = detect_common(c, m, sc, sc->ts, d_scales, p, per_pair, pool.data(), cnt.data(), true);
-    if (rc) return rc;
-    int64_t o = 0;
-    for (int s = 0; s < S; s++)
-        for (int v = 0; v < V; v++) {
-            const size_t pair = (size_t)s * V + v;
-            inlier_offsets[pair] = o;
-            const size_t start = (size_t)s * m->n_rows + (size_t)m->view_offsets[v];
-            memcpy(inlier_scene_xy + 2 * (size_t)o, pool.data() + 2 * start, (size_t)cnt[pair] * 8);
-            o += cnt[pair];
-        }
-    inlier_offsets[(size_t)S * V] = o;
-    return CVG_OK;
+    TrainSet view = sc->ts;                              // device pointers shared; rows_pad_total stays (TMA map bounds)
+    if (S != sc->ts.n_segs) {
+        view.segs.assign(sc->ts.segs.begin() + s0, sc->ts.segs.begin() + s1);
+        view.n_segs = S;
+        view.d_kpt_offsets = sc->ts.d_kpt_offsets + s0;
+        view.max_rows = 0;
+        for (const SegInfo& g : view.segs) view.max_rows = std::max(view.max_rows, g.rows);
+    }
+    const bool want_inl = pool != nullptr && cnt != nullptr;
+    if (want_inl) { pool->resize((size_t)S * std::max(m->n_rows, 1) * 2); cnt->resize((size_t)S * V); }
+    // d >= 2048 needs ||q|| + ||t|| >= 2048: with both norms known on the host the guard kernels are not even enqueued
+    const bool safe = sc->max_norm2 >= 0.f && sqrt((double)m->max_norm2) + sqrt((double)sc->max_norm2) < 2047.0;
+    return detect_common(c, m, sc, view, d_scales, p, per_pair, want_inl ? pool->data() : nullptr,
+                         want_inl ? cnt->data() : nullptr, want_inl, !safe);
 }
 
-int cvg_detect_scenes(cvg_ctx* c, const cvg_models* m, const cvg_scenes* scenes, const float* scales,
-                      const cvg_detect_params* p, cvg_pair_result* per_pair)
-{
-    return cvg_detect_scenes_inliers(c, m, scenes, scales, p, per_pair, nullptr, nullptr);
-}
+extern "C" {
 
 // ---- device-pointer building blocks -----------------------------------------------------------------
 int cvg_dev_match_top2(cvg_ctx* c, void* stream, const float* query_dev, int n_query, const float* train_dev,
                        int n_train, int32_t train_index_base, float* dist_dev, int32_t* idx_dev)
 {
+    c = cvg_primary(c);
     if (!c || n_query < 0 || n_train < 0) return set_err(CVG_ERR_INVALID, "cvg_dev_match_top2: bad argument");
     if (n_query == 0) return CVG_OK;
     CU_CHECK(cudaSetDevice(c->device));
@@ -1191,6 +1140,7 @@ int cvg_dev_match_top2(cvg_ctx* c, void* stream, const float* query_dev, int n_q
 int cvg_dev_merge_top2(cvg_ctx* c, void* stream, const float* dist_parts_dev, const int32_t* idx_parts_dev, int n_parts,
                        int n_query, float ratio, int32_t* idx_dev, float* dist_dev, uint8_t* accept_dev)
 {
+    c = cvg_primary(c);
     if (!c || n_parts < 1 || n_query < 0) return set_err(CVG_ERR_INVALID, "cvg_dev_merge_top2: bad argument");
     CU_CHECK(cudaSetDevice(c->device));
     launch_merge_parts(dist_parts_dev, idx_parts_dev, n_parts, n_query, ratio, idx_dev, dist_dev, accept_dev,

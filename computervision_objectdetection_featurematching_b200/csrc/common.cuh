@@ -74,6 +74,8 @@ struct TcOperands {
     const __nv_bfloat16* Qlo; const __nv_bfloat16* Tlo;      // lo halves of the split operands (candidate path), or NULL
 };
 int  tc_init(char* err, size_t errlen);     // resolves cuTensorMapEncodeTiled; 0 = ok
+int  tc_set_device_attrs(char* err, size_t errlen);       // dynamic shared memory opt-in on the CURRENT device
+int  ransac_set_device_attrs(char* err, size_t errlen);   // same for the verify kernels
 // candidates = 2: exact top-2 (Top2 parts[n_units][128]); 4: candidate records (Top4 parts[n_units][4][128]).
 // gate_flag (device, may be NULL): the kernel runs only if *gate_flag == gate_want.
 // paired: the unit list is made of pairs (2p, 2p + 1) with the same train tiles (build_plan with an even number of row
@@ -86,7 +88,13 @@ bool tc_pair_mode_enabled();                 // CVG_TC_PAIR=1: pair mode for eve
 // merge.cu (in match_exact.cu)
 void launch_merge(const Top2* parts, const MergeEntry* dir, int n_segments, int n_rowblocks, int n_query,
                   float ratio, int32_t* idx, float* dist, uint8_t* accept,
-                  const int* gate_flag /*skipped if *flag == gate_skip, or NULL*/, int gate_skip, cudaStream_t st);
+                  const int* gate_flag /*skipped if *flag == gate_skip, or NULL*/, int gate_skip, cudaStream_t st,
+                  int* fb_count = nullptr /*guard: rows whose second distance is >= 2048 go to fb_list instead*/,
+                  int2* fb_list = nullptr);
+void launch_fallback_exact(const int* fb_count, const int2* fb_list, unsigned long long* fb_keys, const SegDev* segs,
+                           int n_segments, int n_query, int max_seg_rows, float ratio, const float* Q, int q_row_begin,
+                           const float* T, int32_t* idx, float* dist, uint8_t* accept, const int* gate_flag, int gate_want,
+                           int n_sms, cudaStream_t st);
 // candidate path: merge of Top4 records, fp32 re-rank with proof, exact fallback for the unproven rows
 void launch_merge4_rerank(const Top4* parts4, const MergeEntry* dir, const SegDev* segs, int n_segments, int n_rowblocks,
                           int n_query, int max_seg_rows, float ratio, const float* Q, int q_row_begin, const float* T,
@@ -104,6 +112,8 @@ struct RansacWork {
     const int64_t* starts;      // [P] first pool row of set k
     const int32_t* counts_n;    // [P] number of correspondences of set k
     int n_sets;
+    int n_sms;                  // SMs of the device the work runs on
+    int wave_div;               // engines sharing the GPU (>= 1): rounds are sized to 1 / wave_div of a wave
     int max_n;                  // upper bound of counts_n (host-known; sizes nothing, tunes launches)
     int max_iters;
     float thr2;                 // (float)(thr*thr)

@@ -109,10 +109,17 @@ __device__ __forceinline__ void top2_emit(float d1, int i1, float d2, int i2, fl
 }
 
 // one thread per (segment, query row)
+// Guard (fb_count != NULL): the tensor-core kernel orders a unit's columns by d^2, OpenCV by sqrtf(d^2).  The two orders
+// agree while distinct integer d^2 keep distinct float distances, i.e. below d = 2048 (ulp(2048) = 2^-12 = 1/(2 d)); from
+// there on neighbouring d^2 collapse into one float and OpenCV's tie rule (lower train index) can pick another column.
+// If the row's merged second distance is below 2048 both of its columns are the global top two in either order (every
+// column with d^2 >= 2^22 has a float distance >= 2048); otherwise the row is redone by the exact fallback kernels,
+// which compare rounded distances like cv::batchDistance does.
 __global__ void merge_kernel(const Top2* __restrict__ parts, const MergeEntry* __restrict__ dir,
                              int n_segments, int n_rowblocks, int n_query, float ratio,
                              int32_t* __restrict__ idx, float* __restrict__ dist, uint8_t* __restrict__ accept,
-                             const int* __restrict__ gate_flag, int gate_skip)
+                             const int* __restrict__ gate_flag, int gate_skip, int* __restrict__ fb_count,
+                             int2* __restrict__ fb_list)
 {
     if (gate_flag && *gate_flag == gate_skip) return;          // the candidate path writes the results instead
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -126,17 +133,23 @@ __global__ void merge_kernel(const Top2* __restrict__ parts, const MergeEntry* _
         top2_insert(d1, i1, d2, i2, p.d1, p.i1);
         top2_insert(d1, i1, d2, i2, p.d2, p.i2);
     }
+    if (fb_count && i2 >= 0 && d2 >= 2048.f) {
+        const int slot = atomicAdd(fb_count, 1);
+        fb_list[slot] = make_int2(seg, row);
+        return;
+    }
     top2_emit(d1, i1, d2, i2, ratio, (size_t)gid, idx, dist, accept);
 }
 
 void launch_merge(const Top2* parts, const MergeEntry* dir, int n_segments, int n_rowblocks, int n_query,
                   float ratio, int32_t* idx, float* dist, uint8_t* accept, const int* gate_flag, int gate_skip,
-                  cudaStream_t st)
+                  cudaStream_t st, int* fb_count, int2* fb_list)
 {
     const int64_t n = (int64_t)n_segments * n_query;
     if (n <= 0) return;
+    if (fb_count) cudaMemsetAsync(fb_count, 0, 4, st);
     merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(parts, dir, n_segments, n_rowblocks, n_query,
-                                                              ratio, idx, dist, accept, gate_flag, gate_skip);
+                                                              ratio, idx, dist, accept, gate_flag, gate_skip, fb_count, fb_list);
 }
 
 // ---- candidate path (non-integer descriptors): fp32 re-rank with a proof, exact fallback ------------
@@ -337,6 +350,19 @@ void launch_merge4_rerank(const Top4* parts4, const MergeEntry* dir, const SegDe
     merge4_rerank_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(parts4, dir, segs, n_segments, n_rowblocks, n_query, ratio,
                                                                       Q, q_row_begin, T, qnorm, tnmax_bits, idx, dist, accept,
                                                                       fb_count, fb_list, gate_flag, gate_want);
+    launch_fallback_exact(fb_count, fb_list, fb_keys, segs, n_segments, n_query, max_seg_rows, ratio, Q, q_row_begin, T, idx, dist,
+                          accept, gate_flag, gate_want, n_sms, st);
+}
+
+// exact top-2 (cv::batchDistance arithmetic and order) of the *fb_count rows listed in fb_list: 4 launches, all empty loops
+// when the list is empty
+void launch_fallback_exact(const int* fb_count, const int2* fb_list, unsigned long long* fb_keys, const SegDev* segs,
+                           int n_segments, int n_query, int max_seg_rows, float ratio, const float* Q, int q_row_begin,
+                           const float* T, int32_t* idx, float* dist, uint8_t* accept, const int* gate_flag, int gate_want,
+                           int n_sms, cudaStream_t st)
+{
+    const int64_t n = (int64_t)n_segments * n_query;
+    if (n <= 0) return;
     unsigned long long* g1 = fb_keys; unsigned long long* g2 = fb_keys + n;
     const int chunks = (max_seg_rows + FB_CHUNK - 1) / FB_CHUNK;
     fallback_init_kernel<<<n_sms, 256, 0, st>>>(fb_count, g1, g2, gate_flag, gate_want);

@@ -26,6 +26,7 @@
 #include <cuda.h>
 #include <string.h>
 #include <stdlib.h>
+#include <mutex>
 
 namespace cvg {
 
@@ -628,6 +629,8 @@ static EncodeTiledFn g_encode = nullptr;
 
 int tc_init(char* err, size_t errlen)
 {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> g(mu);
     if (g_encode) return 0;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -637,14 +640,20 @@ int tc_init(char* err, size_t errlen)
         return 1;
     }
     g_encode = (EncodeTiledFn)fn;
-    e = cudaFuncSetAttribute(match_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+    return 0;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a function: called once for every device a
+// context is created on (api.cu, under its own mutex), with that device current.
+int tc_set_device_attrs(char* err, size_t errlen)
+{
+    cudaError_t e = cudaFuncSetAttribute(match_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(match_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(match_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
     if (e != cudaSuccess) {
         snprintf(err, errlen, "cudaFuncSetAttribute(match_tc_kernel): %s", cudaGetErrorString(e));
-        g_encode = nullptr;
         return 1;
     }
     return 0;

@@ -1493,30 +1493,34 @@ int launch_selftest_rcp(unsigned long long* d_mismatches, cudaStream_t st)
     return 1;
 }
 
+int ransac_set_device_attrs(char* err, size_t errlen)
+{
+    cudaError_t e = cudaFuncSetAttribute(ransac_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HYP_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ransac_hyp_g8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HYPG_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(ransac_hyp_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HYPT_SMEM);
+    if (e != cudaSuccess) { snprintf(err, errlen, "cudaFuncSetAttribute(ransac kernels): %s", cudaGetErrorString(e)); return 1; }
+    return 0;
+}
+
 int launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events, int* n_hyp_rounds)
 {
     if (n_hyp_rounds) *n_hyp_rounds = 0;
     if (w.n_sets <= 0) return 0;
     int launches = 1;
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(ransac_hyp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HYP_SMEM);
-        cudaFuncSetAttribute(ransac_hyp_g8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HYPG_SMEM);
-        cudaFuncSetAttribute(ransac_hyp_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HYPT_SMEM);
-        attr_set = true;
-    }
     // Hypotheses are solved and scored in rounds; after each round the serial selection scan advances, so rounds
     // beyond the adaptive stop (RANSACUpdateNumIters) cost one early exit per warp.  A round is a latency-bound
     // launch (~135 dependent rotations per matrix whatever the kernel), so it is made long enough to fill the chip:
     // at least 256 iterations per set, and n_sets x round_len >= one full wave of the thread-per-hypothesis kernel.
     static const int hyp_mode = getenv("CVG_HYP_MODE") ? atoi(getenv("CVG_HYP_MODE")) : 0;   // experiments: 1 warp, 2 g8, 3 thread (generic), 4 thread
     static const int round_env = getenv("CVG_ROUND_LEN") ? atoi(getenv("CVG_ROUND_LEN")) : 0;
-    static int n_sms = 0;
-    if (!n_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev); if (n_sms <= 0) n_sms = 148; }
+    const int n_sms = w.n_sms > 0 ? w.n_sms : 148;
     int round_len = w.max_iters;
     if (!(w.flags & CVG_RANSAC_NO_EARLY_STOP)) {
-        const int64_t wave = (int64_t)n_sms * HYPT_THREADS * HYPT_CTAS_PER_SM;
+        // wave_div engines share the GPU (lanes of one context working on sub-batches of a call): each sizes its rounds
+        // to its share, so that the sum of the concurrent rounds is still one wave and no lane solves hypotheses far
+        // beyond its sets' adaptive stop
+        const int64_t wave = (int64_t)n_sms * HYPT_THREADS * HYPT_CTAS_PER_SM / std::max(1, w.wave_div);
         int64_t fill = wave / w.n_sets / 32 * 32;              // rounded down: n_sets x round_len must not spill into a second wave
         if (fill < 256) {
             // many sets: a round of 256 iterations is several waves; make it a whole number of them (13 350 real pairs in

@@ -34,6 +34,27 @@ def planted_pair(rng, nq, nt, p_match=0.5, sigma=12.0, dim=128):
     return q, t, truth
 
 
+def saturated_pair(rng, nq, nt, dim=128):
+    """u8-range rows far apart (queries near 0, train near 250): every distance is above 2048, where neighbouring integer
+    d^2 round to the same float and cv::BFMatcher's tie rule (lower train index) decides — the regime in which ordering
+    by d^2 and ordering by sqrtf(d^2) differ.  Half of the queries own a planted pair of train rows that are their two
+    nearest (the rows dip to 130 on the query's 8 signature coordinates) and whose d^2 differ by exactly 1, the larger
+    d^2 at the LOWER train index: OpenCV returns that one first whenever the two float distances collide (~12 %)."""
+    q = rng.integers(0, 4, size=(nq, dim)).astype(np.float32)
+    t = rng.integers(244, 256, size=(nt, dim)).astype(np.float32)
+    q[:, dim - 1] = 5
+    slots = rng.permutation(nt // 2)[: nq // 2]
+    for i, lo in enumerate(slots):
+        hi = nt // 2 + int(lo)
+        sig = rng.permutation(dim - 1)[:8]
+        q[i, sig] = 20
+        row = 250.0 - rng.integers(0, 6, size=dim).astype(np.float32)
+        row[sig] = 130
+        t[hi] = row; t[hi, dim - 1] = 5                    # last coordinate: difference 0
+        t[lo] = row; t[lo, dim - 1] = 6                    # difference 1 -> d^2 larger by exactly 1
+    return q, t
+
+
 def random_homography(rng):
     return np.array([[1 + rng.normal(0, .1), rng.normal(0, .1), rng.normal(0, 30)],
                      [rng.normal(0, .1), 1 + rng.normal(0, .1), rng.normal(0, 30)],

@@ -125,63 +125,135 @@ std::vector<Rect> mergeBoxes(const std::vector<Rect>& boxes, float merge_distanc
     return merged;
 }
 
-// All scaled versions of one test image as one streaming batch (copy + conversion on the copy stream).
-cvg_scenes* uploadScales(cvg_ctx* ctx, const std::vector<ScaledScene>& scales)
+// Page-locked staging buffers for the streaming uploads: a per-thread free list; a buffer belongs to the batch that is
+// reading it (ImageJob / the caller of uploadScales) until that batch has been consumed, so nothing in flight is reused.
+namespace {
+struct Pinned { float* p = nullptr; size_t cap = 0; };
+thread_local std::vector<Pinned> g_free_pinned;
+
+Pinned takePinned(size_t n)
+{
+    size_t best = g_free_pinned.size();
+    for (size_t i = 0; i < g_free_pinned.size(); ++i)
+        if (g_free_pinned[i].cap >= n && (best == g_free_pinned.size() || g_free_pinned[i].cap < g_free_pinned[best].cap)) best = i;
+    if (best < g_free_pinned.size()) { Pinned b = g_free_pinned[best]; g_free_pinned.erase(g_free_pinned.begin() + (long)best); return b; }
+    Pinned b; b.cap = n + n / 4 + 256;
+    b.p = (float*)cvg_host_alloc(b.cap * sizeof(float));
+    if (!b.p) throw std::runtime_error("cvg_host_alloc failed");
+    return b;
+}
+void givePinned(Pinned b)
+{
+    if (!b.p) return;
+    if (g_free_pinned.size() >= 32) { cvg_host_free(b.p); return; }
+    g_free_pinned.push_back(b);
+}
+}  // namespace
+
+struct ImageJob {
+    cvg_ctx* ctx = nullptr; const cvg_models* resident = nullptr;
+    cvg_scenes* batch = nullptr; cvg_job* job = nullptr; bool own_batch = true;
+    Pinned desc, kpt;
+    int S = 0, V = 0, N = 0;
+    std::vector<float> sc; std::vector<cvg_pair_result> res; std::vector<float> inl; std::vector<int64_t> off;
+};
+
+static cvg_scenes* uploadInto(cvg_ctx* ctx, const std::vector<ScaledScene>& scales, Pinned& desc, Pinned& kpt)
 {
     std::vector<int64_t> offsets(1, 0);
     size_t total = 0;
     for (const ScaledScene& s : scales) { total += (size_t)s.n; offsets.push_back((int64_t)total); }
-    // the upload is asynchronous: it reads these page-locked staging buffers until the batch has been consumed, so they
-    // live in a ring (grow-only, per thread)
-    struct Pinned { float* p = nullptr; size_t cap = 0;
-                    float* get(size_t n) { if (n > cap) { cvg_host_free(p); cap = n + n / 4; p = (float*)cvg_host_alloc(cap * sizeof(float)); } return p; } };
-    static thread_local Pinned ring_desc[4], ring_kpt[4];
-    static thread_local int ring_pos = 0;
-    float* desc = ring_desc[ring_pos].get(std::max<size_t>(total, 1) * 128);
-    float* kpt = ring_kpt[ring_pos].get(std::max<size_t>(total, 1) * 2);
-    if (!desc || !kpt) throw std::runtime_error("cvg_host_alloc failed");
-    ring_pos = (ring_pos + 1) % 4;
+    desc = takePinned(std::max<size_t>(total, 1) * 128);
+    kpt = takePinned(std::max<size_t>(total, 1) * 2);
     size_t row = 0;
     for (const ScaledScene& s : scales) {
-        std::copy(s.desc, s.desc + (size_t)s.n * 128, desc + row * 128);
-        std::copy(s.kpt_xy, s.kpt_xy + (size_t)s.n * 2, kpt + row * 2);
+        std::copy(s.desc, s.desc + (size_t)s.n * 128, desc.p + row * 128);
+        std::copy(s.kpt_xy, s.kpt_xy + (size_t)s.n * 2, kpt.p + row * 2);
         row += (size_t)s.n;
     }
-    cvg_scenes* batch = nullptr;
-    if (cvg_scenes_upload_async(ctx, desc, kpt, offsets.data(), (int)scales.size(), &batch) != CVG_OK)
+    cvg_scenes* batch = nullptr;      // the library copies `offsets` during the call; desc / kpt are read until the batch is consumed
+    if (cvg_scenes_upload_async(ctx, desc.p, kpt.p, offsets.data(), (int)scales.size(), &batch) != CVG_OK)
         throw std::runtime_error(std::string("cvg_scenes_upload_async: ") + cvg_last_error());
     return batch;
 }
 
-std::vector<std::pair<Rect, std::string>> detectObjects(cvg_ctx* ctx, const cvg_models* resident,
-                                                        const std::vector<ObjectModel>& models,
-                                                        const std::vector<ScaledScene>& scales,
-                                                        const cvg_detect_params& params, const DetectConstants& k,
-                                                        std::vector<cvg_pair_result>* per_pair_out, cvg_scenes* prepared)
+// All scaled versions of one test image as one streaming batch (copy + conversion on the copy stream).  The staging
+// buffers of a batch uploaded this way go back to the free list only when the thread exits its next finishImage /
+// detectObjects on that batch; here they are parked on the batch through a side table.
+namespace { thread_local std::vector<std::pair<cvg_scenes*, std::pair<Pinned, Pinned>>> g_parked; }
+
+cvg_scenes* uploadScales(cvg_ctx* ctx, const std::vector<ScaledScene>& scales)
 {
-    const int V = cvg_models_num_views(resident);
-    const int N = cvg_models_num_rows(resident);
-    const int S = (int)scales.size();
+    Pinned d, k;
+    cvg_scenes* batch = uploadInto(ctx, scales, d, k);
+    g_parked.push_back({ batch, { d, k } });
+    return batch;
+}
+
+static void unpark(cvg_scenes* batch)
+{
+    for (size_t i = 0; i < g_parked.size(); ++i)
+        if (g_parked[i].first == batch) {
+            givePinned(g_parked[i].second.first); givePinned(g_parked[i].second.second);
+            g_parked.erase(g_parked.begin() + (long)i);
+            return;
+        }
+}
+
+static ImageJob* startImage(cvg_ctx* ctx, const cvg_models* resident, const std::vector<ScaledScene>& scales,
+                            const cvg_detect_params& params, cvg_scenes* prepared, bool async)
+{
+    ImageJob* j = new ImageJob();
+    j->ctx = ctx; j->resident = resident;
+    j->V = cvg_models_num_views(resident); j->N = cvg_models_num_rows(resident); j->S = (int)scales.size();
     // The reference recomputes every scaled scene per model (:99-106 inside the model loop) and matches only that
     // model's views; the pairs are independent, so ONE fused call covers all scales x all views of all models.
-    cvg_scenes* batch = prepared;
-    if (!batch) batch = uploadScales(ctx, scales);
-    std::vector<float> sc(S);
-    for (int s = 0; s < S; ++s) sc[(size_t)s] = scales[(size_t)s].scale;
-    std::vector<cvg_pair_result> res((size_t)S * V);
-    std::vector<float> inl(2 * (size_t)S * (size_t)std::max(N, 1));
-    std::vector<int64_t> off((size_t)S * V + 1);
-    const int rc = cvg_detect_scenes_inliers(ctx, resident, batch, sc.data(), &params, res.data(), inl.data(), off.data());
-    cvg_scenes_free(ctx, batch);
-    if (rc != CVG_OK) throw std::runtime_error(std::string("cvg_detect_scenes_inliers: ") + cvg_last_error());
-    if (per_pair_out) per_pair_out->insert(per_pair_out->end(), res.begin(), res.end());
+    try {
+        j->batch = prepared ? prepared : uploadInto(ctx, scales, j->desc, j->kpt);
+    } catch (...) { delete j; throw; }
+    j->sc.resize((size_t)j->S);
+    for (int s = 0; s < j->S; ++s) j->sc[(size_t)s] = scales[(size_t)s].scale;
+    j->res.resize((size_t)j->S * j->V);
+    j->inl.resize(2 * (size_t)j->S * (size_t)std::max(j->N, 1));
+    j->off.resize((size_t)j->S * j->V + 1);
+    // async: enqueue and return; else the synchronous call (which splits the batch over the context's lanes itself)
+    const int rc = async ? cvg_detect_scenes_submit(ctx, resident, j->batch, j->sc.data(), &params, j->res.data(), j->inl.data(),
+                                                    j->off.data(), &j->job)
+                         : cvg_detect_scenes_inliers(ctx, resident, j->batch, j->sc.data(), &params, j->res.data(), j->inl.data(),
+                                                     j->off.data());
+    if (rc != CVG_OK) {
+        const std::string msg = std::string("cvg_detect_scenes: ") + cvg_last_error();
+        cvg_scenes_free(ctx, j->batch); unpark(j->batch); givePinned(j->desc); givePinned(j->kpt);
+        delete j;
+        throw std::runtime_error(msg);
+    }
+    return j;
+}
+
+ImageJob* submitImage(cvg_ctx* ctx, const cvg_models* resident, const std::vector<ScaledScene>& scales,
+                      const cvg_detect_params& params, cvg_scenes* prepared)
+{
+    return startImage(ctx, resident, scales, params, prepared, true);
+}
+
+std::vector<std::pair<Rect, std::string>> finishImage(ImageJob* j, const std::vector<ObjectModel>& models,
+                                                      const DetectConstants& k, std::vector<cvg_pair_result>* per_pair_out)
+{
+    const int rc = j->job ? cvg_job_wait(j->ctx, j->job) : CVG_OK;
+    const std::string msg = rc != CVG_OK ? std::string("cvg_job_wait: ") + cvg_last_error() : std::string();
+    cvg_scenes_free(j->ctx, j->batch);
+    unpark(j->batch); givePinned(j->desc); givePinned(j->kpt);
+    if (rc != CVG_OK) { delete j; throw std::runtime_error(msg); }
+    const int S = j->S, V = j->V;
+    const std::vector<float>& inl = j->inl; const std::vector<int64_t>& off = j->off;
+    if (per_pair_out) per_pair_out->insert(per_pair_out->end(), j->res.begin(), j->res.end());
     std::vector<std::pair<Rect, std::string>> detections;
     for (const ObjectModel& model : models) {
         std::vector<Point2f> scenePts;                                     // allUnfilteredScenePts
         for (int s = 0; s < S; ++s)
             for (int v = model.first_view; v < model.first_view + model.n_views; ++v)
-                for (int64_t j = off[(size_t)s * V + v]; j < off[(size_t)s * V + v + 1]; ++j)
-                    scenePts.push_back(Point2f{ inl[2 * (size_t)j], inl[2 * (size_t)j + 1] });
+                for (int64_t q = off[(size_t)s * V + v]; q < off[(size_t)s * V + v + 1]; ++q)
+                    scenePts.push_back(Point2f{ inl[2 * (size_t)q], inl[2 * (size_t)q + 1] });
         if (scenePts.empty()) continue;
         const auto clusters = clusterPoints(scenePts, k.cluster_distance, k.min_points_per_cluster);
         if (clusters.empty()) continue;
@@ -192,7 +264,17 @@ std::vector<std::pair<Rect, std::string>> detectObjects(cvg_ctx* ctx, const cvg_
             detections.emplace_back(b, model.name);
         }
     }
+    delete j;
     return detections;
+}
+
+std::vector<std::pair<Rect, std::string>> detectObjects(cvg_ctx* ctx, const cvg_models* resident,
+                                                        const std::vector<ObjectModel>& models,
+                                                        const std::vector<ScaledScene>& scales,
+                                                        const cvg_detect_params& params, const DetectConstants& k,
+                                                        std::vector<cvg_pair_result>* per_pair_out, cvg_scenes* prepared)
+{
+    return finishImage(startImage(ctx, resident, scales, params, prepared, false), models, k, per_pair_out);
 }
 
 bool saveDetections(const std::string& path, const std::vector<std::pair<Rect, std::string>>& detections)

@@ -46,10 +46,22 @@ std::vector<std::pair<Rect, std::string>> detectObjects(cvg_ctx* ctx, const cvg_
                                                         std::vector<cvg_pair_result>* per_pair_out = nullptr,
                                                         cvg_scenes* prepared = nullptr);
 
-// Streaming upload of an image's scaled scenes (cvg_scenes_upload_async); hand the batch to detectObjects as
-// `prepared` so that the next image's upload overlaps this image's detection (the loop of src/Output.cpp:27-47).
-// At most 4 batches may be in flight per thread (the host staging ring).
+// Streaming upload of an image's scaled scenes (cvg_scenes_upload_async); hand the batch to detectObjects /
+// submitImage as `prepared` so that the next image's upload overlaps this image's detection (the loop of
+// src/Output.cpp:27-47).  The page-locked staging buffers of a batch stay with it until it has been consumed.
 cvg_scenes* uploadScales(cvg_ctx* ctx, const std::vector<ScaledScene>& scales);
+
+// detectObjects in two halves for a caller that walks a list of test images on ONE thread (src/Output.cpp:27-47):
+// submitImage uploads the scaled scenes and enqueues the fused call (cvg_detect_scenes_submit) without waiting;
+// finishImage waits for it and runs the consumer.  Keeping two or three images in flight lets the GPU overlap one
+// image's refit/LM kernel with the next image's match and hypothesis kernels, and, on a cvg_create_multi context,
+// spreads the images over the GPUs.  Submit and finish on the same thread.
+struct ImageJob;
+ImageJob* submitImage(cvg_ctx* ctx, const cvg_models* resident, const std::vector<ScaledScene>& scales,
+                      const cvg_detect_params& params, cvg_scenes* prepared = nullptr);
+std::vector<std::pair<Rect, std::string>> finishImage(ImageJob* job, const std::vector<ObjectModel>& models,
+                                                      const DetectConstants& k = DetectConstants(),
+                                                      std::vector<cvg_pair_result>* per_pair_out = nullptr);
 
 // consumer stages, exposed for the tests
 std::vector<std::vector<Point2f>> clusterPoints(const std::vector<Point2f>& pts, float max_dist, int min_points);

@@ -67,6 +67,7 @@ enum {
 typedef struct cvg_ctx cvg_ctx;
 typedef struct cvg_models cvg_models;   /* resident model-view descriptor set                        */
 typedef struct cvg_scenes cvg_scenes;   /* resident batch of scene descriptor sets (bench / multi-GPU)*/
+typedef struct cvg_job cvg_job;         /* a fused call in flight (cvg_detect_scenes_submit)         */
 
 /* findHomography(..., RANSAC, threshold, mask, maxIters, confidence) — src/TestsDetector.cpp:23,78 */
 typedef struct cvg_ransac_params {
@@ -103,7 +104,26 @@ void cvg_detect_params_default(cvg_detect_params* p);
 
 /* ---- context -------------------------------------------------------------------------------- */
 int  cvg_create(cvg_ctx** out, int device, unsigned flags);
+/* One context over several GPUs of this host: single process, one device context and one
+ * worker thread per listed GPU, one NCCL communicator per GPU (ncclCommInitAll; libnccl is resolved at run time).
+ * On such a context: cvg_models_upload replicates the model set on every GPU; cvg_scenes_upload* deals a batch's
+ * scenes to the GPUs by cost (batches of fewer than 2 x n_devices scenes stay whole and take the GPUs in turn);
+ * cvg_detect_scenes* / _submit run every device's share concurrently and return results in the caller's order —
+ * pair sharding of the loop nest of src/TestsDetector.cpp:38,58,99 under src/Output.cpp:23-57, no data-path
+ * collective; cvg_match_knn2_sharded is the train-tile sharded match with its one all-gather.  The other entry
+ * points (cvg_match_knn2, cvg_find_homography, cvg_detect_pairs, cvg_dev_*) run on the first listed GPU.
+ * A device may be listed more than once (logical shards on one GPU, used by the single-GPU tests); NCCL refuses
+ * such a communicator, so the exchange then runs as device-to-device copies (cvg_exchange_kind: "memcpy"). */
+int  cvg_create_multi(cvg_ctx** out, const int* devices, int n_devices, unsigned flags);
+int  cvg_num_devices(const cvg_ctx* ctx);
+const char* cvg_exchange_kind(const cvg_ctx* ctx);   /* "nccl", "memcpy", or "none" for a one-device context */
 void cvg_destroy(cvg_ctx* ctx);
+/* Lanes: engines (stream + scratch + one internal worker thread each) of the context's GPU.  A synchronous
+ * cvg_detect_scenes* call splits its batch into up to n_lanes sub-batches that run concurrently, so that one
+ * sub-batch's latency-bound refit/LM kernel runs under another's match and hypothesis kernels; calls below ~2^25
+ * distance evaluations per lane are not split.  cvg_detect_scenes_submit hands whole batches to the lanes in turn.
+ * n_lanes = 1: everything on the context's own stream, on the caller's thread; 0: default (3, env CVG_LANES). */
+int  cvg_set_lanes(cvg_ctx* ctx, int n_lanes);
 const char* cvg_last_error(void);   /* thread-local message of the last failing call                 */
 /* Page-locked host memory for callers without CUDA headers: buffers handed to the *_async uploads are copied
  * by DMA while the GPU computes only if they are page-locked (pageable memory is staged, which serialises). */
@@ -196,6 +216,25 @@ int  cvg_scenes_upload_u8_async(cvg_ctx* ctx, const uint8_t* desc, const float* 
                                 const int64_t* offsets, int n_scenes, cvg_scenes** out);
 int  cvg_detect_scenes(cvg_ctx* ctx, const cvg_models* models, const cvg_scenes* scenes,
                        const float* scales, const cvg_detect_params* p, cvg_pair_result* per_pair);
+/* Asynchronous pair (SURVEY 8b "async _submit/_wait"): submit enqueues the fused call on one of the context's lanes
+ * and returns at once; cvg_job_wait blocks until its results are in the caller's buffers, returns the call's code
+ * and frees the job.  A single-threaded caller that walks a list of test images (src/Output.cpp:27-47) keeps two or
+ * three jobs in flight — submit image k+1, wait image k, run the consumer on k — and the GPU overlaps one job's
+ * refit/LM kernel with the next job's match and hypothesis kernels.  Output buffers, `models` and `scenes` must stay
+ * valid until the wait; `scales` and `p` are copied.  Every job must be waited for before cvg_destroy. */
+int  cvg_detect_scenes_submit(cvg_ctx* ctx, const cvg_models* models, const cvg_scenes* scenes, const float* scales,
+                              const cvg_detect_params* p, cvg_pair_result* per_pair, float* inlier_scene_xy,
+                              int64_t* inlier_offsets, cvg_job** job);
+int  cvg_job_wait(cvg_ctx* ctx, cvg_job* job);
+
+/* ---- train-tile sharded match over the GPUs of a cvg_create_multi context (BASELINE config 5) ---
+ * knnMatch(query, train, 2) + ratio test for host matrices of any size that fits the GPUs together: GPU g gets
+ * train rows [g*T, (g+1)*T) (T = ceil(n_train / n_devices) rounded up to 256) and the whole query matrix, computes
+ * its local top-2 with global train indices, then ONE exchange step — ncclAllGather of (distance, index) pairs,
+ * 16 B per query and GPU — and the lexicographic (distance, index) merge that reproduces OpenCV's tie rule for
+ * any number of shards.  Same outputs as cvg_match_knn2_raw; replaces src/TestsDetector.cpp:59-72. */
+int  cvg_match_knn2_sharded(cvg_ctx* ctx, const float* query, int n_query, const float* train, int n_train,
+                            float ratio, int32_t* idx, float* dist, uint8_t* accept);
 
 /* ---- device-pointer building blocks (multi-GPU train-tile sharding, BASELINE config 5) --------
  * All pointers are DEVICE memory of the context's GPU; `stream` is a cudaStream_t (NULL = default).
@@ -221,6 +260,12 @@ int  cvg_dev_merge_top2(cvg_ctx* ctx, void* stream, const float* dist_parts_dev,
 int  cvg_last_match_path(const cvg_ctx* ctx);
 /* Rows of the last path-3 call that the re-rank could not prove and the exact fallback kernel redid. */
 int  cvg_last_match_fallback_rows(const cvg_ctx* ctx);
+/* Path 1 selects a unit's columns by d^2, OpenCV orders by sqrtf(d^2); the two differ only from d = 2048 on, where
+ * neighbouring integer d^2 round to one float (u8 rows reach d = 2885; SIFT rows, norm 512, stay below 1024).
+ * Rows whose second distance reaches 2048 are redone by the exact kernels, which compare rounded distances:
+ * how many rows of the last path-1 call that was.  When the norms of both sides are known on the host and
+ * ||q|| + ||t|| < 2047 the guard is not even enqueued. */
+int  cvg_last_match_guard_rows(const cvg_ctx* ctx);
 /* Verify calls with CVG_RANSAC_NO_EARLY_STOP and max_iters >= 32768 cut every set's cv::RNG draw stream into
  * chunks walked by many CTAs (same samples as the serial walk).  Returns how many sets of the last such call
  * were handed back to the one-CTA-per-set sampler, or -1 if the last verify call did not use the chunked sampler. */

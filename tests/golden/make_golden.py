@@ -8,7 +8,8 @@ cv2 4.13.0 (opencv-python-headless 4.13.0.92) — in the build container.  The r
     gates                                                    :74,79,81,84
 
 Run:  python tests/golden/make_golden.py          (needs /root/reference/data and cv2)
-Outputs (committed): features_small.npz, golden_pairs.npz, golden_synth.npz
+Outputs (committed): features_small.npz, golden_pairs.npz, golden_synth.npz, golden_sat.npz
+      python tests/golden/make_golden.py sat      (only golden_sat.npz; needs cv2 alone)
 """
 import os
 import sys
@@ -117,6 +118,23 @@ def make_golden_pairs(feat):
     return out
 
 
+def make_golden_sat():
+    """Saturated u8-range rows: all distances above 2048 (distinct integer d^2 collide after sqrtf), planted pairs whose
+    d^2 differ by 1 with the larger one at the lower index.  cv2 orders by the rounded distance, ties to the lower index."""
+    rng = np.random.default_rng(7001)
+    q, t = synth.saturated_pair(rng, 300, 2000)
+    idx, dist = cv_knn(q, t)
+    d2 = ((q[:, None, :].astype(np.float64) - t[None, idx[:, 0], :][0].astype(np.float64)) ** 2).sum(-1) if False else None
+    path = os.path.join(HERE, "golden_sat.npz")
+    np.savez_compressed(path, q=q.astype(np.uint8), t=t.astype(np.uint8), idx=idx, dist=dist, accept=cv_accept(idx, dist))
+    # how many rows does the rounded-distance order decide differently from the d^2 order?
+    D2 = (q.astype(np.float64) ** 2).sum(1)[:, None] + (t.astype(np.float64) ** 2).sum(1)[None, :] - 2.0 * q.astype(np.float64) @ t.astype(np.float64).T
+    order = np.lexsort((np.broadcast_to(np.arange(t.shape[0]), D2.shape), D2), axis=1)[:, :2]
+    print("golden_sat: rows where cv2 differs from the d^2 order:", int((order != idx).any(axis=1).sum()), "of", len(q),
+          "min distance", float(dist.min()))
+    return path
+
+
 def make_golden_synth():
     out = {}
     # --- kNN: float descriptors (summation-order sensitive), ties, tiny train sets
@@ -221,6 +239,10 @@ def make_golden_synth():
     np.savez_compressed(path, **out)
     return path
 
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "sat":
+    print(make_golden_sat())
+    sys.exit(0)
 
 if __name__ == "__main__":
     full = os.path.join(ROOT, "data_cache", "features_full.npz")

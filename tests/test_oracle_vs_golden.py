@@ -44,6 +44,17 @@ def test_knn_float_and_ties(oracle, gsynth):
         assert np.array_equal(dist, gsynth[f"knn_{tag}_dist"])
 
 
+def test_knn_saturated_rows_sqrt_collisions(oracle):
+    """Distances above 2048: distinct integer d^2 collapse into one float and cv2's tie rule picks the lower index
+    (golden_sat.npz: 78 of 300 rows differ from the d^2 order).  The oracle orders by the rounded distance like cv2."""
+    Z = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_sat.npz"))
+    q, t = Z["q"].astype(np.float32), Z["t"].astype(np.float32)
+    idx, dist = oracle.knn2(q, t, nthreads=4)
+    assert np.array_equal(idx, Z["idx"]) and np.array_equal(dist, Z["dist"])
+    assert np.array_equal(oracle.ratio(idx, dist), Z["accept"])
+    assert dist.min() > 2048 and (dist[:, 0] == dist[:, 1]).sum() > 50
+
+
 def test_knn_tiny_train_sets(oracle, gsynth):
     q, t = gsynth["knn_int_q"], gsynth["knn_int_t"]
     for nt in (1, 2):
