@@ -41,6 +41,10 @@ import time
 
 import numpy as np
 
+# a context runs 1 + lanes compute streams and two copy streams: more hardware queues than the default 8, so that none of them
+# alias (set before CUDA is initialised; libcvgraft does the same in cvg_create for hosts that do not)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 

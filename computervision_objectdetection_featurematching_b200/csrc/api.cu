@@ -4,6 +4,7 @@
 #include "ctx.cuh"
 #include <atomic>
 #include <string.h>
+#include <stdlib.h>
 #include <stdarg.h>
 #include <math.h>
 
@@ -20,6 +21,33 @@ int cvg_set_err(int code, const char* fmt, ...)
     return code;
 }
 #define set_err cvg_set_err
+
+// ---- device timeline for debugging (CVG_TRACE=1): timestamps on the streams, dumped by cvg_trace_dump -----------------
+struct TraceEv { cudaEvent_t ev; const char* tag; int id; int dev; };
+static std::mutex g_trace_mu;
+static std::vector<TraceEv> g_trace;
+static bool trace_on() { static const bool on = getenv("CVG_TRACE") && atoi(getenv("CVG_TRACE")); return on; }
+void cvg_trace_mark(cudaStream_t st, const char* tag, int id)
+{
+    if (!trace_on()) return;
+    TraceEv t; t.tag = tag; t.id = id; cudaGetDevice(&t.dev);
+    if (cudaEventCreate(&t.ev) != cudaSuccess) return;
+    cudaEventRecord(t.ev, st);
+    std::lock_guard<std::mutex> g(g_trace_mu);
+    if (g_trace.size() < 100000) g_trace.push_back(t);
+}
+extern "C" void cvg_trace_dump(void)
+{
+    std::lock_guard<std::mutex> g(g_trace_mu);
+    if (g_trace.empty()) return;
+    for (const TraceEv& t : g_trace) cudaEventSynchronize(t.ev);
+    for (const TraceEv& t : g_trace) {
+        float ms = 0; cudaEventElapsedTime(&ms, g_trace[0].ev, t.ev);
+        fprintf(stderr, "trace %10.3f ms  dev %d  %-14s %d\n", ms, t.dev, t.tag, t.id);
+    }
+    for (const TraceEv& t : g_trace) cudaEventDestroy(t.ev);
+    g_trace.clear();
+}
 
 __global__ void stage_copy_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n16)
 {
@@ -83,6 +111,9 @@ int eng_create(cvg_ctx** out, int device, unsigned flags)
 {
     if (!out) return set_err(CVG_ERR_INVALID, "cvg_create: out is NULL");
     *out = nullptr;
+    // more hardware work queues than the default 8: a context runs up to 1 + lanes compute streams and 2 copy streams, and
+    // streams that share a queue serialise.  Only effective when the process has not initialised CUDA yet; never overrides.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
     if (e != cudaSuccess || n_dev == 0)
@@ -101,7 +132,6 @@ int eng_create(cvg_ctx** out, int device, unsigned flags)
     c->device = device; c->flags = flags; c->n_sms = prop.multiProcessorCount;
     int rc = [&]() -> int {
         CU_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        CU_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         CU_CHECK(cudaMalloc(&c->d_flags, 64 * sizeof(int)));
         CU_CHECK(cudaMemset(c->d_flags, 0, 64 * sizeof(int)));
         for (int i = 0; i < 6; i++) CU_CHECK(cudaEventCreate(&c->ev[i]));
@@ -125,7 +155,7 @@ void eng_destroy(cvg_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    for (int i = 0; i < 3; i++) if (c->copy_stream[i]) cudaStreamSynchronize(c->copy_stream[i]);
     DevBuf* bufs[] = { &c->q_f32, &c->q_b, &c->q_blo, &c->q_aug, &c->q_norm, &c->t_f32, &c->t_b, &c->t_blo, &c->t_aug, &c->t_segtab, &c->t_kpt, &c->t_kptoff,
                        &c->units, &c->dir, &c->parts, &c->parts4, &c->segdev, &c->fb, &c->plan_units, &c->plan_dir, &c->chunk, &c->hypH, &c->idx, &c->dist, &c->accept, &c->pts, &c->starts, &c->counts_n,
                        &c->sample_pos, &c->n_samples, &c->counts, &c->best_iter, &c->best_count, &c->iters_run, &c->niters_cur, &c->smp_state, &c->sel,
@@ -140,7 +170,8 @@ void eng_destroy(cvg_ctx* c)
     if (c->d_scored) cudaFree(c->d_scored);
     if (c->stage_h) cudaFreeHost(c->stage_h);
     if (c->stream) cudaStreamDestroy(c->stream);
-    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (int i = 0; i < 3; i++) if (c->copy_stream[i]) cudaStreamDestroy(c->copy_stream[i]);
+    c->inl_h.release(); c->cnt_h.release(); c->res_h.release();
     delete c;
 }
 
@@ -774,9 +805,10 @@ int cvg_find_homography(cvg_ctx* c, const float* src_xy, const float* dst_xy, in
 }  // extern "C"
 
 // ---- fused detect over a prepared train set --------------------------------------------------------
+// host_needs_inliers: the inlier pool (pair (s, v) at s * n_rows + view_offsets[v]) and the per-pair counts are left in the
+// engine's page-locked c->inl_h / c->cnt_h
 static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, TrainSet& ts, const float* d_scales,
-                         const cvg_detect_params* p, cvg_pair_result* per_pair, float* inlier_xy, int32_t* inlier_counts,
-                         bool host_needs_inliers, bool guard = true)
+                         const cvg_detect_params* p, cvg_pair_result* per_pair, bool host_needs_inliers, bool guard = true)
 {
     const int S = ts.n_segs, V = m->n_views, nq = m->n_rows;
     const int P = S * V;
@@ -809,9 +841,15 @@ static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, Tra
     CU_CHECK(c->pts.ensure(rows * 16)); CU_CHECK(c->starts.ensure((size_t)P * 8)); CU_CHECK(c->counts_n.ensure((size_t)P * 4));
     CU_CHECK(c->results.ensure((size_t)P * sizeof(cvg_pair_result)));
     CU_CHECK(c->inl_cnt.ensure((size_t)P * 4));
-    if (host_needs_inliers) CU_CHECK(c->inl_xy.ensure(rows * 8));
+    if (host_needs_inliers) {
+        CU_CHECK(c->inl_xy.ensure(rows * 8));
+        CU_CHECK(c->inl_h.ensure(rows * 8)); CU_CHECK(c->cnt_h.ensure((size_t)P * 4));
+    }
 
     if (c->timing) cudaEventRecord(c->ev[0], c->stream);
+    static std::atomic<int> det_id{ 0 };
+    const int did = det_id.fetch_add(1);
+    cvg_trace_mark(c->stream, "det_begin", did);
     const int path = path_from_kinds(c->flags, m->nonint, ts.nonint);
     if (path == 0) {
         combine_flags_kernel<<<1, 1, 0, c->stream>>>(c->d_flags, (cache && cache->d_flag) ? cache->d_flag : c->d_flags, m->nonint, 1);
@@ -827,6 +865,7 @@ static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, Tra
     cw.pts = c->pts.as<float4>(); cw.starts = c->starts.as<int64_t>(); cw.n_good = c->counts_n.as<int32_t>();
     launch_compact(cw, c->stream);
     c->launches++;
+    cvg_trace_mark(c->stream, "match_end", did);
     if (c->timing) cudaEventRecord(c->ev[1], c->stream);
     int max_view = 0;
     for (int v = 0; v < V; v++) max_view = std::max(max_view, m->view_offsets[v + 1] - m->view_offsets[v]);
@@ -844,18 +883,30 @@ static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, Tra
         g.inlier_xy = host_needs_inliers ? c->inl_xy.as<float>() : nullptr; g.inlier_count = c->inl_cnt.as<int32_t>();
         launch_gates(g, c->stream);
         c->launches++;
+        cvg_trace_mark(c->stream, "det_end", did);
         if (c->timing) cudaEventRecord(c->ev[2], c->stream);
         CU_CHECK(cudaGetLastError());
-        CU_CHECK(cudaMemcpyAsync(per_pair, c->results.p, (size_t)P * sizeof(cvg_pair_result), cudaMemcpyDeviceToHost, c->stream));
+        // Results travel through the engine's page-locked staging, never straight into the caller's (pageable) arrays: a
+        // device -> host copy into pageable memory is staged by the driver behind EVERYTHING already queued on the device —
+        // measured: with three calls and their uploads in flight, call k's results came back only when call k + 2 was done
+        // and the H2D engine idled 4.4 ms in every 15 (e2e 7.0 instead of 5.1 ms per step).
+        const size_t res_bytes = (size_t)P * sizeof(cvg_pair_result);
+        CU_CHECK(c->res_h.ensure(res_bytes + 16));
+        int* words_h = reinterpret_cast<int*>(c->res_h.as<uint8_t>() + res_bytes);     // [0] RNG table short, [1] match path word
+        words_h[0] = 0; words_h[1] = 0;
+        CU_CHECK(cudaMemcpyAsync(c->res_h.p, c->results.p, res_bytes, cudaMemcpyDeviceToHost, c->stream));
         if (host_needs_inliers) {
-            CU_CHECK(cudaMemcpyAsync(inlier_counts, c->inl_cnt.p, (size_t)P * 4, cudaMemcpyDeviceToHost, c->stream));
-            CU_CHECK(cudaMemcpyAsync(inlier_xy, c->inl_xy.p, rows * 8, cudaMemcpyDeviceToHost, c->stream));
+            // the whole pool (one slot range per pair) into the engine's page-locked staging; the callers pack it
+            CU_CHECK(cudaMemcpyAsync(c->cnt_h.p, c->inl_cnt.p, (size_t)P * 4, cudaMemcpyDeviceToHost, c->stream));
+            CU_CHECK(cudaMemcpyAsync(c->inl_h.p, c->inl_xy.p, rows * 8, cudaMemcpyDeviceToHost, c->stream));
         }
-        int rng_short = 0;
-        CU_CHECK(cudaMemcpyAsync(&rng_short, c->d_flags + 4, 4, cudaMemcpyDeviceToHost, c->stream));
-        if (path == 0) CU_CHECK(cudaMemcpyAsync(&flag, c->d_flags + 2, 4, cudaMemcpyDeviceToHost, c->stream));
+        CU_CHECK(cudaMemcpyAsync(&words_h[0], c->d_flags + 4, 4, cudaMemcpyDeviceToHost, c->stream));
+        if (path == 0) CU_CHECK(cudaMemcpyAsync(&words_h[1], c->d_flags + 2, 4, cudaMemcpyDeviceToHost, c->stream));
         rc = sync_and_check(c);
         if (rc) return rc;
+        memcpy(per_pair, c->res_h.p, res_bytes);
+        const int rng_short = words_h[0];
+        flag = words_h[1];
         if (!(rng_short & 1)) break;
         if (c->rng_len >= RNG_TABLE_CAP || attempt >= 4)
             return set_err(CVG_ERR_LIMIT, "RNG draw table exhausted (pathological rejection rate)");
@@ -918,17 +969,15 @@ int cvg_detect_pairs(cvg_ctx* c, const cvg_models* m, const float* scene_desc, c
     if (rc) return rc;
     ts.nonint = -1;                                    // decided on the device
     const bool want_inl = inlier_scene_xy != nullptr && inlier_offsets != nullptr;
-    std::vector<float> pool; std::vector<int32_t> cnt;
-    if (want_inl) { pool.resize((size_t)std::max(m->n_rows, 1) * 2); cnt.resize(std::max(V, 1)); }
-    rc = detect_common(c, m, nullptr, ts, c->scales.as<float>(), p, per_view, want_inl ? pool.data() : nullptr,
-                       want_inl ? cnt.data() : nullptr, want_inl);
+    rc = detect_common(c, m, nullptr, ts, c->scales.as<float>(), p, per_view, want_inl);
     if (rc) return rc;
     if (want_inl) {
+        const float* pool = c->inl_h.as<float>(); const int32_t* cnt = c->cnt_h.as<int32_t>();
         int32_t o = 0;
         for (int v = 0; v < V; v++) {
             inlier_offsets[v] = o;
             const size_t start = (size_t)m->view_offsets[v];
-            memcpy(inlier_scene_xy + 2 * (size_t)o, pool.data() + 2 * start, (size_t)cnt[v] * 8);
+            memcpy(inlier_scene_xy + 2 * (size_t)o, pool + 2 * start, (size_t)cnt[v] * 8);
             o += cnt[v];
         }
         inlier_offsets[V] = o;
@@ -964,7 +1013,15 @@ int eng_scenes_upload(cvg_ctx* c, const float* desc, const uint8_t* desc_u8, con
     sc->offsets_copy.assign(offsets, offsets + n_scenes + 1);   // the library's own copy: the caller's array may go away at once
     layout_segments(sc->ts, offsets, n_scenes);
     if (sc->ts.rows_pad_total > 0x7fffff00LL) { delete sc; return set_err(CVG_ERR_LIMIT, "scene batch too large (>2^31 padded rows)"); }
-    cudaStream_t st = async ? c->copy_stream : c->stream;
+    cudaStream_t st = c->stream;
+    if (async) {
+        // copy streams are made on first use: only the engine that uploads needs them, and every stream beyond the
+        // device's hardware queues (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default) aliases with another one — a bulk copy
+        // sharing a queue with a lane's compute stream serialises the two (measured: e2e 5.1 -> 7.0 ms per step)
+        cudaStream_t& cs = c->copy_stream[c->next_copy++ % 2];
+        if (!cs) CU_CHECK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        st = cs;
+    }
     const int rc = [&]() -> int {
         CU_CHECK(c->pool.acquire(sc->f32, (size_t)std::max<int64_t>(total, 1) * DIM * 4));
         CU_CHECK(c->pool.acquire(sc->kpt, (size_t)std::max<int64_t>(total, 1) * 8));
@@ -972,6 +1029,9 @@ int eng_scenes_upload(cvg_ctx* c, const float* desc, const uint8_t* desc_u8, con
         sc->ts.d_f32 = sc->f32.as<float>(); sc->ts.d_kpt = sc->kpt.as<float>(); sc->ts.d_kpt_offsets = sc->kptoff.as<int64_t>();
         sc->d_flag = reinterpret_cast<int*>(sc->kptoff.as<int64_t>() + (n_scenes + 1));
         sc->ts.d_tnmax = sc->d_flag + 1;
+        static std::atomic<int> up_id{ 0 };
+        const int tid = up_id.fetch_add(1);
+        cvg_trace_mark(st, "h2d_begin", tid);
         // host -> device copies: one per array, or one per scene when the scenes are gathered from all over the caller's arrays
         auto h2d_rows = [&](void* dst, const void* src, size_t row_bytes) -> int {
             if (!src_row0) { CU_CHECK(cudaMemcpyAsync(dst, src, (size_t)total * row_bytes, cudaMemcpyHostToDevice, st)); return CVG_OK; }
@@ -995,8 +1055,10 @@ int eng_scenes_upload(cvg_ctx* c, const float* desc, const uint8_t* desc_u8, con
         else if (total > 0) CU_CHECK(cudaMemsetAsync(sc->ts.d_kpt, 0, (size_t)total * 8, st));
         CU_CHECK(cudaMemcpyAsync(sc->ts.d_kpt_offsets, sc->offsets_copy.data(), (size_t)(n_scenes + 1) * 8, cudaMemcpyHostToDevice, st));
         CU_CHECK(cudaMemsetAsync(sc->d_flag, 0, 8, st));
+        cvg_trace_mark(st, "h2d_end", tid);
         int r = prep_train(c, sc->ts, sc->b, sc->blo, sc->aug, sc->segtab, 0, true, st, sc->d_flag);
         if (r) return r;
+        cvg_trace_mark(st, "prep_end", tid);
         if (async) {
             // the caller's buffers are read by the copy engine until `ready`; cvg_detect_scenes orders itself after it
             CU_CHECK(cudaEventCreateWithFlags(&sc->ready, cudaEventDisableTiming));
@@ -1075,11 +1137,24 @@ int eng_detect_range(cvg_ctx* c, const cvg_models* m, cvg_scenes* sc, int s0, in
         for (const SegInfo& g : view.segs) view.max_rows = std::max(view.max_rows, g.rows);
     }
     const bool want_inl = pool != nullptr && cnt != nullptr;
-    if (want_inl) { pool->resize((size_t)S * std::max(m->n_rows, 1) * 2); cnt->resize((size_t)S * V); }
     // d >= 2048 needs ||q|| + ||t|| >= 2048: with both norms known on the host the guard kernels are not even enqueued
     const bool safe = sc->max_norm2 >= 0.f && sqrt((double)m->max_norm2) + sqrt((double)sc->max_norm2) < 2047.0;
-    return detect_common(c, m, sc, view, d_scales, p, per_pair, want_inl ? pool->data() : nullptr,
-                         want_inl ? cnt->data() : nullptr, want_inl, !safe);
+    const int rc = detect_common(c, m, sc, view, d_scales, p, per_pair, want_inl, !safe);
+    if (rc || !want_inl) return rc;
+    // pack the pool pair after pair (scene-major, then view), on this engine's thread
+    const float* hp = c->inl_h.as<float>(); const int32_t* hc = c->cnt_h.as<int32_t>();
+    cnt->assign(hc, hc + (size_t)S * V);
+    size_t total = 0;
+    for (size_t i = 0; i < (size_t)S * V; i++) total += (size_t)hc[i];
+    pool->resize(total * 2);
+    size_t o = 0;
+    for (int s = 0; s < S; s++)
+        for (int v = 0; v < V; v++) {
+            const size_t n = (size_t)hc[(size_t)s * V + v];
+            memcpy(pool->data() + 2 * o, hp + 2 * ((size_t)s * m->n_rows + (size_t)m->view_offsets[v]), n * 8);
+            o += n;
+        }
+    return CVG_OK;
 }
 
 extern "C" {

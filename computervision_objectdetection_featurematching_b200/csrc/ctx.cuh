@@ -38,6 +38,23 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// grow-only page-locked host buffer (device -> host results land here by DMA, without a staging copy inside the driver)
+struct HostBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
 // Freed device buffers are kept for reuse: cudaMalloc/cudaFree cost milliseconds and serialise the
 // device, which would dominate a streaming caller that uploads a scene batch per step.
 struct BufPool {
@@ -49,7 +66,9 @@ struct BufPool {
         int best = -1;
         for (int i = 0; i < (int)free_list.size(); i++)
             if (free_list[i].cap >= bytes && (best < 0 || free_list[i].cap < free_list[best].cap)) best = i;
-        if (best >= 0 && free_list[best].cap <= 2 * bytes + (1 << 20)) {
+        // a buffer serves requests down to two thirds of its size: the buffers of a streaming caller (fp32 rows, bf16 operands,
+        // u8 rows: 4 : 2 : 1) then stay with their own kind instead of stealing each other's and forcing a cudaMalloc
+        if (best >= 0 && free_list[best].cap <= bytes + bytes / 2 + (1 << 20)) {
             b = free_list[best];
             free_list.erase(free_list.begin() + best);
             return cudaSuccess;
@@ -117,7 +136,10 @@ struct MultiState;
 struct cvg_ctx {
     int device = 0; unsigned flags = 0; int n_sms = 148;
     cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;                // uploads of cvg_scenes_upload_async (overlap with compute)
+    // uploads of cvg_scenes_upload_async (overlap with compute) take these in turn: the operand conversion kernels of one
+    // batch then run under the host -> device copy of the next
+    cudaStream_t copy_stream[3] = { nullptr, nullptr, nullptr }; unsigned next_copy = 0;
+    HostBuf inl_h, cnt_h, res_h;                       // inlier pool, counts, per-pair results + status words of the last fused call (page-locked)
     int* d_flags = nullptr;            // [0] train row kinds, [1] query row kinds, [2] match path (0 tensor exact, 1 tensor
                                        // candidates + re-rank, 2 exact SIMT), [3] raw-query kinds, [4] RNG table short,
                                        // [5] max ||t||^2 bits, [6] fallback row count, [7] rows the d >= 2048 guard redid, [8..16) kernel debug words,
@@ -196,9 +218,9 @@ int  eng_scenes_upload(cvg_ctx* c, const float* desc, const uint8_t* desc_u8, co
                        int n_scenes, cvg_scenes** out, bool async, const int64_t* src_row0 = nullptr);
 void eng_scenes_free(cvg_ctx* c, cvg_scenes* sc);
 int  eng_scenes_wait(cvg_ctx* c, cvg_scenes* sc);
-// scenes [s0, s1) of a resident batch against every view: per_pair [(s1 - s0) * V]; pool / cnt (may be NULL) receive
-// the device inlier pool ((s1 - s0) * n_rows * 2 floats, pair (s, v) at (s - s0) * n_rows + view_offsets[v]) and the
-// inlier counts per pair.  `c` may be any engine of the device that holds the scenes and the models.
+// scenes [s0, s1) of a resident batch against every view: per_pair [(s1 - s0) * V]; pool / cnt (may be NULL) receive the
+// inlier scene points packed pair after pair (scene-major, then view) and the inlier counts per pair.  `c` may be any
+// engine of the device that holds the scenes and the models.
 int  eng_detect_range(cvg_ctx* c, const cvg_models* m, cvg_scenes* sc, int s0, int s1, const float* scales,
                       const cvg_detect_params* p, cvg_pair_result* per_pair, std::vector<float>* pool,
                       std::vector<int32_t>* cnt);

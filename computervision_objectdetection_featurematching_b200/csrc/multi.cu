@@ -58,7 +58,7 @@ struct MultiState {
     const char* exchange = "none";
 };
 
-struct ChunkTask { int s0 = 0, s1 = 0; Done done; std::vector<float> pool; std::vector<int32_t> cnt; };
+struct ChunkTask { int s0 = 0, s1 = 0; Done done; std::vector<float> pool; std::vector<int32_t> cnt; int match_path = 0; };
 
 struct cvg_job {
     // single-device part
@@ -163,6 +163,7 @@ static int dev_submit(cvg_ctx* c, const cvg_models* m, cvg_scenes* sc, const flo
             eng->wave_div = share;
             const int r = eng_detect_range(eng, m, sc, t->s0, t->s1, j->have_scales ? j->scales.data() : nullptr, &j->params,
                                            j->per_pair + (size_t)t->s0 * V, want_inl ? &t->pool : nullptr, want_inl ? &t->cnt : nullptr);
+            t->match_path = eng->last_match_path;
             t->done.set(r, cvg_last_error());
         });
     }
@@ -178,20 +179,15 @@ static int dev_wait(cvg_job* j)
         if (r && !rc) { rc = r; err = t->done.err; }
     }
     if (rc) return cvg_set_err(rc, "%s", err.c_str());
+    for (ChunkTask* t : j->chunks) j->ctx->last_match_path = std::max(t == j->chunks[0] ? 0 : j->ctx->last_match_path, t->match_path);
     if (j->inl_xy && j->inl_off) {
-        // every chunk's device pool has one slot range per (scene, view) at scene * n_rows + view offset: pack pair after pair
-        const cvg_models* m = j->m;
-        const int V = m->n_views;
+        // every chunk comes back packed pair after pair (eng_detect_range): concatenate in scene order
+        const int V = j->m->n_views;
         int64_t o = 0;
-        for (ChunkTask* t : j->chunks)
-            for (int s = t->s0; s < t->s1; s++)
-                for (int v = 0; v < V; v++) {
-                    const size_t pair = (size_t)s * V + v, lp = (size_t)(s - t->s0) * V + v;
-                    j->inl_off[pair] = o;
-                    const size_t start = (size_t)(s - t->s0) * m->n_rows + (size_t)m->view_offsets[v];
-                    memcpy(j->inl_xy + 2 * (size_t)o, t->pool.data() + 2 * start, (size_t)t->cnt[lp] * 8);
-                    o += t->cnt[lp];
-                }
+        for (ChunkTask* t : j->chunks) {
+            memcpy(j->inl_xy + 2 * (size_t)o, t->pool.data(), t->pool.size() * 4);
+            for (size_t lp = 0; lp < t->cnt.size(); lp++) { j->inl_off[(size_t)t->s0 * V + lp] = o; o += t->cnt[lp]; }
+        }
         j->inl_off[(size_t)j->sc->ts.n_segs * V] = o;
     }
     return CVG_OK;
@@ -505,17 +501,10 @@ int cvg_detect_scenes_inliers(cvg_ctx* c, const cvg_models* m, const cvg_scenes*
         std::vector<float> pool; std::vector<int32_t> cnt;
         rc = eng_detect_range(c, m, sc, 0, sc->ts.n_segs, scales, p, per_pair, want_inl ? &pool : nullptr, want_inl ? &cnt : nullptr);
         if (rc || !want_inl) return rc;
-        const int S = sc->ts.n_segs, V = m->n_views;
+        memcpy(inlier_scene_xy, pool.data(), pool.size() * 4);
         int64_t o = 0;
-        for (int s = 0; s < S; s++)
-            for (int v = 0; v < V; v++) {
-                const size_t pair = (size_t)s * V + v;
-                inlier_offsets[pair] = o;
-                const size_t start = (size_t)s * m->n_rows + (size_t)m->view_offsets[v];
-                memcpy(inlier_scene_xy + 2 * (size_t)o, pool.data() + 2 * start, (size_t)cnt[pair] * 8);
-                o += cnt[pair];
-            }
-        inlier_offsets[(size_t)S * V] = o;
+        for (size_t pair = 0; pair < cnt.size(); pair++) { inlier_offsets[pair] = o; o += cnt[pair]; }
+        inlier_offsets[cnt.size()] = o;
         return CVG_OK;
     }
     rc = dev_submit(c, m, sc, scales, p, per_pair, inlier_scene_xy, inlier_offsets, true, &job);

@@ -290,6 +290,9 @@ int  cvg_last_score_ms(const cvg_ctx* ctx, float* score_ms);
 /* Device self tests.  which = 0: the reciprocal the scoring kernel writes out by hand (MUFU.RCP + one Newton step) against
  * __frcp_rn and against 1.f / x on EVERY float with 2^-126 <= |x| < 2^126; *mismatches must come back 0. */
 int  cvg_selftest(cvg_ctx* ctx, int which, uint64_t* mismatches);
+/* Debugging aid: with CVG_TRACE=1 in the environment the library timestamps its uploads and fused calls on their streams;
+ * this prints the device timeline to stderr and clears it. */
+void cvg_trace_dump(void);
 
 #ifdef __cplusplus
 }

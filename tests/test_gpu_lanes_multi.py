@@ -33,13 +33,15 @@ def test_match_guard_saturated_rows_vs_cv2(api, oracle):
         assert ctx.last_match_path == api.PATH_TENSOR           # integer rows: the tcgen05 kernel serves the call ...
         assert ctx.last_match_guard_rows == len(q)              # ... and every row (all distances >= 2048) is redone exactly
         assert np.array_equal(idx, Z["idx"]) and np.array_equal(dist, Z["dist"]) and np.array_equal(acc, Z["accept"])
-        # mixed: SIFT-like rows (d < 1024) next to saturated ones; only the far rows take the guard
+        # mixed: mid-range query rows (values 120..139, d ~ 1300 to every train row) next to the saturated ones; only the
+        # far rows take the guard
         rng = np.random.default_rng(11)
-        qs, ts, _ = synth.planted_pair(rng, 200, 2000)
-        q2 = np.concatenate([qs, q[:100]]); t2 = np.concatenate([ts, t[:1500]])
+        qm = rng.integers(120, 140, size=(200, 128)).astype(np.float32)
+        q2 = np.concatenate([qm, q[:100]]); t2 = t[:1500]
         got = ctx.match_knn2(q2, t2)
-        assert ctx.last_match_path == api.PATH_TENSOR and 0 < ctx.last_match_guard_rows <= 100
+        assert ctx.last_match_path == api.PATH_TENSOR and ctx.last_match_guard_rows == 100
         oi, od = oracle.knn2(q2, t2, nthreads=8)
+        assert od[:200].max() < 2048 and od[200:].min() > 2048
         assert np.array_equal(got[0], oi) and np.array_equal(got[1], od) and np.array_equal(got[2], oracle.ratio(oi, od))
         # resident model set + fused call: same guard inside detect (keypoints are irrelevant here)
         models = ctx.upload_models(q2, np.zeros((len(q2), 2), np.float32), [0, 150, len(q2)], [0, 0])
