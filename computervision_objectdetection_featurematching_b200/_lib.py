@@ -70,6 +70,7 @@ SYMBOLS = {
     "cvg_last_score_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "cvg_selftest": (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint64)]),
     "cvg_trace_dump": (None, []),
+    "cvg_device_reset": (C.c_int, [C.c_int]),
 }
 
 _lib = None

@@ -21,6 +21,7 @@ RANSAC_NO_EARLY_STOP = 1
 RANSAC_NO_REFINE = 2
 FORCE_EXACT_MATCH = 1
 MATCH_PAIR_MODE = 2
+NITERS_ALL_ON_HOST = 4
 PATH_TENSOR, PATH_EXACT, PATH_TENSOR_RERANK = 1, 2, 3   # cvg_last_match_path
 
 PAIR_DTYPE = np.dtype([("status", "<i4"), ("n_good", "<i4"), ("n_inliers", "<i4"), ("ransac_iters", "<i4"),

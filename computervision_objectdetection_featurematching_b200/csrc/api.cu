@@ -5,8 +5,10 @@
 #include <atomic>
 #include <string.h>
 #include <stdlib.h>
+#include <unistd.h>
 #include <stdarg.h>
 #include <math.h>
+#include <float.h>
 
 using namespace cvg;
 
@@ -73,6 +75,15 @@ static cudaError_t h2d_small(cvg_ctx* c, void* dst, const void* src, size_t byte
     return cudaGetLastError();
 }
 
+__global__ void fault_trap_kernel(int* dbg)
+{
+    if (threadIdx.x == 0) { dbg[0] = 99; dbg[1] = (int)blockIdx.x; dbg[2] = 0; }
+    __threadfence_system();
+    __trap();
+}
+
+static int sync_and_check(cvg_ctx* c);
+
 extern "C" {
 
 const char* cvg_last_error(void) { return g_err; }
@@ -94,10 +105,12 @@ void cvg_detect_params_default(cvg_detect_params* p)
 }  // extern "C"
 
 // Opt-in attributes (dynamic shared memory) belong to a (function, device) pair: set once per device of the process.
+static std::mutex g_dev_mu;
+static bool g_dev_done[64] = {};
+static void device_forget(int device) { std::lock_guard<std::mutex> g(g_dev_mu); if (device >= 0 && device < 64) g_dev_done[device] = false; }
 static int device_init_once(int device, char* err, size_t errlen)
 {
-    static std::mutex mu;
-    static bool done[64] = {};
+    std::mutex& mu = g_dev_mu; bool* done = g_dev_done;
     std::lock_guard<std::mutex> g(mu);
     if (device >= 0 && device < 64 && done[device]) return 0;
     if (tc_init(err, errlen)) return 1;
@@ -160,7 +173,7 @@ void eng_destroy(cvg_ctx* c)
                        &c->units, &c->dir, &c->parts, &c->parts4, &c->segdev, &c->fb, &c->plan_units, &c->plan_dir, &c->chunk, &c->hypH, &c->idx, &c->dist, &c->accept, &c->pts, &c->starts, &c->counts_n,
                        &c->sample_pos, &c->n_samples, &c->counts, &c->best_iter, &c->best_count, &c->iters_run, &c->niters_cur, &c->smp_state, &c->sel,
                        &c->H, &c->mask, &c->rmask, &c->found, &c->sflags, &c->results, &c->inl_xy, &c->inl_cnt,
-                       &c->scales, &c->src, &c->dst, &c->nit };
+                       &c->scales, &c->src, &c->dst, &c->nit, &c->nitreq };
     for (DevBuf* b : bufs) b->release();
     c->pool.clear();
     if (c->d_flags) cudaFree(c->d_flags);
@@ -176,6 +189,28 @@ void eng_destroy(cvg_ctx* c)
 }
 
 extern "C" {
+
+int cvg_device_reset(int device)
+{
+    // cudaDeviceReset: the only way out of a sticky error.  Every handle of this device (contexts, model sets, scene batches,
+    // cvg_host_alloc memory) is void afterwards; so is every other CUDA user's state in this process.
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaDeviceReset();
+    cudaGetLastError();
+    device_forget(device);
+    // after a fault the driver tears the channel down asynchronously: the device reports "busy or unavailable" for a moment
+    for (int attempt = 0; attempt < 20; attempt++) {
+        e = cudaSetDevice(device);
+        if (e == cudaSuccess) e = cudaFree(nullptr);             // forces a fresh primary context
+        if (e == cudaSuccess) break;
+        cudaGetLastError();
+        usleep(100 * 1000);
+    }
+    if (e != cudaSuccess)
+        return set_err(CVG_ERR_CUDA, "cudaDeviceReset(%d): %s — this driver does not hand the device back to a process that "
+                       "faulted on it; restart the process", device, cudaGetErrorString(e));
+    return CVG_OK;
+}
 
 void* cvg_host_alloc(size_t bytes)
 {
@@ -223,8 +258,15 @@ int cvg_last_hyp_stats(const cvg_ctx* c0, float* hyp_ms, int* hyp_launches, uint
 int cvg_selftest(cvg_ctx* c0, int which, uint64_t* mismatches)
 {
     cvg_ctx* c = cvg_primary(c0);
-    if (!c || !mismatches || which != 0) return set_err(CVG_ERR_INVALID, "cvg_selftest: bad argument");
+    if (!c || !mismatches || (which != 0 && which != 99)) return set_err(CVG_ERR_INVALID, "cvg_selftest: bad argument");
     CU_CHECK(cudaSetDevice(c->device));
+    if (which == 99) {
+        // fault injection for the tests of the error path: what a protocol bug in a kernel ends in (mbar_wait -> __trap)
+        *mismatches = 0;
+        fault_trap_kernel<<<1, 32, 0, c->stream>>>(c->d_flags + 8);
+        c->launches++;
+        return sync_and_check(c);
+    }
     CU_CHECK(cudaMemsetAsync(c->d_scored, 0, 8, c->stream));
     c->launches += launch_selftest_rcp(c->d_scored, c->stream);
     unsigned long long n = 0;
@@ -259,6 +301,7 @@ int cvg_last_timing(const cvg_ctx* c0, float* m, float* r, float* t)
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 constexpr int64_t RNG_TABLE_CAP = 1LL << 28;                    // 1 GiB of draws
+constexpr int NIT_REQ_CAP = 16384;                              // (n, good) pairs a call may ask the host about per attempt
 
 // The raw cv::RNG stream of the fixed seed as a device table.  An accepted 4-point sample costs 4 draws plus the
 // draws of the attempts checkSubset rejected before it (5-8 attempts on outlier-heavy sets), so the table is sized
@@ -549,10 +592,48 @@ static int run_ransac(cvg_ctx* c, const float4* d_pts, const int64_t* d_starts, 
     }
     w.err_flag = c->d_flags + 4;
     CU_CHECK(cudaMemsetAsync(c->d_flags + 4, 0, 4, c->stream));
+    // RANSACUpdateNumIters: the host's log(1 - confidence), the table of host-verified entries and the request list
+    {
+        double pc = p->confidence; pc = pc > 0. ? pc : 0.; pc = pc < 1. ? pc : 1.;
+        const double one_minus = 1. - pc > DBL_MIN ? 1. - pc : DBL_MIN;
+        w.log_num = log(one_minus);
+        w.nit_margin = (c->flags & CVG_NITERS_ALL_ON_HOST) ? 1e300 : 1e-10;
+        CU_CHECK(c->nitreq.ensure((size_t)NIT_REQ_CAP * sizeof(int2)));
+        w.nit_req = c->nitreq.as<int2>(); w.nit_req_n = c->d_flags + 19; w.nit_req_cap = NIT_REQ_CAP;
+        w.nit_tab = c->nit_host.empty() ? nullptr : c->nit.as<NitEntry>(); w.nit_n = (int)c->nit_host.size();
+        CU_CHECK(cudaMemsetAsync(c->d_flags + 19, 0, 4, c->stream));
+    }
     w.scored_pts = c->timing ? c->d_scored : nullptr;
     if (c->timing) CU_CHECK(cudaMemsetAsync(c->d_scored, 0, 8, c->stream));
     c->launches += launch_ransac(w, c->stream, c->timing ? c->hyp_ev : nullptr, &c->hyp_rounds);
     CU_CHECK(cudaGetLastError());
+    return CVG_OK;
+}
+
+// The device asked about (n, good) pairs (err_flag bit 1): evaluate them with this host's libm — the functions OpenCV itself
+// calls — and put them in the engine's table; the caller then repeats the verify stage.  Stream is idle (caller synchronised).
+static int answer_nit_requests(cvg_ctx* c)
+{
+    int n_req = 0;
+    CU_CHECK(cudaMemcpy(&n_req, c->d_flags + 19, 4, cudaMemcpyDeviceToHost));
+    n_req = std::min(n_req, NIT_REQ_CAP);
+    std::vector<int2> req((size_t)std::max(n_req, 0));
+    if (n_req > 0) CU_CHECK(cudaMemcpy(req.data(), c->nitreq.p, (size_t)n_req * sizeof(int2), cudaMemcpyDeviceToHost));
+    size_t added = 0;
+    for (const int2& r : req) {
+        bool have = false;
+        for (const NitEntry& e : c->nit_host) if (e.n == r.x && e.good == r.y) { have = true; break; }
+        if (have || r.x <= 0) continue;
+        double ep = (double)(r.x - r.y) / r.x;                       // ptsetreg.cpp: (double)(count - goodCount) / count
+        ep = ep > 0. ? ep : 0.; ep = ep < 1. ? ep : 1.;
+        const double d0 = 1. - pow(1. - ep, 4);                      // modelPoints = 4
+        NitEntry e; e.n = r.x; e.good = r.y; e.zero = d0 < DBL_MIN ? 1 : 0; e.denom_log = e.zero ? -1. : log(d0); e.pad = 0;
+        c->nit_host.push_back(e); added++;
+    }
+    if (!added) return set_err(CVG_ERR_LIMIT, "RANSACUpdateNumIters: the device keeps asking about entries it already has");
+    if (c->nit_host.size() > (1u << 20)) return set_err(CVG_ERR_LIMIT, "RANSACUpdateNumIters: verification table overflow");
+    CU_CHECK(c->nit.ensure(c->nit_host.size() * sizeof(NitEntry)));
+    CU_CHECK(cudaMemcpy(c->nit.p, c->nit_host.data(), c->nit_host.size() * sizeof(NitEntry), cudaMemcpyHostToDevice));
     return CVG_OK;
 }
 
@@ -568,8 +649,12 @@ static int sync_and_check(cvg_ctx* c)
 {
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) {
-        int dbg[4] = { 0, 0, 0, 0 };
-        return set_err(CVG_ERR_CUDA, "device execution failed: %s (dbg %d)", cudaGetErrorString(e), dbg[0]);
+        // A device-side trap (bounded mbarrier wait that ran out, see match_tc.cu) leaves the CUDA context of the whole
+        // process in a sticky error state: every later call of every context on this device fails with the same code until
+        // cvg_device_reset.  The kernels leave a code in d_flags[8..] before trapping, but device memory is unreadable now.
+        return set_err(CVG_ERR_CUDA, "device execution failed: %s — the CUDA context of this process is unusable; destroy the "
+                       "cvgraft contexts of device %d, call cvg_device_reset(%d) and create them again", cudaGetErrorString(e),
+                       c->device, c->device);
     }
     return CVG_OK;
 }
@@ -781,6 +866,14 @@ int cvg_find_homography_batch(cvg_ctx* c, const float* src_xy, const float* dst_
         if (rc) return rc;
         int bad = -1;
         for (int k = 0; k < n_sets && bad < 0; k++) if (sflags[k] & 1) bad = k;
+        int words = 0;
+        CU_CHECK(cudaMemcpy(&words, c->d_flags + 4, 4, cudaMemcpyDeviceToHost));
+        if (bad < 0 && (words & 2)) {                               // niters entries to verify on the host, then again
+            if (attempt >= 12) return set_err(CVG_ERR_LIMIT, "RANSACUpdateNumIters verification did not converge");
+            rc = answer_nit_requests(c);
+            if (rc) return rc;
+            continue;
+        }
         if (bad < 0) break;
         if (c->rng_len >= RNG_TABLE_CAP || attempt >= 4)
             return set_err(CVG_ERR_LIMIT, "set %d: RNG draw table exhausted (pathological rejection rate)", bad);
@@ -907,6 +1000,12 @@ static int detect_common(cvg_ctx* c, const cvg_models* m, cvg_scenes* cache, Tra
         memcpy(per_pair, c->res_h.p, res_bytes);
         const int rng_short = words_h[0];
         flag = words_h[1];
+        if (!(rng_short & 1) && (rng_short & 2)) {                  // niters entries to verify on the host, then again
+            if (attempt >= 12) return set_err(CVG_ERR_LIMIT, "RANSACUpdateNumIters verification did not converge");
+            rc = answer_nit_requests(c);
+            if (rc) return rc;
+            continue;
+        }
         if (!(rng_short & 1)) break;
         if (c->rng_len >= RNG_TABLE_CAP || attempt >= 4)
             return set_err(CVG_ERR_LIMIT, "RNG draw table exhausted (pathological rejection rate)");

@@ -107,6 +107,11 @@ void launch_shift_index(const int32_t* idx_in, const float* dist_in, int n_query
                         float* dist, int32_t* idx, cudaStream_t st);
 
 // ransac.cu
+// RANSACUpdateNumIters depends on log() and pow() of the C library OpenCV runs on; CUDA's are up to 2 ulp away, which could
+// move cvRound(num / denom) when the quotient sits within ~1e-12 of a half-integer.  The device therefore uses the HOST's
+// log(1 - confidence), flags every evaluation whose rounding or cap decision is closer than `nit_margin` to a boundary, and
+// the host answers those (n, good) pairs with its own libm values; the verify stage is then repeated with the table.
+struct NitEntry { int32_t n; int32_t good; double denom_log; int32_t zero; int32_t pad; };   // zero: 1 - (1-ep)^4 < DBL_MIN
 struct RansacWork {
     const float4* pts;          // correspondence pool, (X, Y, x, y)
     const int64_t* starts;      // [P] first pool row of set k
@@ -139,7 +144,11 @@ struct RansacWork {
     uint8_t* ransac_mask;       // [total] or NULL
     int32_t* found;             // [P]
     int32_t* status_flags;      // [P] bit0: rng table exhausted
-    int* err_flag;              // one word, OR of all status_flags (or NULL)
+    int* err_flag;              // one word, OR of all status_flags (or NULL); bit 1: niters entries were requested
+    double log_num;             // log(max(1 - confidence, DBL_MIN)) from the host's libm
+    const NitEntry* nit_tab; int nit_n;       // host-verified entries (usually none)
+    int2* nit_req; int* nit_req_n; int nit_req_cap;   // (n, good) pairs the device asks the host about
+    double nit_margin;          // distance to a decision boundary below which an evaluation is not trusted
     // chunked sampler scratch (huge single rounds; NULL / 0 = not available)
     void* chunk_outs; int32_t* chunk_lists; int32_t* chunk_offsets; int* chunk_serial; int n_chunks;
     uint8_t* chunk_maps; int32_t* chunk_entries; int* chunk_serial_count;

@@ -163,7 +163,8 @@ struct cvg_ctx {
     uint64_t plan_models_uid = 0; std::vector<int> plan_shape; int plan_units_n = 0;   // keyed on cvg_models::uid: addresses get reused
     DevBuf pts, starts, counts_n, sample_pos, n_samples, counts, best_iter, best_count, iters_run, niters_cur, smp_state, sel;
     DevBuf H, mask, rmask, found, sflags, results, inl_xy, inl_cnt, scales, src, dst;
-    DevBuf nit;                                        // host-verified RANSACUpdateNumIters entries (see run_ransac)
+    DevBuf nit, nitreq;                                // host-verified RANSACUpdateNumIters entries, the device's requests (run_ransac)
+    std::vector<cvg::NitEntry> nit_host;
     BufPool pool;                                      // recycled buffers of freed scene batches
     // Small host->device parameter blocks of the fused path go through a mapped pinned staging area read by a
     // copy kernel, not through cudaMemcpyAsync: the H2D copy engine may be busy for milliseconds with the next

@@ -922,6 +922,47 @@ ransac_score_kernel(RansacWork w, int round_base, int round_len, int n_slices, i
 }
 
 // ---- 3. select kernel: the serial scan of RANSACPointSetRegistrator::run --------------------------
+// cv::RANSACUpdateNumIters(confidence, (double)(n - good) / n, 4, niters) for the whole warp (same arguments in every lane).
+// log(1 - confidence) comes from the host; log(1 - (1 - ep)^4) comes from the host-verified table when the pair is listed,
+// else from CUDA's log / pow with a check that neither the cap comparison nor cvRound is within nit_margin of flipping
+// (then the pair is sent to the host and the call repeats the verify stage, see run_ransac in api.cu).
+__device__ int update_num_iters_checked(const RansacWork& w, int n, int good, int niters, int lane)
+{
+    int found = -1;
+    for (int i = lane; i < w.nit_n; i += 32)
+        if (w.nit_tab[i].n == n && w.nit_tab[i].good == good) found = i;
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) found = max(found, __shfl_xor_sync(0xffffffffu, found, o));
+    double ep = (double)(n - good) / n;
+    ep = ep > 0. ? ep : 0.; ep = ep < 1. ? ep : 1.;
+    const double num = w.log_num;
+    double denom; bool zero;
+    if (found >= 0) { denom = w.nit_tab[found].denom_log; zero = w.nit_tab[found].zero != 0; }
+    else {
+        const double d0 = 1. - pow(1. - ep, 4.0);
+        zero = d0 < DBL_MIN;
+        denom = zero ? -1. : log(d0);
+    }
+    int result;
+    if (zero) result = 0;
+    else if (denom >= 0 || -num >= niters * (-denom)) result = niters;
+    else result = (int)rint(num / denom);            // cvRound: round half to even
+    if (found < 0 && w.nit_req) {
+        bool unsure = zero || !(denom < 0);           // never reached with good >= 4; let the host decide if it is
+        if (!unsure) {
+            const double q = num / denom;
+            const double m = w.nit_margin * (fabs(q) + 1.);
+            unsure = fabs(q - floor(q) - 0.5) < m || fabs(q - (double)niters) < m;
+        }
+        if (unsure && lane == 0) {
+            const int slot = atomicAdd(w.nit_req_n, 1);
+            if (slot < w.nit_req_cap) w.nit_req[slot] = make_int2(n, good);
+            if (w.err_flag) atomicOr(w.err_flag, 2);
+        }
+    }
+    return result;
+}
+
 __global__ void ransac_select_kernel(RansacWork w, int round_base, int round_len)
 {
     const int set = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -946,7 +987,7 @@ __global__ void ransac_select_kernel(RansacWork w, int round_base, int round_len
             best = __shfl_sync(0xffffffffu, c, f);
             best_iter = base + f;
             if (!(w.flags & CVG_RANSAC_NO_EARLY_STOP))
-                niters = update_num_iters(w.conf, (double)(n - best) / n, niters);
+                niters = update_num_iters_checked(w, n, best, niters, lane);
             start = f + 1;
         }
         base += 32;

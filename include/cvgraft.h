@@ -64,6 +64,10 @@ enum {
                                     /* cta_group::2, M = 256): same results; measured slower than    */
                                     /* the one-CTA form on B200, kept for A-B runs   */
 
+#define CVG_NITERS_ALL_ON_HOST 4u   /* every RANSACUpdateNumIters evaluation is answered by the host's libm (log, pow)    */
+                                    /* instead of only those within 1e-10 of a rounding / cap boundary: same results,     */
+                                    /* one extra pass of the verify stage per new (n, good) pair; for tests               */
+
 typedef struct cvg_ctx cvg_ctx;
 typedef struct cvg_models cvg_models;   /* resident model-view descriptor set                        */
 typedef struct cvg_scenes cvg_scenes;   /* resident batch of scene descriptor sets (bench / multi-GPU)*/
@@ -287,6 +291,15 @@ int  cvg_last_hyp_stats(const cvg_ctx* ctx, float* hyp_ms, int* hyp_launches, ui
 /* hyp_ms above covers the solve kernel (4-point DLT, one launch per round); the inlier counting of those models runs in
  * ransac_score_kernel, one launch per round as well: its summed device time in the last fused call. */
 int  cvg_last_score_ms(const cvg_ctx* ctx, float* score_ms);
+/* Error model of device faults.  The kernels never hang: every wait on a barrier is bounded and ends in a trap.  A trap (or
+ * any other device-side fault) is reported by the call that synchronises — CVG_ERR_CUDA, cvg_last_error() says so — and it
+ * leaves the process' CUDA context in a sticky error state: every later call on that GPU fails the same way, none hangs.
+ * Recovery: cvg_destroy the contexts of that GPU (model sets and scene batches die with them), then cvg_device_reset(device)
+ * — cudaDeviceReset, which also voids every other CUDA user's state in the process — and cvg_create again.  Whether the
+ * driver hands the device back to the SAME process is up to the system: on this pool's B200 boxes it answers "device busy or
+ * unavailable" (cvg_device_reset then returns CVG_ERR_CUDA and says so) and the process has to be restarted; a new process
+ * gets the GPU at once.  cvg_selftest(ctx, 99, &n) injects such a fault on purpose (tests/test_zz_gpu_fault.py). */
+int  cvg_device_reset(int device);
 /* Device self tests.  which = 0: the reciprocal the scoring kernel writes out by hand (MUFU.RCP + one Newton step) against
  * __frcp_rn and against 1.f / x on EVERY float with 2^-126 <= |x| < 2^126; *mismatches must come back 0. */
 int  cvg_selftest(cvg_ctx* ctx, int which, uint64_t* mismatches);

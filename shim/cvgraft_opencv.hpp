@@ -29,11 +29,25 @@ struct ModelSet {
     cvg_models* models = nullptr;
     std::vector<int32_t> view_offsets;            // [V+1] rows of the concatenated descriptor matrix
     std::vector<int> first_view_of_model;         // [M] index of a model's first view in the resident set
+    // The reference recomputes every scaled scene once per model (detectAndCompute sits inside the model loop,
+    // src/TestsDetector.cpp:38,99-106) and detectAtScale is called per (model, scale).  One fused call covers every view of
+    // EVERY model, so its result is kept per scaled scene (keyed on the descriptor bytes) and the calls for the second and
+    // third model are served from it: no scene is uploaded or verified twice.
+    struct SceneResult { uint64_t key = 0; int rows = 0; float scale = 0; std::vector<float> inl; std::vector<int32_t> off; };
+    mutable std::vector<SceneResult> recent;      // the last few scaled scenes (five scales per image)
+    mutable size_t hits = 0, misses = 0;
     ~ModelSet() { if (models) cvg_models_free(ctx, models); if (ctx) cvg_destroy(ctx); }
     ModelSet() = default;
     ModelSet(const ModelSet&) = delete;
     ModelSet& operator=(const ModelSet&) = delete;
 };
+
+// the process-wide resident set the patched reference uses (processAllModelsImages and detectObjects keep their signatures)
+inline ModelSet& residentModels()
+{
+    static ModelSet set;
+    return set;
+}
 
 inline void check(int rc, const char* what)
 {
@@ -117,22 +131,38 @@ inline cv::Mat findHomography(const ModelSet& set, const std::vector<cv::Point2f
 inline void detectAtScale(const ModelSet& set, int m, size_t n_views_of_model, const std::vector<cv::KeyPoint>& sceneKP,
                           const cv::Mat& sceneDesc, float scale, std::vector<cv::Point2f>& allUnfilteredScenePts)
 {
-    std::vector<float> skpt;
-    skpt.reserve(sceneKP.size() * 2);
-    for (const cv::KeyPoint& k : sceneKP) { skpt.push_back(k.pt.x); skpt.push_back(k.pt.y); }
     const std::vector<float> train = continuousRows(sceneDesc);
-    cvg_detect_params p;
-    cvg_detect_params_default(&p);                     // 0.9f, MIN_INLIERS 4, RANSAC 5.0, det in [0.1f, 10.0f]   :21-25
-    const int V = cvg_models_num_views(set.models);
-    std::vector<cvg_pair_result> per_view((size_t)V);
-    std::vector<float> inl(2 * (size_t)cvg_models_num_rows(set.models));
-    std::vector<int32_t> off((size_t)V + 1);
-    check(cvg_detect_pairs(set.ctx, set.models, train.data(), skpt.data(), sceneDesc.rows, scale, &p, per_view.data(),
-                           inl.data(), off.data()), "cvg_detect_pairs");
+    uint64_t key = 1469598103934665603ull;             // FNV-1a over the descriptor bytes
+    {
+        const unsigned char* b = reinterpret_cast<const unsigned char*>(train.data());
+        for (size_t i = 0, n = train.size() * sizeof(float); i < n; ++i) { key ^= b[i]; key *= 1099511628211ull; }
+    }
+    const ModelSet::SceneResult* hit = nullptr;
+    for (const ModelSet::SceneResult& r : set.recent)
+        if (r.key == key && r.rows == sceneDesc.rows && r.scale == scale) { hit = &r; break; }
+    if (!hit) {
+        std::vector<float> skpt;
+        skpt.reserve(sceneKP.size() * 2);
+        for (const cv::KeyPoint& k : sceneKP) { skpt.push_back(k.pt.x); skpt.push_back(k.pt.y); }
+        cvg_detect_params p;
+        cvg_detect_params_default(&p);                 // 0.9f, MIN_INLIERS 4, RANSAC 5.0, det in [0.1f, 10.0f]   :21-25
+        const int V = cvg_models_num_views(set.models);
+        std::vector<cvg_pair_result> per_view((size_t)V);
+        ModelSet::SceneResult r;
+        r.key = key; r.rows = sceneDesc.rows; r.scale = scale;
+        r.inl.resize(2 * (size_t)cvg_models_num_rows(set.models));
+        r.off.resize((size_t)V + 1);
+        check(cvg_detect_pairs(set.ctx, set.models, train.data(), skpt.data(), sceneDesc.rows, scale, &p, per_view.data(),
+                               r.inl.data(), r.off.data()), "cvg_detect_pairs");
+        if (set.recent.size() >= 8) set.recent.erase(set.recent.begin());
+        set.recent.push_back(std::move(r));
+        hit = &set.recent.back();
+        set.misses++;
+    } else set.hits++;
     const int first = set.first_view_of_model[(size_t)m];
     for (int v = first; v < first + (int)n_views_of_model; ++v)
-        for (int j = off[(size_t)v]; j < off[(size_t)v + 1]; ++j)
-            allUnfilteredScenePts.emplace_back(inl[2 * (size_t)j], inl[2 * (size_t)j + 1]);
+        for (int j = hit->off[(size_t)v]; j < hit->off[(size_t)v + 1]; ++j)
+            allUnfilteredScenePts.emplace_back(hit->inl[2 * (size_t)j], hit->inl[2 * (size_t)j + 1]);
 }
 
 }  // namespace cvg

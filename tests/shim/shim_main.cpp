@@ -69,6 +69,18 @@ int main(int argc, char** argv)
             }
     }
     cvg::detectAtScale(set, 0, model.descriptors.size(), sceneKP, sceneDesc, scale, fused);
+    {
+        // the patched reference calls detectAtScale once per (model, scale) on a re-extracted copy of the same scene: the
+        // second call is served from the per-scene result
+        std::vector<cv::Point2f> again;
+        cv::Mat copy(nt, 128, CV_32F);
+        for (int r = 0; r < nt; ++r) memcpy(copy.ptr<float>(r), sceneDesc.ptr<float>(r), 512);
+        cvg::detectAtScale(set, 0, model.descriptors.size(), sceneKP, copy, scale, again);
+        if (again.size() != fused.size() || (fused.size() && memcmp(again.data(), fused.data(), 8 * fused.size())) || set.hits != 1 || set.misses != 1) {
+            fprintf(stderr, "per-scene result cache: hits %zu misses %zu\n", set.hits, set.misses);
+            return 3;
+        }
+    }
     FILE* o = fopen(argv[2], "wb");
     const int32_t n1 = (int32_t)callForCall.size(), n2 = (int32_t)fused.size();
     fwrite(&n1, 4, 1, o); fwrite(&n2, 4, 1, o);

@@ -52,6 +52,31 @@ def test_match_guard_saturated_rows_vs_cv2(api, oracle):
         models.free()
 
 
+# ---------------------------------------------------------------- parity hole 4d: RANSACUpdateNumIters on the host's libm
+def test_niters_from_host_libm_equals_device_math(api, gsynth, feats, gpairs):
+    """The adaptive iteration count depends on log() / pow(); the device normally uses CUDA's and asks the host only when a
+    rounding or cap decision is within 1e-10 of flipping.  With CVG_NITERS_ALL_ON_HOST every evaluation is answered by the
+    host's libm (what OpenCV calls): masks, H, iteration counts and gate decisions must not move, on the cv2 goldens."""
+    off = gsynth["fh_offsets"]
+    with api.Context(0) as c0, api.Context(0, api.NITERS_ALL_ON_HOST) as c1:
+        a = c0.find_homography_batch(gsynth["fh_src"], gsynth["fh_dst"], off, want_ransac_mask=True)
+        b = c1.find_homography_batch(gsynth["fh_src"], gsynth["fh_dst"], off, want_ransac_mask=True)
+        for k in ("H", "mask", "found", "iters", "ransac_mask"):
+            assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(b["mask"], gsynth["fh_mask"]) and (b["iters"] < 2000).any() and (b["iters"] > 0).any()
+        # fused path on the real pairs of the small feature cache (statuses pinned to cv2 by golden_pairs.npz)
+        md = feats["model_desc"].astype(np.float32); so = feats["scene_offsets"]
+        scales = np.tile(feats["scales"], (len(so) - 1) // 5)
+        outs = []
+        for c in (c0, c1):
+            m = c.upload_models(md, feats["model_kpt"], feats["view_offsets"], feats["view_model"])
+            sc = c.upload_scenes(feats["scene_desc"].astype(np.float32), feats["scene_kpt"], so)
+            outs.append(c.detect_scenes_inliers(m, sc, scales=scales))
+            sc.free(); m.free()
+        _same(outs[0], outs[1])
+        assert np.array_equal(outs[1][0]["status"], gpairs["status"].astype(np.int32))
+
+
 # ---------------------------------------------------------------- lanes
 def _scene_batch(rng, n_scenes, nq=1500, nt_lo=900, nt_hi=2600):
     q = synth.sift_like(rng, nq)

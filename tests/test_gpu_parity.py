@@ -599,4 +599,34 @@ def test_full_dataset_13350_pairs_vs_cv2(ctx):
     rel = np.abs(res["H"][has_h] - G["H"][has_h]) / np.maximum(np.abs(G["H"][has_h]), 1e-12)
     assert rel.max() < 1e-5
     assert np.bincount(res["status"].ravel(), minlength=5).tolist() == [1308, 83, 116, 1182, 10661]
-    scenes.free(); models.free()
+    # what the reference consumes (src/TestsDetector.cpp:87-94): the inlier scene points of all 1 308 accepted pairs, divided
+    # by the scale, pair after pair — bit for bit cv2's
+    res2, xy, off = ctx.detect_scenes_inliers(models, scenes, scales=np.tile(Z["scales"], (len(so) - 1) // 5))
+    assert res2.tobytes() == res.tobytes()
+    assert np.array_equal(off, G["inlier_offsets"])
+    assert np.array_equal(xy, G["inlier_xy"]) and len(xy) == 17506
+    scenes.free()
+    # the returned inlier MASK of every pair that reaches findHomography (:78), accepted or not: the pairs' correspondences are
+    # rebuilt from the match stage and verified in one batch per scaled scene
+    vo = Z["view_offsets"]; mk = Z["model_kpt"]; V = len(vo) - 1
+    gmask = np.unpackbits(G["mask"])[:G["mask_offsets"][-1]]; moff = G["mask_offsets"]
+    n_masks = 0
+    for s in range(0, len(so) - 1):
+        t = Z["scene_desc"][so[s]:so[s + 1]].astype(np.float32); tk = Z["scene_kpt"][so[s]:so[s + 1]]
+        idx, dist, acc = ctx.match_knn2(models, t)
+        src, dst, offs, views = [], [], [0], []
+        for v in range(V):
+            sel = np.nonzero(acc[vo[v]:vo[v + 1]])[0] + vo[v]
+            assert len(sel) == G["n_good"][s, v]
+            if len(sel) >= 4:
+                src.append(mk[sel]); dst.append(tk[idx[sel, 0]]); offs.append(offs[-1] + len(sel)); views.append(v)
+        if not views:
+            continue
+        out = ctx.find_homography_batch(np.concatenate(src), np.concatenate(dst), offs)
+        for k, v in enumerate(views):
+            a, b = moff[s * V + v], moff[s * V + v + 1]
+            assert np.array_equal(out["mask"][offs[k]:offs[k + 1]], gmask[a:b]), (s, v)
+            assert bool(out["found"][k]) == (G["status"][s, v] != 2)
+            n_masks += 1
+    assert n_masks == 13350 - 83                               # every pair with >= 4 matches
+    models.free()

@@ -2,10 +2,13 @@
 in libcvgraft, consumer restated in host/detect_objects.cpp) in the reference's layout
 (output/<folder>/<scene>_results.txt, src/Output.cpp:46, src/utils.cpp:12-20).
 
-tests/golden/replay_output/ holds the files of a B200 run over the whole dataset.  They are checked against
+tests/golden/replay_output/ is derived from cv2 itself: the inlier scene points cv2 4.13.0 returns for the 1 308 accepted pairs
+of the loop nest (tests/golden/full_dataset_cv2.npz, tools/full_dataset_replay.py --cv2) pushed through the C++ consumer
+(tools/make_replay_golden.py) — no GPU result is involved.  The files are checked against
+ (0) a regeneration from the committed cv2 points on the CPU,
  (1) the survey's independent replay with cv2 (SURVEY App. C.3 detections, Mean IoU 0.351, accuracy 12/14, 2/14, 2/14),
  (2) the reference's own metrics code compiled from /root/reference (oracle/_ref/metrics_ref, build container only),
-and the GPU test re-runs the driver and compares the files byte for byte."""
+and the GPU test runs the driver (one GPU; every GPU of the box behind cvg_create_multi) and compares byte for byte."""
 import os
 import subprocess
 
@@ -50,6 +53,21 @@ def find(folder_scene):
     return os.path.join(GOLD, folder, hits[0])
 
 
+def test_golden_results_are_the_consumer_on_cv2_points():
+    """The committed results files = cv2's inlier points (full_dataset_cv2.npz) through host/libcvghost_consumer.so."""
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_replay_golden as mg
+    from computervision_objectdetection_featurematching_b200 import build
+    build.build()                                               # the consumer library links against libcvgraft
+    G = np.load(os.path.join(ROOT, "tests", "golden", "full_dataset_cv2.npz"))
+    files = mg.results_from_points(G, mg.consumer())
+    assert len(files) == 30
+    for (folder, scene), text in files.items():
+        assert open(os.path.join(GOLD, folder, scene + "_results.txt")).read() == text, (folder, scene)
+
+
 def test_golden_results_match_survey_anchors():
     assert sum(len(fs) for _, _, fs in os.walk(GOLD)) == 30
     for key, boxes in ANCHORS.items():
@@ -78,12 +96,17 @@ def test_cpp_driver_reproduces_golden_results(tmp_path):
         pytest.skip("binary feature cache not built (python __graft_entry__.py in the build container)")
     if not os.path.exists(exe):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "host"), "cvg_replay"])
-    out = str(tmp_path / "output")
-    r = subprocess.run([exe, cache, out], capture_output=True, text=True, cwd=os.path.join(ROOT, "host"))
-    assert r.returncode == 0, r.stdout + r.stderr
-    n = 0
-    for folder in os.listdir(GOLD):
-        for f in os.listdir(os.path.join(GOLD, folder)):
-            assert open(os.path.join(out, folder, f)).read() == open(os.path.join(GOLD, folder, f)).read(), (folder, f)
-            n += 1
-    assert n == 30
+    import torch
+    runs = [["--sync"], []]                                       # synchronous calls; three images in flight from one thread
+    if torch.cuda.device_count() >= 2:
+        runs.append(["--gpus", str(torch.cuda.device_count())])   # cvg_create_multi: images dealt to the GPUs in turn
+    for k, extra in enumerate(runs):
+        out = str(tmp_path / f"output{k}")
+        r = subprocess.run([exe, cache, out] + extra, capture_output=True, text=True, cwd=os.path.join(ROOT, "host"))
+        assert r.returncode == 0, r.stdout + r.stderr
+        n = 0
+        for folder in os.listdir(GOLD):
+            for f in os.listdir(os.path.join(GOLD, folder)):
+                assert open(os.path.join(out, folder, f)).read() == open(os.path.join(GOLD, folder, f)).read(), (extra, folder, f)
+                n += 1
+        assert n == 30

@@ -41,42 +41,86 @@ def run_gpu(Z):
     return res
 
 
-def run_cv2(Z):
+_Z = None
+
+
+def _cv2_scene(s):
+    """One scaled scene against all 89 views with cv2 — the reference's arithmetic for src/TestsDetector.cpp:58-95, incl.
+    the inlier mask (:78) and the inlier scene points divided by the scale (:87-94, :48-55)."""
     import cv2
-    from multiprocessing import Pool
+    cv2.setNumThreads(1)
+    Z = _Z
     md = Z["model_desc"].astype(np.float32); mk = Z["model_kpt"]; vo = Z["view_offsets"]; so = Z["scene_offsets"]
-    S = len(so) - 1; V = len(vo) - 1
-    out = np.zeros((S, V), dtype=[("status", "<i4"), ("n_good", "<i4"), ("n_inliers", "<i4"), ("H", "<f8", (9,))])
-    bf = cv2.BFMatcher(cv2.NORM_L2)
-    t0 = time.time()
-    for s in range(S):
-        t = Z["scene_desc"][so[s]:so[s + 1]].astype(np.float32); tk = Z["scene_kpt"][so[s]:so[s + 1]]
-        m = bf.knnMatch(md, t, 2)
-        idx = np.array([[a.trainIdx, b.trainIdx] for a, b in m]); dist = np.array([[a.distance, b.distance] for a, b in m], np.float32)
-        acc = dist[:, 0] < np.float32(0.9) * dist[:, 1]
-        for v in range(V):
-            sel = np.nonzero(acc[vo[v]:vo[v + 1]])[0] + vo[v]
-            out["n_good"][s, v] = len(sel)
-            if len(sel) < 4:
-                out["status"][s, v] = 1; continue
-            H, mask = cv2.findHomography(mk[sel], tk[idx[sel, 0]], cv2.RANSAC, 5.0)
+    V = len(vo) - 1
+    scale = np.float32(Z["scales"][s % 5])
+    out = np.zeros(V, dtype=[("status", "<i4"), ("n_good", "<i4"), ("n_inliers", "<i4"), ("H", "<f8", (9,))])
+    masks, pts = [], []
+    t = Z["scene_desc"][so[s]:so[s + 1]].astype(np.float32); tk = Z["scene_kpt"][so[s]:so[s + 1]].astype(np.float32)
+    m = cv2.BFMatcher(cv2.NORM_L2).knnMatch(md, t, 2)
+    idx = np.array([[a.trainIdx, b.trainIdx] for a, b in m]); dist = np.array([[a.distance, b.distance] for a, b in m], np.float32)
+    acc = dist[:, 0] < np.float32(0.9) * dist[:, 1]
+    for v in range(V):
+        sel = np.nonzero(acc[vo[v]:vo[v + 1]])[0] + vo[v]
+        out["n_good"][v] = len(sel)
+        mask = np.zeros(len(sel), np.uint8); inl = np.zeros((0, 2), np.float32)
+        if len(sel) < 4:
+            out["status"][v] = 1
+        else:
+            H, mk_ = cv2.findHomography(mk[sel], tk[idx[sel, 0]], cv2.RANSAC, 5.0)
             if H is None:
-                out["status"][s, v] = 2; continue
-            out["H"][s, v] = H.ravel(); out["n_inliers"][s, v] = int(mask.sum())
-            if mask.sum() < 4:
-                out["status"][s, v] = 3; continue
-            d = abs(np.linalg.det(H))
-            m0 = H.ravel(); d = abs(m0[0] * (m0[4] * m0[8] - m0[5] * m0[7]) - m0[1] * (m0[3] * m0[8] - m0[5] * m0[6]) + m0[2] * (m0[3] * m0[7] - m0[4] * m0[6]))
-            out["status"][s, v] = 4 if (d < np.float32(0.1) or d > np.float32(10.0)) else 0
-        print(f"scene-scale {s + 1}/{S}  {time.time() - t0:.0f}s", flush=True)
-    return out
+                out["status"][v] = 2
+            else:
+                mask = mk_.ravel().astype(np.uint8)
+                out["H"][v] = H.ravel(); out["n_inliers"][v] = int(mask.sum())
+                if mask.sum() < 4:
+                    out["status"][v] = 3
+                else:
+                    m0 = H.ravel(); d = abs(m0[0] * (m0[4] * m0[8] - m0[5] * m0[7]) - m0[1] * (m0[3] * m0[8] - m0[5] * m0[6]) + m0[2] * (m0[3] * m0[7] - m0[4] * m0[6]))
+                    out["status"][v] = 4 if (d < np.float32(0.1) or d > np.float32(10.0)) else 0
+                    if out["status"][v] == 0:
+                        inl = tk[idx[sel, 0]][mask != 0].astype(np.float32)
+                        if scale != np.float32(1.0):
+                            inl = (inl / scale).astype(np.float32)          # fp32 divide, as scalePoints does
+        masks.append(mask); pts.append(inl)
+    return s, out, masks, pts
+
+
+def run_cv2(Z):
+    """-> per-pair records [S, V], the returned inlier masks of every pair (concatenated, pair order) and the inlier scene
+    points of the ACCEPTED pairs as the reference appends them (concatenated, pair order)."""
+    global _Z
+    from multiprocessing import Pool
+    _Z = Z
+    S = len(Z["scene_offsets"]) - 1; V = len(Z["view_offsets"]) - 1
+    out = np.zeros((S, V), dtype=[("status", "<i4"), ("n_good", "<i4"), ("n_inliers", "<i4"), ("H", "<f8", (9,))])
+    masks = [None] * S; pts = [None] * S
+    t0 = time.time()
+    with Pool(os.cpu_count()) as pool:
+        for k, (s, o, mk, pt) in enumerate(pool.imap_unordered(_cv2_scene, range(S))):
+            out[s] = o; masks[s] = mk; pts[s] = pt
+            print(f"scene-scale {k + 1}/{S}  {time.time() - t0:.0f}s", flush=True)
+    mask_off = np.zeros(S * V + 1, np.int64); inl_off = np.zeros(S * V + 1, np.int64)
+    for s in range(S):
+        for v in range(V):
+            mask_off[s * V + v + 1] = mask_off[s * V + v] + len(masks[s][v])
+            inl_off[s * V + v + 1] = inl_off[s * V + v] + len(pts[s][v])
+    mask_cat = np.concatenate([m for ms in masks for m in ms]) if S else np.zeros(0, np.uint8)
+    inl_cat = np.concatenate([p for ps in pts for p in ps]).astype(np.float32) if S else np.zeros((0, 2), np.float32)
+    return out, mask_cat, mask_off, inl_cat, inl_off
 
 
 if __name__ == "__main__":
     Z = load()
     if "--cv2" in sys.argv:
-        out = run_cv2(Z)
+        out, mask_cat, mask_off, inl_cat, inl_off = run_cv2(Z)
         np.savez_compressed(os.path.join(ROOT, "data_cache", "replay_cv2.npz"), res=out)
+        # the committed golden: gate records + returned masks + the accepted pairs' inlier scene points (src/TestsDetector.cpp:87-94)
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "full_dataset_cv2.npz"), status=out["status"].astype(np.int8),
+                            n_good=out["n_good"], n_inliers=out["n_inliers"], H=out["H"], mask=np.packbits(mask_cat),
+                            mask_offsets=mask_off, inlier_xy=inl_cat, inlier_offsets=inl_off,
+                            # what the consumer + results writer need besides the points (tools/make_replay_golden.py)
+                            view_model=Z["view_model"], model_names=Z["model_names"], scene_names=Z["scene_names"],
+                            scene_folder=Z["scene_folder"])
     elif "--compare" in sys.argv:
         a = np.load(os.path.join(ROOT, "data_cache", "replay_cv2.npz"))["res"]
         b = np.load(os.path.join(ROOT, "gpurun_out", "replay_gpu.npz"))["res"]
