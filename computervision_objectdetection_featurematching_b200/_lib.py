@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libcvgraft.so")
+SO_PATH = os.environ.get("CVGRAFT_SO") or os.path.join(HERE, "libcvgraft.so")      # CVGRAFT_SO: A/B builds of experiments
 
 
 class RansacParams(C.Structure):
@@ -70,6 +70,7 @@ SYMBOLS = {
     "cvg_last_score_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "cvg_selftest": (C.c_int, [_P, C.c_int, C.POINTER(C.c_uint64)]),
     "cvg_trace_dump": (None, []),
+    "cvg_debug_words": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int]),
     "cvg_device_reset": (C.c_int, [C.c_int]),
 }
 

@@ -6,7 +6,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SO = os.path.join(HERE, "libcvgraft.so")
+SO = os.environ.get("CVGRAFT_SO") or os.path.join(HERE, "libcvgraft.so")
 SOURCES = ["api.cu", "multi.cu", "prep.cu", "match_exact.cu", "match_tc.cu", "ransac.cu"]
 HEADERS = ["common.cuh", "ctx.cuh", "homography_math.cuh", "jacobi_warp.cuh", "jacobi_thread.cuh", os.path.join("..", "..", "include", "cvgraft.h")]
 # -fmad=false: the verify stage and the exact match kernel must not contract a*b+c (OpenCV's baseline
@@ -22,7 +22,7 @@ def nvcc():
     raise RuntimeError("nvcc not found")
 
 
-OBJ_DIR = os.path.join(HERE, "build")
+OBJ_DIR = os.environ.get("CVGRAFT_OBJ_DIR") or os.path.join(HERE, "build")
 COMPILE_FLAGS = [f for f in NVCC_FLAGS if f != "--shared"]
 
 

@@ -190,6 +190,15 @@ void eng_destroy(cvg_ctx* c)
 
 extern "C" {
 
+int cvg_debug_words(const cvg_ctx* c0, int* out, int n)
+{
+    const cvg_ctx* c = cvg_primary(c0);
+    if (!c || !out || n < 0 || n > 64) return set_err(CVG_ERR_INVALID, "cvg_debug_words: bad argument");
+    CU_CHECK(cudaSetDevice(c->device));
+    CU_CHECK(cudaMemcpy(out, c->d_flags, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return CVG_OK;
+}
+
 int cvg_device_reset(int device)
 {
     // cudaDeviceReset: the only way out of a sticky error.  Every handle of this device (contexts, model sets, scene batches,

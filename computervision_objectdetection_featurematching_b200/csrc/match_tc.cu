@@ -201,6 +201,57 @@ __device__ __forceinline__ void top2_insert4(const uint32_t* r4, int c, float& b
     }
 }
 
+// The same for a group of 4 columns whose maximum gmax is known to exceed f.  Nearly always exactly ONE column of the group
+// is a candidate, so the maximum is inserted without branches (its column = the first one equal to gmax) and only a second
+// candidate in the same group — the largest of the other three still above the raised filter — takes the generic path.
+// Inserting the maximum first gives the result of the ascending scan: among equal values the first column goes in first,
+// and a smaller value that is inserted after a larger one lands where the ascending scan would have left it.
+struct Top2State { float b1; int i1; float b2; int i2; float f; };
+#ifndef TC_OUTLINE_SLOW
+#define TC_OUTLINE_SLOW 0       // measured: the outlined slow path halves the kernel (3048 -> 1608 SASS instructions) but costs 7 % (call overhead)
+#endif
+#if TC_OUTLINE_SLOW
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+Top2State top2_insert_group_impl(float v0, float v1, float v2, float v3, int c, float gmax, Top2State st)
+{
+    float b1 = st.b1, b2 = st.b2, f = st.f; int i1 = st.i1, i2 = st.i2;
+    int j = 3;
+    j = (v2 == gmax) ? 2 : j; j = (v1 == gmax) ? 1 : j; j = (v0 == gmax) ? 0 : j;
+    const bool top = gmax > b1;
+    b2 = top ? b1 : gmax; i2 = top ? i1 : c + j;
+    b1 = top ? gmax : b1; i1 = top ? c + j : i1;
+    f = fmaxf(f, b2);
+    const float w0 = j == 0 ? -INFINITY : v0, w1 = j == 1 ? -INFINITY : v1, w2 = j == 2 ? -INFINITY : v2, w3 = j == 3 ? -INFINITY : v3;
+    if (fmaxf(fmaxf(w0, w1), fmaxf(w2, w3)) > f) {
+        const float w[4] = { w0, w1, w2, w3 };
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float v = w[k];
+            if (v > f) {
+                if (v > b1) { b2 = b1; i2 = i1; b1 = v; i1 = c + k; }
+                else        { b2 = v; i2 = c + k; }
+                f = fmaxf(f, b2);
+            }
+        }
+    }
+    return Top2State{ b1, i1, b2, i2, f };
+}
+__device__ __forceinline__ void top2_insert_group(const uint32_t* r4, int c, float gmax, float& b1, int& i1, float& b2, int& i2, float& f)
+{
+    const Top2State st = top2_insert_group_impl(__uint_as_float(r4[0]), __uint_as_float(r4[1]), __uint_as_float(r4[2]), __uint_as_float(r4[3]),
+                                                c, gmax, Top2State{ b1, i1, b2, i2, f });
+    b1 = st.b1; i1 = st.i1; b2 = st.b2; i2 = st.i2; f = st.f;
+}
+
+#ifdef TC_PROF
+__device__ int g_prof_entries[4];
+#define PROF_ENTRY(k) { const unsigned am__ = __activemask(); if ((int)(threadIdx.x & 31) == __ffs(am__) - 1) { atomicAdd(&g_prof_entries[k], 1); atomicAdd(&g_prof_entries[k + 1], __popc(am__)); } }
+#else
+#define PROF_ENTRY(k)
+#endif
 __device__ __forceinline__ void top2_scan32(const uint32_t* r, int c0, float& b1, int& i1, float& b2, int& i2, float& f)
 {
     float g[8];
@@ -215,10 +266,27 @@ __device__ __forceinline__ void top2_scan32(const uint32_t* r, int c0, float& b1
         #pragma unroll
         for (int e = 1; e < TOP2_GROUPS_PER_TEST; e++) gm = fmaxf(gm, g[k + e]);
         if (gm > f) {
+            PROF_ENTRY(0)
             #pragma unroll
             for (int e = 0; e < TOP2_GROUPS_PER_TEST; e++)
-                if (g[k + e] > f) top2_insert4(r + 4 * (k + e), c0 + 4 * (k + e), b1, i1, b2, i2, f);
+                if (g[k + e] > f) top2_insert_group(r + 4 * (k + e), c0 + 4 * (k + e), g[k + e], b1, i1, b2, i2, f);
         }
+    }
+}
+
+// The first tile(s) of a unit: no filter exists yet, every group of columns holds candidates for every row, and the branchy
+// scan above would run its slow path 16 times per tile with all 32 lanes diverging.  Here every column is inserted without
+// a branch (strict >: ties keep the earlier column, as the ascending scan does).
+__device__ __forceinline__ void top2_dense32(const uint32_t* r, int c0, float& b1, int& i1, float& b2, int& i2)
+{
+    #pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const float v = __uint_as_float(r[j]);
+        const bool gt1 = v > b1, gt2 = v > b2;
+        b2 = gt1 ? b1 : (gt2 ? v : b2);
+        i2 = gt1 ? i1 : (gt2 ? c0 + j : i2);
+        b1 = gt1 ? v : b1;
+        i1 = gt1 ? c0 + j : i1;
     }
 }
 
@@ -290,6 +358,12 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
     // exp_mode (experiments only, set through CVG_TC_EXP): bit 0 = epilogue releases the accumulator without
     // scanning it, bit 1 = the producer re-arms ring stages without issuing the B loads
     if (gate_flag && *gate_flag != gate_want) return;
+#ifdef TC_PROF
+    if (blockIdx.x == 0 && threadIdx.x == 0 && dbg) {        // slow-path entries of the PREVIOUS launch: warp level, lane level
+        dbg[34] = g_prof_entries[0]; dbg[35] = g_prof_entries[1];
+        g_prof_entries[0] = 0; g_prof_entries[1] = 0;
+    }
+#endif
     constexpr bool SPLIT = KP == 4;                  // hi/lo split operands (non-integer descriptors)
     static_assert(!(SPLIT && PAIR), "pair mode serves the exact (integer descriptor) form only");
     constexpr int N_STAGES_PER_TILE = SPLIT ? 4 : 2;
@@ -419,6 +493,14 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
         // ===================== MMA issuer =====================
         if (lane == 0 && leader) {                   // pair mode: the leader CTA issues for both
             uint32_t ua = 0, bs = 0, tc = 0;
+#ifdef TC_PROF
+            long long w_a = 0, w_t = 0, w_b = 0, w_g = 0, q0 = 0; const long long m_start = clock64();
+#define MPROF_BEGIN q0 = clock64();
+#define MPROF_END(acc) acc += clock64() - q0;
+#else
+#define MPROF_BEGIN
+#define MPROF_END(acc)
+#endif
             auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t accumulate) {
                 if constexpr (PAIR) tc_mma_bf16_pair(d, da, db, TC_IDESC_PAIR, accumulate);
                 else tc_mma_bf16(d, da, db, TC_IDESC, accumulate);
@@ -427,16 +509,16 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
             for (int e = worker; e < n_entries; e += n_workers, ua++) {
                 const int n_tiles = units[unit_of(e)].n_tiles;
                 const uint32_t ab = SPLIT ? 0u : (ua & 1);
-                mbar_wait(a_full + 8 * ab, SPLIT ? (ua & 1) : ((ua >> 1) & 1), dbg, 3);
+                MPROF_BEGIN mbar_wait(a_full + 8 * ab, SPLIT ? (ua & 1) : ((ua >> 1) & 1), dbg, 3); MPROF_END(w_a)
                 const uint32_t sa = smem_base + OFF_A + ab * A_BYTES;
                 for (int t = 0; t < n_tiles; t++, tc++) {
                     const uint32_t acc = tc & 1;
-                    mbar_wait(t_empty + 8 * acc, ((tc >> 1) & 1) ^ 1, dbg, 5);
+                    MPROF_BEGIN mbar_wait(t_empty + 8 * acc, ((tc >> 1) & 1) ^ 1, dbg, 5); MPROF_END(w_t)
                     const uint32_t d_tmem = tmem_base + acc * TILE_N;
                     #pragma unroll 1
                     for (int h = 0; h < N_STAGES_PER_TILE; h++, bs++) {
                         const uint32_t s = bs % NB;
-                        mbar_wait(b_full + 8 * s, (bs / NB) & 1, dbg, 4);
+                        MPROF_BEGIN mbar_wait(b_full + 8 * s, (bs / NB) & 1, dbg, 4); MPROF_END(w_b)
                         tc_fence_after();
                         const uint32_t sb = smem_base + OFF_B + s * STAGE_BYTES;
                         #pragma unroll
@@ -456,7 +538,7 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                     }
                     {
                         const uint32_t g = tc % NG;
-                        mbar_wait(g_full + 8 * g, (tc / NG) & 1, dbg, 8);
+                        MPROF_BEGIN mbar_wait(g_full + 8 * g, (tc / NG) & 1, dbg, 8); MPROF_END(w_g)
                         tc_fence_after();
                         mma(d_tmem, desc_sw32(sa + (SPLIT ? 4 : 2) * A_ATOM_BYTES),
                             desc_sw32(smem_base + OFF_BAUG + g * G_BYTES), 1u);
@@ -466,6 +548,12 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                 }
                 commit(a_empty + 8 * ab);
             }
+#ifdef TC_PROF
+            if ((exp_mode & 32) && dbg && blockIdx.x == 0) {
+                int* o = dbg + 28;
+                o[0] = (int)tc; o[1] = (int)(w_a / 64); o[2] = (int)(w_t / 64); o[3] = (int)(w_b / 64); o[4] = (int)(w_g / 64); o[5] = (int)((clock64() - m_start) / 64);
+            }
+#endif
         }
     } else {
         // ===================== epilogue =====================
@@ -485,31 +573,56 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
         asm volatile("bar.sync 1, %0;" :: "n"(32 * TC_EPI_WARPS) : "memory");
         if constexpr (KP == 2) {
             uint32_t tc = 0;
+            // exp bit 5: cycle counts of the phases of this warp's tile loop, summed over its tiles (debug words 12..)
+#ifdef TC_PROF
+            const bool prof = (exp_mode & 32) != 0;
+#else
+            constexpr bool prof = false;
+#endif
+            long long c_wait = 0, c_ld = 0, c_share = 0, c_scan = 0, c_tiles = 0, c_flush = 0, c_unit = 0, t0 = 0, t1 = 0, tu = 0;
+            const long long t_start = prof ? clock64() : 0;
             for (int e = worker; e < n_entries; e += n_workers) {
+                if (prof) tu = clock64();
                 const MatchUnit un = units[unit_of(e)];
-                float b1 = -INFINITY, b2 = -INFINITY, f = -INFINITY;
+                float b1 = -INFINITY, b2 = -INFINITY, f = (exp_mode & 4) ? INFINITY : -INFINITY;   // exp bit 2: nothing ever passes the filter
                 int i1 = -1, i2 = -1;
+                if (prof) { t1 = clock64(); c_unit += t1 - tu; }
                 // Measured and rejected: two groups of 8 warps taking alternate tiles (128 columns per warp): 1.21 ms instead
                 // of 1.10 ms per 64 pairs — the epilogue is bound by its instruction stream (~250 per warp and tile, four
                 // warps per scheduler), not by the latency of one tile's chain.
                 for (int t = 0; t < un.n_tiles; t++, tc++) {
                     const uint32_t acc = tc & 1;
+                    if (prof) t0 = clock64();
+                    // The filter update (what the other three column parts of these rows have found so far) runs BEFORE the wait for
+                    // the next accumulator: the tile loop is paced by its slowest warp (the accumulator is released when all 16
+                    // have loaded it), so whatever a warp can do while it would wait anyway is off the critical path.
+                    auto update_filter = [&]() {
+                        if (t > 0 && !(exp_mode & 8)) {               // exp bit 3: no filter sharing between the column parts
+                            float o1[3], o2[3];
+                            #pragma unroll
+                            for (int pp = 0; pp < 3; pp++) {
+                                const int op = (part + 1 + pp) & 3;
+                                share_load(share + (uint32_t)(op * TILE_M + row_in_tile) * 8u, o1[pp], o2[pp]);
+                            }
+                            // second largest of the four bests, and the largest of the four seconds
+                            const float m1 = fmaxf(b1, o1[0]), n1 = fminf(b1, o1[0]);
+                            const float m2 = fmaxf(o1[1], o1[2]), n2 = fminf(o1[1], o1[2]);
+                            const float second_best = fmaxf(fminf(m1, m2), fmaxf(n1, n2));
+                            const float foreign = fmaxf(fmaxf(second_best, o2[0]), fmaxf(o2[1], o2[2]));
+                            f = fmaxf(f, float_pred(foreign));
+                        }
+                    };
+#ifndef TC_SHARE_AFTER_WAIT
+#define TC_SHARE_AFTER_WAIT 0                         // A/B: 1 = the round-1 order (wait, filter update, loads)
+#endif
+                    // (Measured and rejected: letting a warp that is late — accumulator already there — skip the update: its filter goes
+                    // stale, it enters the slow path far more often and falls further behind: 1.11 -> 1.27 ms per 64 pairs.)
+                    if (!TC_SHARE_AFTER_WAIT) update_filter();
+                    if (prof) { t1 = clock64(); c_share += t1 - t0; t0 = t1; }
                     mbar_wait(t_full + 8 * acc, (tc >> 1) & 1, dbg, 6);
                     tc_fence_after();
-                    if (t > 0) {
-                        float o1[3], o2[3];
-                        #pragma unroll
-                        for (int pp = 0; pp < 3; pp++) {
-                            const int op = (part + 1 + pp) & 3;
-                            share_load(share + (uint32_t)(op * TILE_M + row_in_tile) * 8u, o1[pp], o2[pp]);
-                        }
-                        // second largest of the four bests, and the largest of the four seconds
-                        const float m1 = fmaxf(b1, o1[0]), n1 = fminf(b1, o1[0]);
-                        const float m2 = fmaxf(o1[1], o1[2]), n2 = fminf(o1[1], o1[2]);
-                        const float second_best = fmaxf(fminf(m1, m2), fmaxf(n1, n2));
-                        const float foreign = fmaxf(fmaxf(second_best, o2[0]), fmaxf(o2[1], o2[2]));
-                        f = fmaxf(f, float_pred(foreign));
-                    }
+                    if (prof) { t1 = clock64(); c_wait += t1 - t0; t0 = t1; c_tiles++; }
+                    if (TC_SHARE_AFTER_WAIT) update_filter();
                     const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TILE_N + part * 64;
                     const int col_base = un.t_local0 + t * TILE_N + part * 64;
                     if (!(exp_mode & 1)) {
@@ -517,14 +630,33 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                         tc_ld32(tbase, ra);                           // two loads in flight before the wait
                         tc_ld32(tbase + 32, rb);
                         tc_wait_ld();
-                        // the warp's 64 columns are in registers: the accumulator goes back to the MMA issuer BEFORE the
-                        // scan, so the next-but-one tile's MMAs overlap it (1.14 -> 1.10 ms per 64 pairs)
+                        if (prof) { t1 = clock64(); c_ld += t1 - t0; t0 = t1; }
+                        // The warp's 64 columns are in registers: the accumulator goes back to the MMA issuer at once — before
+                        // the filter update and before the scan — so that the next-but-one tile's MMAs start as early as they
+                        // can (the MMA issuer waited 394 cycles per tile for this arrival when the filter update came first).
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) { if constexpr (PAIR) mbar_arrive_leader(t_empty + 8 * acc); else mbar_arrive(t_empty + 8 * acc); }
-                        top2_scan32(ra, col_base, b1, i1, b2, i2, f);
-                        top2_scan32(rb, col_base + 32, b1, i1, b2, i2, f);
+                        if (exp_mode & 16) {                          // exp bit 4: loads, no scan (the values are consumed by one OR chain)
+                            uint32_t acc_or = 0;
+                            #pragma unroll
+                            for (int k = 0; k < 32; k++) acc_or |= ra[k] | rb[k];
+                            if (acc_or == 0x12345678u) b1 = 1.f;
+                        } else {
+#ifndef TC_DENSE_TILES
+#define TC_DENSE_TILES 0
+#endif
+                            if (t < TC_DENSE_TILES && !(exp_mode & 4)) {
+                                top2_dense32(ra, col_base, b1, i1, b2, i2);
+                                top2_dense32(rb, col_base + 32, b1, i1, b2, i2);
+                                f = fmaxf(f, b2);
+                            } else {
+                                top2_scan32(ra, col_base, b1, i1, b2, i2, f);
+                                top2_scan32(rb, col_base + 32, b1, i1, b2, i2, f);
+                            }
+                        }
                         share_store(my_share, b1, b2);
+                        if (prof) { t1 = clock64(); c_scan += t1 - t0; }
                     } else {
                         tc_fence_before();
                         __syncwarp();
@@ -532,6 +664,7 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                     }
                 }
                 // ---- unit flush: merge the four column parts, convert to distances, write the partial ----
+                if (prof) t0 = clock64();
                 share_store(my_share, -INFINITY, -INFINITY);     // reset before the barriers below
                 if (b1 < ABSENT_BELOW) { i1 = -1; }
                 if (b2 < ABSENT_BELOW) { i2 = -1; }
@@ -563,6 +696,12 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                     reinterpret_cast<Top2*>(parts_out)[(size_t)un.part_slot * TILE_M + row_in_tile] = out;
                 }
                 asm volatile("bar.sync 1, %0;" :: "n"(32 * TC_EPI_WARPS) : "memory");
+                if (prof) c_flush += clock64() - t0;
+            }
+            if (prof && dbg && blockIdx.x == 0 && lane == 0 && (ew == 0 || ew == 15)) {
+                int* o = dbg + 12 + (ew == 0 ? 0 : 8);
+                o[0] = (int)c_tiles; o[1] = (int)(c_wait / 64); o[2] = (int)(c_share / 64); o[3] = (int)(c_ld / 64); o[4] = (int)(c_scan / 64);
+                o[5] = (int)(c_flush / 64); o[6] = (int)(c_unit / 64); o[7] = (int)((clock64() - t_start) / 64);
             }
         } else {
             uint32_t tc = 0;

@@ -306,6 +306,8 @@ int  cvg_selftest(cvg_ctx* ctx, int which, uint64_t* mismatches);
 /* Debugging aid: with CVG_TRACE=1 in the environment the library timestamps its uploads and fused calls on their streams;
  * this prints the device timeline to stderr and clears it. */
 void cvg_trace_dump(void);
+/* Debugging aid: the context's device status words (row kinds, match path, counters, kernel debug words; csrc/ctx.cuh). */
+int  cvg_debug_words(const cvg_ctx* ctx, int* out, int n);
 
 #ifdef __cplusplus
 }
