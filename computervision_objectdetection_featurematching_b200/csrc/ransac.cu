@@ -950,9 +950,11 @@ __device__ int update_num_iters_checked(const RansacWork& w, int n, int good, in
     if (found < 0 && w.nit_req) {
         bool unsure = zero || !(denom < 0);           // never reached with good >= 4; let the host decide if it is
         if (!unsure) {
+            // q >= niters: the cap wins and nothing is rounded; only a quotient within the margin of the cap, or — below the
+            // cap — within the margin of a half-integer, could come out differently with the host's log / pow
             const double q = num / denom;
-            const double m = w.nit_margin * (fabs(q) + 1.);
-            unsure = fabs(q - floor(q) - 0.5) < m || fabs(q - (double)niters) < m;
+            const double m = w.nit_margin * ((double)niters + 1.);
+            unsure = fabs(q - (double)niters) < m || (q < (double)niters && fabs(q - floor(q) - 0.5) < m);
         }
         if (unsure && lane == 0) {
             const int slot = atomicAdd(w.nit_req_n, 1);

@@ -2,3 +2,5 @@ set -x
 mkdir -p gpurun_out
 timeout 1800 python -m pytest tests -m gpu -x -q > gpurun_out/r02c_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r02c_pytest.log
 tail -6 gpurun_out/r02c_pytest.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu --no-extras 2>/dev/null | cut -c1-200
