@@ -575,7 +575,7 @@ static int run_ransac(cvg_ctx* c, const float4* d_pts, const int64_t* d_starts, 
     w.conf = p->confidence; w.flags = p->flags;
     w.rng_tab = c->d_rng; w.rng_len = c->rng_len;
     w.sample_pos = c->sample_pos.as<int32_t>(); w.n_samples = c->n_samples.as<int32_t>();
-    w.hyp_H = split_score ? c->hypH.as<float>() : nullptr;
+    w.hyp_H = split_score ? c->hypH.as<float>() : nullptr; w.hyp_H_complete = 0;
     w.counts = c->counts.as<int32_t>(); w.best_iter = c->best_iter.as<int32_t>();
     w.best_count = c->best_count.as<int32_t>(); w.iters_run = c->iters_run.as<int32_t>();
     w.niters_cur = c->niters_cur.as<int32_t>();

@@ -139,6 +139,7 @@ struct RansacWork {
     int64_t* smp_state;         // [P, 2] sampler state between rounds: next draw position, failure run (-1 = finished)
     unsigned long long* scored_pts;   // device counter: sum over scored hypotheses of n (or NULL)
     float* hyp_H;               // [P, max_iters, 8] fp32 models for ransac_score_kernel, or NULL = score inside the solve kernel
+    int hyp_H_complete;         // every round's kernel left its models in hyp_H (set by launch_ransac for the finish kernel)
     int32_t* sel;               // [total] compacted inlier indices
     // outputs
     double* H;                  // [P, 9]

@@ -718,6 +718,11 @@ ransac_hyp_warp_kernel(RansacWork w, int round_base)
     if (lane == 0) {
         w.counts[(size_t)set * w.max_iters + iter] = good;
         if (w.scored_pts && valid) atomicAdd(w.scored_pts, (unsigned long long)n);
+        if (w.hyp_H && valid) {                                  // the finish kernel reads the winner's model from here
+            float4* dst = reinterpret_cast<float4*>(w.hyp_H + ((size_t)set * w.max_iters + iter) * 8);
+            dst[0] = make_float4((float)H[0], (float)H[1], (float)H[2], (float)H[3]);
+            dst[1] = make_float4((float)H[4], (float)H[5], (float)H[6], (float)H[7]);
+        }
     }
 }
 
@@ -1281,8 +1286,11 @@ ransac_finish_kernel(RansacWork w)
     const int best_iter = w.best_iter[set];
     if (best_iter < 0) { fail(); return; }
 
-    // winner's model again (deterministic) -> its mask, in original order
-    if (tid < 32) {                                          // warp 0, cooperatively (bit-identical to the hypothesis kernels)
+    // The winner's model.  Its mask needs the fp32 model only, and that is what the solve kernel left in hyp_H (8 floats, the
+    // (float) of the fp64 H it computed): no second eigen-solve.  The fp64 H itself is needed when nothing refines it
+    // (CVG_RANSAC_NO_REFINE) or when the DLT refit on the inliers is degenerate and LM starts from it: solved again then.
+    const bool have_model = w.hyp_H != nullptr && w.hyp_H_complete && !(w.flags & CVG_RANSAC_NO_REFINE);
+    auto solve_winner = [&]() {                              // warp 0, cooperatively (bit-identical to the hypothesis kernels)
         int idx[4];
         draw_subset(w.rng_tab, w.rng_len, w.sample_pos[(size_t)set * w.max_iters + best_iter], (uint32_t)n, idx);
         float ms1[8], ms2[8];
@@ -1297,9 +1305,12 @@ ransac_finish_kernel(RansacWork w)
         if (tid == 0) {
             for (int i = 0; i < 9; i++) sh.H[i] = H[i];
             for (int i = 0; i < 8; i++) sh.Hf[i] = (float)H[i];
-            sh.base_cnt = 0;
         }
-    }
+    };
+    if (have_model) {
+        if (tid < 8) sh.Hf[tid] = w.hyp_H[((size_t)set * w.max_iters + best_iter) * 8 + tid];
+    } else if (tid < 32) solve_winner();
+    if (tid == 0) sh.base_cnt = 0;
     __syncthreads();
     float Hf[8];
     #pragma unroll
@@ -1375,6 +1386,10 @@ ransac_finish_kernel(RansacWork w)
         }
         const bool dlt_ok = !(fabs(smx) < DBL_EPSILON || fabs(smy) < DBL_EPSILON ||
                               fabs(sMx) < DBL_EPSILON || fabs(sMy) < DBL_EPSILON);
+        if (!dlt_ok && have_model) {                         // block-uniform: LM starts from the RANSAC model in fp64
+            if (tid < 32) solve_winner();
+            __syncthreads();
+        }
         if (dlt_ok) {
             smx = n_inl / smx; smy = n_inl / smy; sMx = n_inl / sMx; sMy = n_inl / sMy;
             double* LtL = sh.scratch_a;
@@ -1490,6 +1505,10 @@ ransac_finish_kernel(RansacWork w)
         }
     } else {
         for (int i = tid; i < n; i += (int)blockDim.x) mask[i] = 0;
+        if (have_model) {                                    // never reached with a winner of >= 4 inliers; keep H defined
+            if (tid < 32) solve_winner();
+            __syncthreads();
+        }
     }
     if (tid < 9) Hout[tid] = sh.H[tid];
     if (tid == 0) w.found[set] = 1;
@@ -1576,6 +1595,7 @@ int launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events,
     }
     const int warps_per_block = 4;
     int round = 0;
+    bool hyp_complete = w.hyp_H != nullptr;
     for (int rb = 0; rb < w.max_iters; rb += round_len, round++) {
         const int len = w.max_iters - rb < round_len ? w.max_iters - rb : round_len;
         if (rb == 0 && w.chunk_outs && w.n_chunks > 1 && (int64_t)len >= CHUNKED_MIN_ITERS) {
@@ -1601,6 +1621,7 @@ int launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events,
         // One set alone (256 hypotheses): warp 0.30 ms, generic thread 1.1 ms.
         const int64_t hyps = (int64_t)len * w.n_sets;
         const int mode = hyp_mode ? hyp_mode : (hyps <= 4096 ? 1 : 4);
+        if (mode == 2 || mode == 3) hyp_complete = false;      // the A/B kernels do not leave their models in hyp_H
         if (mode == 1) {                                       // a handful of hypotheses: latency of one matrix counts
             dim3 grid((len + HYPW_WARPS - 1) / HYPW_WARPS, w.n_sets);
             ransac_hyp_warp_kernel<<<grid, HYPW_WARPS * 32, 0, st>>>(w, rb);
@@ -1635,7 +1656,9 @@ int launch_ransac(const RansacWork& w, cudaStream_t st, cudaEvent_t* hyp_events,
     // warp 0's serial eigen-solves plus 56 single-thread sums: with 64 threads per CTA four CTAs fit an SM (206 registers)
     // and the call's sets run in one wave instead of two.  Every loop of the kernel strides by blockDim.x.
     const int finish_threads = w.max_n <= 512 ? 64 : RS_THREADS;
-    ransac_finish_kernel<<<w.n_sets, finish_threads, 0, st>>>(w);
+    RansacWork wf = w;
+    wf.hyp_H_complete = hyp_complete ? 1 : 0;
+    ransac_finish_kernel<<<w.n_sets, finish_threads, 0, st>>>(wf);
     return launches;
 }
 
