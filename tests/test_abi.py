@@ -40,6 +40,19 @@ def test_no_cpu_fallback():
     assert e.value.code == 2 and "no CPU fallback" in str(e.value)
 
 
+def test_no_cpu_fallback_for_multi_device_contexts():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from computervision_objectdetection_featurematching_b200 import api
+    with pytest.raises(api.CvgError) as e:
+        api.Context([0, 1])                                     # cvg_create_multi
+    assert e.value.code == 2 and "no CPU fallback" in str(e.value)
+    lib = api._lib.load()
+    assert lib.cvg_num_devices(None) == 0 and lib.cvg_exchange_kind(None) == b"none"
+    assert lib.cvg_set_lanes(None, 2) == 1                     # CVG_ERR_INVALID, no crash on a NULL context
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "computervision_objectdetection_featurematching_b200")
     for dirpath, _, files in os.walk(pkg):
