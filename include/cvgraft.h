@@ -22,7 +22,7 @@
  * time, or several fused calls in flight through cvg_detect_scenes_submit / cvg_job_wait — the
  * context's lanes (internal engines with a worker thread each) overlap them on the GPU, so that one
  * call's latency-bound refit/LM kernel runs beside the next call's match and hypothesis kernels
- * (2.38 instead of 3.91 ms per batch of 64 pairs).  There is no CPU fallback: every entry point fails
+ * (2.3 instead of 3.7 ms per batch of 64 pairs).  There is no CPU fallback: every entry point fails
  * with CVG_ERR_CUDA when no sm_100 device is present.
  */
 #ifndef CVGRAFT_H

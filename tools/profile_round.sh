@@ -18,5 +18,7 @@ CVG_LANES=1 ncu --set full --clock-control none --import-source on -k regex:rans
     python tools/gpu_prof_match.py 64 > $out/${tag}_ncu_hyp.log 2>&1
 CVG_LANES=1 ncu --set full --clock-control none --import-source on -k regex:ransac_finish -s 1 -c 1 -o $out/${tag}_prof_finish \
     python tools/gpu_prof_match.py 64 > $out/${tag}_ncu_finish.log 2>&1
+CVG_LANES=1 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:match_tc --csv --log-file $out/${tag}_single_pair_match.csv \
+    python tools/gpu_prof_match.py 1 > $out/${tag}_ncu_single.log 2>&1
 cat $out/${tag}_bench_n1.json | cut -c1-400; cat $out/${tag}_bench_reference_n1.json | cut -c1-300
 tail -n 2 $out/${tag}_ncu_launches.log $out/${tag}_ncu_match.log $out/${tag}_ncu_hyp.log $out/${tag}_ncu_finish.log
