@@ -20,9 +20,9 @@ ONE context per GPU, driven by ONE host thread, in every number below.
              rate (its SURVEY-8d HBM figure is kept as algorithmic_gbs); solve_stage: the 4-point DLT kernel (fp64 Jacobi,
              latency-bound) — all from CUDA events around the kernels inside the serial timed steps
   cpu_baseline : cv2 4.13.0 (the reference's own arithmetic) on this host's cores, bounded sample
-  c4, c5_match (N >= 2 only, outside the timed regions above): BASELINE config 4 (4096 pairs of 4096 x 4096, pair p -> GPU
-             p mod N) and config 5's match (262 144 queries x 131 072 train rows per GPU, train-tile sharded, ONE NCCL
-             all-gather + top-2 merge), each with an inline parity check against the CPU oracle
+  c4, c5_match, c5_ransac (N >= 2 only, outside the timed regions above): BASELINE config 4 (4096 pairs of 4096 x 4096, pair
+             p -> GPU p mod N), config 5's match (262 144 queries x 131 072 train rows per GPU, train-tile sharded, ONE NCCL
+             all-gather + top-2 merge) and config 5's 2^20-hypothesis RANSAC, each with an inline check against the CPU oracle
 
 `--impl reference` times the reference's CPU implementation (cv2 BFMatcher.knnMatch + findHomography, all
 host threads; the C oracle port if cv2 is unavailable) on the same workload, metric and unit.
@@ -316,6 +316,42 @@ def run_c5_match(ctx, dev, rank, world, dist, all_max, barrier):
     return out
 
 
+# ---- BASELINE config 5 (verify): 2^20 RANSAC hypotheses on 8192 correspondences at 30 % inliers, every GPU a replica -------
+def run_c5_ransac(ctx, api, dev, rank, world, all_max, barrier):
+    """All 2^20 hypotheses are sampled (cv::RNG replay), solved and scored (CVG_RANSAC_NO_EARLY_STOP: a throughput mode outside
+    OpenCV's maxIters semantics), the first best one wins, no refit.  Checked on rank 0: the winner's mask is what the
+    CPU oracle's computeError gives for the returned H, bit for bit, and it holds at least as many inliers as the oracle's own
+    2000-iteration RANSAC stage finds on the same set."""
+    import torch
+    n_hyp = 1 << 20
+    src, dst, _ = synth.correspondences(np.random.default_rng(5002), 8192, 0.3)
+    flags = api.RANSAC_NO_EARLY_STOP | api.RANSAC_NO_REFINE
+    ctx.set_lanes(1)
+    H, mask = ctx.find_homography(src, dst, max_iters=n_hyp, flags=flags)               # warm-up: RNG table, scratch
+    barrier()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    H, mask = ctx.find_homography(src, dst, max_iters=n_hyp, flags=flags)
+    e1.record(stream); e1.synchronize()
+    ms = all_max(e0.elapsed_time(e1))
+    serial_sets = ctx.last_sampler_serial_sets
+    ctx.set_lanes(0)
+    out = {"hypotheses_per_gpu": n_hyp, "n": 8192, "ms_incl_h2d_d2h": ms, "hyps_per_s_per_gpu": n_hyp / (ms * 1e-3),
+           "hyps_per_s": world * n_hyp / (ms * 1e-3), "algorithmic_gbs_per_gpu": 16.0 * 8192 * n_hyp / (ms * 1e-3) / 1e9,
+           "hbm_bound_hyps_per_s_per_gpu": load_peaks()["hbm"] * 1e9 / (16.0 * 8192), "best_count": int(mask.sum()),
+           "sets_handed_to_the_serial_sampler": serial_sets,
+           "note": "every GPU runs the same set (replicas: a single RANSAC set does not shard without an exchange of counts); "
+                   "sampler + solve + score + select of 2^20 hypotheses, host copies of the 64 KB set and of H / mask included"}
+    if rank == 0:
+        from oracle import cvoracle as o
+        err = o.compute_error(src, dst, H)
+        ref = o.ransac_stage(src, dst, max_iters=2000)
+        out["parity"] = bool(np.array_equal((err <= np.float32(25.0)).astype(np.uint8), mask) and mask.sum() >= ref["mask"].sum())
+        out["oracle_best_count_2000_iters"] = int(ref["mask"].sum())
+    return out
+
+
 # ---- BASELINE config 4: 4096 pairs of 4096 x 4096, pair p -> GPU p mod N, no data-path collective ------------------------
 def run_c4(ctx, api, dev, rank, world, all_max, barrier):
     import torch
@@ -549,9 +585,10 @@ def run_cvgraft(args):
         single_pair_us = 1e3 * min(ts[1:])
 
     # ---- N >= 2: BASELINE configs 4 and 5 on the same ranks, outside the c3 timed regions --------------------------------
-    c4 = c5 = None
+    c4 = c5 = c5r = None
     if world > 1 and args.desc == "sift" and not args.no_multi:
         c5 = run_c5_match(ctx, dev, rank, world, dist, all_max, barrier)
+        c5r = run_c5_ransac(ctx, api, dev, rank, world, all_max, barrier)
         c4 = run_c4(ctx, api, dev, rank, world, all_max, barrier)
 
     # ---- extra key: the reference's own dataset (BASELINE configs 1-2: 30 test images x 5 scales x 89 model views), when
@@ -695,6 +732,8 @@ def run_cvgraft(args):
             line["c4"] = c4
         if c5 is not None:
             line["c5_match"] = c5
+        if c5r is not None:
+            line["c5_ransac"] = c5r
         if world == 1 and not args.no_cpu:
             os.sched_setaffinity(0, all_cpus)           # the CPU baseline gets every core of the box
             threads = os.cpu_count() or 1
