@@ -766,7 +766,7 @@ def main():
     ap.add_argument("--batches", type=int, default=4, help="distinct scene batches rotated over the steps")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--depth", type=int, default=3,
+    ap.add_argument("--depth", type=int, default=6,
                     help="calls the one host thread keeps in flight on the one context (cvg_detect_scenes_submit / cvg_job_wait)")
     ap.add_argument("--no-multi", action="store_true", help="N >= 2: skip the c4 / c5_match keys")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra keys (e2e_u8, real_dataset): launch-list runs")

@@ -78,7 +78,7 @@ struct BufPool {
     void release(DevBuf& b)
     {
         if (!b.p) return;
-        if (free_list.size() >= 64) {               // bounded: the buffer that has waited longest goes (sizes of a
+        if (free_list.size() >= 256) {              // bounded: the buffer that has waited longest goes (sizes of a
             free_list.front().release();            // streaming caller drift; keeping the smallest ones thrashed)
             free_list.erase(free_list.begin());
         }
@@ -171,6 +171,8 @@ struct cvg_ctx {
     // scene batch (cvg_scenes_upload_async) and would hold the compute stream behind it.
     uint8_t* stage_h = nullptr; uint8_t* stage_d = nullptr; size_t stage_cap = 0, stage_used = 0; bool stage_fallback = false;
     int wave_div = 1;                  // how many engines share this GPU right now (sizes the RANSAC rounds)
+    cudaEvent_t sync_ev = nullptr;     // blocking-sync event a lane's worker sleeps on (sync_and_check)
+    bool blocking_sync = false;        // this engine's current work is a pipelined job: sleep, do not spin, while the GPU works
     // lanes: engines of the same device, each driven by its own worker thread, that serve the sub-batches of one
     // synchronous fused call and the jobs of cvg_detect_scenes_submit (multi.cu)
     cvg_ctx* parent = nullptr;         // set on a lane / device engine

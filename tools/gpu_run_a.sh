@@ -1,8 +1,8 @@
-set -x
 mkdir -p gpurun_out
-timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/r02e_bench.json 2> gpurun_out/r02e_bench.err; echo "bench rc=$?"
-python - <<'PY'
-import json
-j=json.load(open('gpurun_out/r02e_bench.json'))
-print('value',round(j['value']), j['ms_per_step'], 'sync', round(j['value_single_context']['value']), 'serial', round(j['value_serial']['value']), 'e2e', round(j['e2e']['value']), 'u8', j['e2e_u8'] and round(j['e2e_u8']['value']), 'real', j['real_dataset'] and (j['real_dataset'].get('seconds'), j['real_dataset'].get('seconds_sync_calls')), 'launches', j['gpu_launches'], 'match', j['roofline']['kernel_ms_per_launch'])
-PY
+for cfg in "6 6" "8 8" "6 4"; do set -- $cfg
+CVG_LANES=$1 timeout 300 python bench.py --steps 24 --warmup 4 --no-cpu --depth $2 2>/dev/null | python -c "
+import json,sys
+j=json.loads(sys.stdin.read())
+print('lanes $1 depth $2: value',round(j['value']), 'sync', round(j['value_single_context']['value']), 'e2e', round(j['e2e']['value']), 'u8', round(j['e2e_u8']['value']), 'real', j['real_dataset']['seconds'], j['real_dataset']['seconds_sync_calls'])"
+done
+./host/cvg_replay data_cache/features_full.bin gpurun_out/rp1 | tail -2; ./host/cvg_replay data_cache/features_full.bin gpurun_out/rp2 --depth 3 | tail -1; rm -rf gpurun_out/rp1 gpurun_out/rp2
