@@ -336,7 +336,7 @@ def run_c5_ransac(ctx, api, dev, rank, world, all_max, barrier):
     e1.record(stream); e1.synchronize()
     ms = all_max(e0.elapsed_time(e1))
     serial_sets = ctx.last_sampler_serial_sets
-    ctx.set_lanes(0)
+    ctx.set_lanes(3)
     out = {"hypotheses_per_gpu": n_hyp, "n": 8192, "ms_incl_h2d_d2h": ms, "hyps_per_s_per_gpu": n_hyp / (ms * 1e-3),
            "hyps_per_s": world * n_hyp / (ms * 1e-3), "algorithmic_gbs_per_gpu": 16.0 * 8192 * n_hyp / (ms * 1e-3) / 1e9,
            "hbm_bound_hyps_per_s_per_gpu": load_peaks()["hbm"] * 1e9 / (16.0 * 8192), "best_count": int(mask.sum()),
@@ -437,6 +437,8 @@ def run_cvgraft(args):
     clocks = ClockSampler(local); clocks.start()
     q, qk, batches = make_workload(3000 + rank, B, R, args.desc)
     ctx = api.Context(local)                             # ONE context, driven by this one host thread
+    LANES = min(8, max(3, DEPTH))                        # one lane per call in flight (3 by default; more pay off on one GPU
+                                                         # with cores to spare: 6 -> +7 %, 8 -> +12 %, but cost 20 % at 8 GPUs x 4 vCPUs)
     models = ctx.upload_models(q, qk, [0, NQ], [0])
     params = api.detect_params()
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
@@ -487,7 +489,7 @@ def run_cvgraft(args):
     ctx.set_timing(False)
 
     # ---- phase 2: synchronous calls, each split over the context's lanes (what a caller of the blocking API gets) -------
-    ctx.set_lanes(0)
+    ctx.set_lanes(LANES)
 
     def loop_sync(steps):
         for k in range(steps):
@@ -580,7 +582,7 @@ def run_cvgraft(args):
         for _ in range(6):
             ctx.detect_scenes(models, one, params=params)
             ts.append(ctx.last_timing()["match_ms"])
-        ctx.set_timing(False); ctx.set_lanes(0)
+        ctx.set_timing(False); ctx.set_lanes(LANES)
         one.free()
         single_pair_us = 1e3 * min(ts[1:])
 
@@ -604,6 +606,7 @@ def run_cvgraft(args):
             sd = torch.from_numpy(Z["scene_desc"].astype(np.float32)).pin_memory(); sk = torch.from_numpy(Z["scene_kpt"].astype(np.float32)).pin_memory()
             sdn, skn = sd.numpy(), sk.numpy()
             rctx = api.Context(local)                      # own context: its buffer pools hold this workload's sizes
+            rctx.set_lanes(LANES)
             rstream = torch.cuda.ExternalStream(rctx.stream, device=dev)
             rmodels = rctx.upload_models(md, Z["model_kpt"], Z["view_offsets"], Z["view_model"])
             sc5 = Z["scales"].astype(np.float32)
@@ -675,7 +678,7 @@ def run_cvgraft(args):
                                           "fp32, non-integer (candidate + fp32 re-rank match path)",
                            "match_path": ctx.last_match_path,
                            "scene_batches_rotated": R, "parallelism": f"pair-sharded x{world}, no data-path collective",
-                           "contexts_per_gpu": 1, "host_threads_per_gpu": 1, "calls_in_flight": DEPTH, "host_numa_node": numa,
+                           "contexts_per_gpu": 1, "host_threads_per_gpu": 1, "calls_in_flight": DEPTH, "lanes": LANES, "host_numa_node": numa,
                            "l2": f"{R} rotating batches, {R * B * NT * DIM * 2 / 2**20:.0f} MiB of bf16 operands > 126 MB L2"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps,
@@ -766,7 +769,7 @@ def main():
     ap.add_argument("--batches", type=int, default=4, help="distinct scene batches rotated over the steps")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--depth", type=int, default=6,
+    ap.add_argument("--depth", type=int, default=3,
                     help="calls the one host thread keeps in flight on the one context (cvg_detect_scenes_submit / cvg_job_wait)")
     ap.add_argument("--no-multi", action="store_true", help="N >= 2: skip the c4 / c5_match keys")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra keys (e2e_u8, real_dataset): launch-list runs")

@@ -86,7 +86,7 @@ const cvg_models* cvg_models_on(const cvg_models* m, const cvg_ctx* eng)
 // ---- lanes ------------------------------------------------------------------------------------------------
 static int default_lanes()
 {
-    static const int n = [] { const char* e = getenv("CVG_LANES"); const int v = e ? atoi(e) : 6; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
+    static const int n = [] { const char* e = getenv("CVG_LANES"); const int v = e ? atoi(e) : 3; return v < 1 ? 1 : (v > 8 ? 8 : v); }();
     return n;
 }
 static int lanes_of(const cvg_ctx* c) { return c->lanes_cfg > 0 ? c->lanes_cfg : default_lanes(); }
@@ -164,7 +164,7 @@ static int dev_submit(cvg_ctx* c, const cvg_models* m, cvg_scenes* sc, const flo
         const int share = split ? K : need;
         lane->worker->post([=] {
             eng->wave_div = share;
-            eng->blocking_sync = !split;
+            eng->blocking_sync = !split && need > 4;     // many lanes: their workers sleep while the GPU works (api.cu, sync_and_check)
             const int r = eng_detect_range(eng, m, sc, t->s0, t->s1, j->have_scales ? j->scales.data() : nullptr, &j->params,
                                            j->per_pair + (size_t)t->s0 * V, want_inl ? &t->pool : nullptr, want_inl ? &t->cnt : nullptr);
             t->match_path = eng->last_match_path;

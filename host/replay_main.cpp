@@ -27,7 +27,7 @@ int main(int argc, char** argv)
         else if (!strcmp(argv[i], "--sync")) sync = true;
     }
     if (n_gpus < 1) n_gpus = 1;
-    if (depth <= 0) depth = (n_gpus == 1 ? 6 : 3) * n_gpus;   // images in flight: enough to keep every GPU's lanes busy
+    if (depth <= 0) depth = 3 * n_gpus;                  // images in flight: three per GPU keep its lanes busy
     FeatureCache fc;
     std::string err;
     if (!fc.load(argv[1], &err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }

@@ -129,8 +129,10 @@ void cvg_destroy(cvg_ctx* ctx);
  * cvg_detect_scenes* call splits its batch into up to min(n_lanes, 3) sub-batches that run concurrently, so that one
  * sub-batch's latency-bound refit/LM kernel runs under another's match and hypothesis kernels; calls below ~2^25
  * distance evaluations per lane are not split.  cvg_detect_scenes_submit hands whole batches to the lanes in turn.
- * n_lanes = 1: everything on the context's own stream, on the caller's thread; 0: default (6, env CVG_LANES; a
- * synchronous call uses at most 3 of them, env CVG_SPLIT_LANES). */
+ * n_lanes = 1: everything on the context's own stream, on the caller's thread; 0: default (3, env CVG_LANES); up to
+ * 8.  A synchronous call uses at most 3 of them (env CVG_SPLIT_LANES).  More lanes (and as many calls in flight) pay
+ * off when the host has cores to spare: 6 lanes +7 %, 8 lanes +12 % on one GPU with 16 vCPUs, but -20 % on 8 GPUs
+ * sharing 32 vCPUs (profiles/README.md). */
 int  cvg_set_lanes(cvg_ctx* ctx, int n_lanes);
 const char* cvg_last_error(void);   /* thread-local message of the last failing call                 */
 /* Page-locked host memory for callers without CUDA headers: buffers handed to the *_async uploads are copied
