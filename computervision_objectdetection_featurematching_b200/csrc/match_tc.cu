@@ -432,10 +432,12 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
     constexpr uint32_t G_BYTES = PAIR ? B_AUG_HALF_BYTES : B_AUG_BYTES;
     const uint32_t g_full = bar0 + 64 + 16 * NB, g_empty = g_full + 8 * NG;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 64 + 16 * NB + 16 * NG + 16);
+    int* chunk_ctr = reinterpret_cast<int*>(smem + OFF_BAR + 480);      // [4]: next 64-column chunk of the unit, per TMEM lane quarter
     static_assert(64 + 16 * B_STAGES_PAIR + 16 * 4 + 16 + 8 <= 512, "barrier area");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; i++) chunk_ctr[i] = 0;
         for (int i = 0; i < 2; i++) {
             mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1);
             mbar_init(t_full + 8 * i, 1); mbar_init(t_empty + 8 * i, (PAIR ? 2 : 1) * TC_EPI_WARPS);   // pair: both CTAs' epilogues arrive on the leader's
@@ -631,7 +633,32 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                 // Measured and rejected: two groups of 8 warps taking alternate tiles (128 columns per warp): 1.21 ms instead
                 // of 1.10 ms per 64 pairs — the epilogue is bound by its instruction stream (~250 per warp and tile, four
                 // warps per scheduler), not by the latency of one tile's chain.
-                for (int t = 0; t < un.n_tiles; t++, tc++) {
+#ifndef TC_DYNAMIC_PARTS
+#define TC_DYNAMIC_PARTS 0                            // measured: 1.153 ms with dynamic parts, 1.114 ms with fixed ones (same run)
+#endif
+                // Dynamic column parts (experiment, off): the four warps of a TMEM lane quarter (the same 32 query rows) do not own a fixed 64-column
+                // part of every tile; each takes the next unclaimed 64-column chunk of the unit from a shared counter.  The
+                // accumulator of a tile goes back to the MMA issuer when its 16 chunks have been loaded, whoever loaded them: a
+                // warp that is held up by a burst of candidates no longer holds up the tile, a faster warp of its quarter takes
+                // the chunk it would have been late for.  Chunks are claimed in ascending order, so every warp still scans its
+                // columns in ascending order (ties keep the earlier column) and the unit flush merges the four warps' records by
+                // (value, index) as before.  A chunk of tile T can only be claimed after some warp finished a chunk of T - 1, i.e.
+                // after t_full of T - 2 completed: the parity wait below cannot mistake an older phase for the one it needs.
+                const uint32_t tc_unit0 = tc;
+                const int n_chunks_unit = un.n_tiles * 4;
+                for (int t_static = 0;; t_static++) {
+                    int t, dpart;
+                    if (TC_DYNAMIC_PARTS) {
+                        int c = 0;
+                        if (lane == 0) c = atomicAdd(&chunk_ctr[quarter], 1);
+                        c = __shfl_sync(0xffffffffu, c, 0);
+                        if (c >= n_chunks_unit) break;
+                        t = c >> 2; dpart = c & 3;
+                    } else {
+                        if (t_static >= un.n_tiles) break;
+                        t = t_static; dpart = part;
+                    }
+                    tc = tc_unit0 + (uint32_t)t;
                     const uint32_t acc = tc & 1;
                     if (prof) t0 = clock64();
                     // The filter update (what the other three column parts of these rows have found so far) runs BEFORE the wait for
@@ -664,8 +691,8 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                     tc_fence_after();
                     if (prof) { t1 = clock64(); c_wait += t1 - t0; t0 = t1; c_tiles++; }
                     if (TC_SHARE_AFTER_WAIT) update_filter();
-                    const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TILE_N + part * 64;
-                    const int col_base = un.t_local0 + t * TILE_N + part * 64;
+                    const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TILE_N + dpart * 64;
+                    const int col_base = un.t_local0 + t * TILE_N + dpart * 64;
                     if (!(exp_mode & 1)) {
                         uint32_t ra[32], rb[32];
                         tc_ld32(tbase, ra);                           // two loads in flight before the wait
@@ -704,6 +731,7 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                         if (lane == 0) { if constexpr (PAIR) mbar_arrive_leader(t_empty + 8 * acc); else mbar_arrive(t_empty + 8 * acc); }
                     }
                 }
+                tc = tc_unit0 + (uint32_t)un.n_tiles;
                 // ---- unit flush: merge the four column parts, convert to distances, write the partial ----
                 if (prof) t0 = clock64();
                 share_store(my_share, -INFINITY, -INFINITY);     // reset before the barriers below
@@ -715,6 +743,7 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                 }
                 asm volatile("bar.sync 1, %0;" :: "n"(32 * TC_EPI_WARPS) : "memory");
                 if (part == 0) {
+                    if (lane == 0) chunk_ctr[quarter] = 0;        // every warp of the quarter has left the chunk loop; next unit starts at 0
                     // larger acc' first, ties -> lower train index
                     #pragma unroll
                     for (int pp = 0; pp < 3; pp++) {
