@@ -662,8 +662,8 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                     const uint32_t acc = tc & 1;
                     if (prof) t0 = clock64();
                     // The filter update (what the other three column parts of these rows have found so far) runs BEFORE the wait for
-                    // the next accumulator: the tile loop is paced by its slowest warp (the accumulator is released when all 16
-                    // have loaded it), so whatever a warp can do while it would wait anyway is off the critical path.
+                    // the next accumulator: a warp that has to wait anyway does it for free (same-run A/B: no slower than after the
+                    // wait, and the accumulator goes back to the MMA issuer ~300 cycles earlier once it has arrived).
                     auto update_filter = [&]() {
                         if (t > 0 && !(exp_mode & 8)) {               // exp bit 3: no filter sharing between the column parts
                             float o1[3], o2[3];
