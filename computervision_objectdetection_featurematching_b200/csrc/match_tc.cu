@@ -62,6 +62,13 @@ constexpr uint32_t OFF_BAR = OFF_SHARE + SHARE_BYTES;
 constexpr uint32_t TC_SMEM_SLACK = 512;                           // the dynamic window is 1024-aligned in practice; checked in the kernel
 constexpr uint32_t TC_SMEM_BYTES = OFF_BAR + 512 + TC_SMEM_SLACK;
 static_assert(TC_SMEM_BYTES <= 232448, "shared memory budget of one CTA (227 KB)");
+#ifndef TC_ISSUER_UNROLL
+#define TC_ISSUER_UNROLL 2                                        // stage loop of the MMA issuer: 1 = rolled
+#endif
+constexpr int kIssuerUnroll = TC_ISSUER_UNROLL;
+#ifndef TC_ISSUER_WARP
+#define TC_ISSUER_WARP 1
+#endif
 #ifndef TOP2_GROUPS_PER_TEST
 #define TOP2_GROUPS_PER_TEST 2
 #endif
@@ -139,6 +146,14 @@ __device__ __forceinline__ uint32_t cluster_ctarank()
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
+}
+__device__ __forceinline__ bool elect_one()                       // one lane of the (converged) warp
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "elect.sync _|p, 0xffffffff;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok));
+    return ok != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -464,7 +479,17 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
 
     if (warp == 0) {
         // ===================== TMA producer =====================
+#if TC_ISSUER_WARP
+        const bool el = elect_one();                 // all lanes walk the loop and wait, one issues (see the MMA issuer)
+        {
+#else
+        constexpr bool el = true;
         if (lane == 0) {
+#endif
+            auto expect_tx = [&](uint32_t bar, uint32_t bytes) { if (el) mbar_expect_tx(bar, bytes); };
+            auto load = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) { if (el) tma_load_2d(dst, map, c0, c1, bar); };
+            auto load_pair = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) { if (el) tma_load_2d_pair(dst, map, c0, c1, bar); };
+            auto arrive = [&](uint32_t bar) { if (el) mbar_arrive(bar); };
             uint32_t ua = 0, bs = 0, tcnt = 0;
             for (int e = worker; e < n_entries; e += n_workers, ua++) {
                 const MatchUnit un = units[unit_of(e)];
@@ -474,23 +499,23 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                 mbar_wait(a_empty + 8 * ab, (SPLIT ? (ua & 1) : ((ua >> 1) & 1)) ^ 1, dbg, 1);
                 const uint32_t sa = smem_base + OFF_A + ab * A_BYTES;
                 if constexpr (SPLIT) {
-                    mbar_expect_tx(a_full, 4 * A_ATOM_BYTES + A_AUG_BYTES);
-                    tma_load_2d(sa, &maps.q, 0, un.q_row0, a_full);
-                    tma_load_2d(sa + A_ATOM_BYTES, &maps.q, 64, un.q_row0, a_full);
-                    tma_load_2d(sa + 2 * A_ATOM_BYTES, &maps.qlo, 0, un.q_row0, a_full);
-                    tma_load_2d(sa + 3 * A_ATOM_BYTES, &maps.qlo, 64, un.q_row0, a_full);
-                    tma_load_2d(sa + 4 * A_ATOM_BYTES, &maps.qaug, 0, un.q_row0, a_full);
+                    expect_tx(a_full, 4 * A_ATOM_BYTES + A_AUG_BYTES);
+                    load(sa, &maps.q, 0, un.q_row0, a_full);
+                    load(sa + A_ATOM_BYTES, &maps.q, 64, un.q_row0, a_full);
+                    load(sa + 2 * A_ATOM_BYTES, &maps.qlo, 0, un.q_row0, a_full);
+                    load(sa + 3 * A_ATOM_BYTES, &maps.qlo, 64, un.q_row0, a_full);
+                    load(sa + 4 * A_ATOM_BYTES, &maps.qaug, 0, un.q_row0, a_full);
                 } else if constexpr (PAIR) {
                     // both CTAs load their own query tile; the bytes of both are counted on the leader's barrier
-                    if (leader) mbar_expect_tx(a_full + 8 * ab, 2 * A_BYTES);
-                    tma_load_2d_pair(sa, &maps.q, 0, un.q_row0, a_full + 8 * ab);
-                    tma_load_2d_pair(sa + A_ATOM_BYTES, &maps.q, 64, un.q_row0, a_full + 8 * ab);
-                    tma_load_2d_pair(sa + 2 * A_ATOM_BYTES, &maps.qaug, 0, un.q_row0, a_full + 8 * ab);
+                    if (leader) expect_tx(a_full + 8 * ab, 2 * A_BYTES);
+                    load_pair(sa, &maps.q, 0, un.q_row0, a_full + 8 * ab);
+                    load_pair(sa + A_ATOM_BYTES, &maps.q, 64, un.q_row0, a_full + 8 * ab);
+                    load_pair(sa + 2 * A_ATOM_BYTES, &maps.qaug, 0, un.q_row0, a_full + 8 * ab);
                 } else {
-                    mbar_expect_tx(a_full + 8 * ab, A_BYTES);
-                    tma_load_2d(sa, &maps.q, 0, un.q_row0, a_full + 8 * ab);
-                    tma_load_2d(sa + A_ATOM_BYTES, &maps.q, 64, un.q_row0, a_full + 8 * ab);
-                    tma_load_2d(sa + 2 * A_ATOM_BYTES, &maps.qaug, 0, un.q_row0, a_full + 8 * ab);
+                    expect_tx(a_full + 8 * ab, A_BYTES);
+                    load(sa, &maps.q, 0, un.q_row0, a_full + 8 * ab);
+                    load(sa + A_ATOM_BYTES, &maps.q, 64, un.q_row0, a_full + 8 * ab);
+                    load(sa + 2 * A_ATOM_BYTES, &maps.qaug, 0, un.q_row0, a_full + 8 * ab);
                 }
                 for (int t = 0; t < un.n_tiles; t++, tcnt++) {
                     const int row = un.t_row0 + t * TILE_N;
@@ -502,26 +527,26 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                         mbar_wait(b_empty + 8 * s, ((bs / NB) & 1) ^ 1, dbg, 2);
                         if constexpr (PAIR) {
                             // this CTA's half of the stage: train rows [row + 128 r, +128) — accumulator columns 128 r ..
-                            if ((exp_mode & 2) && bs >= NB) { if (leader) mbar_arrive(b_full + 8 * s); continue; }
-                            if (leader) mbar_expect_tx(b_full + 8 * s, 2 * B_HALF_BYTES);
-                            tma_load_2d_pair(smem_base + OFF_B + s * B_HALF_BYTES, &maps.th, 64 * (h & 1), row + (int)cta_rank * (TILE_N / 2),
+                            if ((exp_mode & 2) && bs >= NB) { if (leader) arrive(b_full + 8 * s); continue; }
+                            if (leader) expect_tx(b_full + 8 * s, 2 * B_HALF_BYTES);
+                            load_pair(smem_base + OFF_B + s * B_HALF_BYTES, &maps.th, 64 * (h & 1), row + (int)cta_rank * (TILE_N / 2),
                                              b_full + 8 * s);
                             continue;
                         }
-                        if (!SPLIT && (exp_mode & 2) && bs >= B_STAGES) { mbar_arrive(b_full + 8 * s); continue; }
-                        mbar_expect_tx(b_full + 8 * s, B_ATOM_BYTES);
-                        tma_load_2d(smem_base + OFF_B + s * B_ATOM_BYTES, (SPLIT && h >= 2) ? &maps.tlo : &maps.t, 64 * (h & 1), row,
+                        if (!SPLIT && (exp_mode & 2) && bs >= B_STAGES) { arrive(b_full + 8 * s); continue; }
+                        expect_tx(b_full + 8 * s, B_ATOM_BYTES);
+                        load(smem_base + OFF_B + s * B_ATOM_BYTES, (SPLIT && h >= 2) ? &maps.tlo : &maps.t, 64 * (h & 1), row,
                                     b_full + 8 * s);
                     }
                     const uint32_t g = tcnt % NG;
                     mbar_wait(g_empty + 8 * g, ((tcnt / NG) & 1) ^ 1, dbg, 7);
                     if constexpr (PAIR) {
-                        if (leader) mbar_expect_tx(g_full + 8 * g, 2 * B_AUG_HALF_BYTES);
-                        tma_load_2d_pair(smem_base + OFF_BAUG + g * G_BYTES, &maps.taugh, 0, row + (int)cta_rank * (TILE_N / 2), g_full + 8 * g);
+                        if (leader) expect_tx(g_full + 8 * g, 2 * B_AUG_HALF_BYTES);
+                        load_pair(smem_base + OFF_BAUG + g * G_BYTES, &maps.taugh, 0, row + (int)cta_rank * (TILE_N / 2), g_full + 8 * g);
                         continue;
                     }
-                    mbar_expect_tx(g_full + 8 * g, B_AUG_BYTES);
-                    tma_load_2d(smem_base + OFF_BAUG + g * B_AUG_BYTES, &maps.taug, 0, row, g_full + 8 * g);
+                    expect_tx(g_full + 8 * g, B_AUG_BYTES);
+                    load(smem_base + OFF_BAUG + g * B_AUG_BYTES, &maps.taug, 0, row, g_full + 8 * g);
                 }
             }
             if constexpr (PAIR) {
@@ -534,7 +559,15 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+#if TC_ISSUER_WARP
+        // the whole warp walks the loop and waits; one elected lane issues (the compiler then keeps the descriptor
+        // arithmetic on the uniform datapath and needs no per-instruction election loop around tcgen05.mma / commit)
+        const bool el = elect_one();
+        if (leader) {
+#else
+        constexpr bool el = true;
         if (lane == 0 && leader) {                   // pair mode: the leader CTA issues for both
+#endif
             uint32_t ua = 0, bs = 0, tc = 0;
 #ifdef TC_PROF
             long long w_a = 0, w_t = 0, w_b = 0, w_g = 0, q0 = 0; const long long m_start = clock64();
@@ -545,36 +578,43 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
 #define MPROF_END(acc)
 #endif
             auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t accumulate) {
+                if (!el) return;
                 if constexpr (PAIR) tc_mma_bf16_pair(d, da, db, TC_IDESC_PAIR, accumulate);
                 else tc_mma_bf16(d, da, db, TC_IDESC, accumulate);
             };
-            auto commit = [&](uint32_t bar) { if constexpr (PAIR) tc_commit_pair(bar); else tc_commit(bar); };
+            auto commit = [&](uint32_t bar) { if (!el) return; if constexpr (PAIR) tc_commit_pair(bar); else tc_commit(bar); };
             for (int e = worker; e < n_entries; e += n_workers, ua++) {
                 const int n_tiles = units[unit_of(e)].n_tiles;
                 const uint32_t ab = SPLIT ? 0u : (ua & 1);
                 MPROF_BEGIN mbar_wait(a_full + 8 * ab, SPLIT ? (ua & 1) : ((ua >> 1) & 1), dbg, 3); MPROF_END(w_a)
                 const uint32_t sa = smem_base + OFF_A + ab * A_BYTES;
+                const uint64_t da_aug = desc_sw32(sa + (SPLIT ? 4 : 2) * A_ATOM_BYTES);
                 for (int t = 0; t < n_tiles; t++, tc++) {
                     const uint32_t acc = tc & 1;
                     MPROF_BEGIN mbar_wait(t_empty + 8 * acc, ((tc >> 1) & 1) ^ 1, dbg, 5); MPROF_END(w_t)
                     const uint32_t d_tmem = tmem_base + acc * TILE_N;
-                    #pragma unroll 1
+                    #pragma unroll kIssuerUnroll
                     for (int h = 0; h < N_STAGES_PER_TILE; h++, bs++) {
                         const uint32_t s = bs % NB;
                         MPROF_BEGIN mbar_wait(b_full + 8 * s, (bs / NB) & 1, dbg, 4); MPROF_END(w_b)
                         tc_fence_after();
                         const uint32_t sb = smem_base + OFF_B + s * STAGE_BYTES;
+                        // descriptors of the stage once, then + 2 per K step (the address field counts 16-byte units; stage and A
+                        // buffers are 1024-aligned, so the 14-bit field cannot carry): fewer instructions on the one thread that
+                        // feeds the tensor pipe and shares its scheduler with four busy epilogue warps
+                        const uint64_t db0 = desc_sw128(sb);
+                        const uint64_t da0 = desc_sw128(sa + (uint32_t)h * A_ATOM_BYTES);
                         #pragma unroll
                         for (int k = 0; k < 4; k++) {
                             const uint32_t koff = (uint32_t)k * 32u;             // 16 bf16 = 32 B inside the swizzle atom
-                            const uint64_t db = desc_sw128(sb + koff);
+                            const uint64_t db = db0 + 2u * (uint32_t)k;
                             if constexpr (SPLIT) {
                                 // 2q.t ~ hi.hi + lo.hi (stages 0, 1: train hi) + hi.lo (stages 2, 3: train lo)
                                 const uint32_t kh = (uint32_t)(h & 1);
-                                tc_mma_bf16(d_tmem, desc_sw128(sa + kh * A_ATOM_BYTES + koff), db, TC_IDESC, (h | k) ? 1u : 0u);
-                                if (h < 2) tc_mma_bf16(d_tmem, desc_sw128(sa + (2 + kh) * A_ATOM_BYTES + koff), db, TC_IDESC, 1u);
+                                mma(d_tmem, desc_sw128(sa + kh * A_ATOM_BYTES + koff), db, (h | k) ? 1u : 0u);
+                                if (h < 2) mma(d_tmem, desc_sw128(sa + (2 + kh) * A_ATOM_BYTES + koff), db, 1u);
                             } else {
-                                mma(d_tmem, desc_sw128(sa + h * A_ATOM_BYTES + koff), db, (h | k) ? 1u : 0u);
+                                mma(d_tmem, da0 + 2u * (uint32_t)k, db, (h | k) ? 1u : 0u);
                             }
                         }
                         commit(b_empty + 8 * s);         // ring stage reusable once these MMAs retire
@@ -583,8 +623,7 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                         const uint32_t g = tc % NG;
                         MPROF_BEGIN mbar_wait(g_full + 8 * g, (tc / NG) & 1, dbg, 8); MPROF_END(w_g)
                         tc_fence_after();
-                        mma(d_tmem, desc_sw32(sa + (SPLIT ? 4 : 2) * A_ATOM_BYTES),
-                            desc_sw32(smem_base + OFF_BAUG + g * G_BYTES), 1u);
+                        mma(d_tmem, da_aug, desc_sw32(smem_base + OFF_BAUG + g * G_BYTES), 1u);
                         commit(g_empty + 8 * g);
                     }
                     commit(t_full + 8 * acc);            // accumulator ready for the epilogue (of both CTAs)
@@ -592,7 +631,7 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                 commit(a_empty + 8 * ab);
             }
 #ifdef TC_PROF
-            if ((exp_mode & 32) && dbg && blockIdx.x == 0) {
+            if (el && (exp_mode & 32) && dbg && blockIdx.x == 0) {
                 int* o = dbg + 28;
                 o[0] = (int)tc; o[1] = (int)(w_a / 64); o[2] = (int)(w_t / 64); o[3] = (int)(w_b / 64); o[4] = (int)(w_g / 64); o[5] = (int)((clock64() - m_start) / 64);
             }
