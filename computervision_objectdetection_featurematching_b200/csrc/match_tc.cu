@@ -70,7 +70,7 @@ constexpr int kIssuerUnroll = TC_ISSUER_UNROLL;
 #define TC_ISSUER_WARP 1
 #endif
 #ifndef TOP2_GROUPS_PER_TEST
-#define TOP2_GROUPS_PER_TEST 2
+#define TOP2_GROUPS_PER_TEST 4                                    // groups of 4 columns per filter test; same run: 1 -> 1.061 ms, 2 -> 0.957, 4 -> 0.949
 #endif
 constexpr float ABSENT_BELOW = -5.0e8f;                           // padded train rows carry -2^30
 
@@ -308,7 +308,7 @@ __device__ __forceinline__ void top2_scan32(const uint32_t* r, int c0, float& b1
     for (int k = 0; k < 8; k++)
         g[k] = fmaxf(fmaxf(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1])),
                      fmaxf(__uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3])));
-    // one branch per 8 columns on the fast path (branch resolution was 17 % of the epilogue's stalls with one per 4)
+    // one branch per 16 columns on the fast path (branch resolution was 17 % of the epilogue's stalls with one per 4)
     #pragma unroll
     for (int k = 0; k < 8; k += TOP2_GROUPS_PER_TEST) {
         float gm = g[k];
