@@ -405,12 +405,15 @@ struct TcMaps { CUtensorMap q, qaug, t, taug, qlo, tlo, th, taugh; };   // th / 
 //         accumulator values, slot (part_slot * 4 + column part).
 // PAIR: launched as clusters of two CTAs (cta_group::2); unit 2p + r belongs to CTA r of the cluster that owns pair p, and
 //       both units of a pair name the same train tiles.
-template <int KP, bool PAIR>
+// EXPB: the instance with the CVG_TC_EXP experiment switches; the product instance (EXPB = false) carries none of their
+//       per-tile tests (~15 instructions per warp and tile in a loop that is bound by its instruction count).
+template <int KP, bool PAIR, bool EXPB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ qnorm,
                 const MatchUnit* __restrict__ units, int n_units, void* __restrict__ parts_out,
-                const int* __restrict__ gate_flag, int gate_want, int* dbg, int exp_mode)
+                const int* __restrict__ gate_flag, int gate_want, int* dbg, int exp_mode_arg)
 {
+    const int exp_mode = EXPB ? exp_mode_arg : 0;
     // exp_mode (experiments only, set through CVG_TC_EXP): bit 0 = epilogue releases the accumulator without
     // scanning it, bit 1 = the producer re-arms ring stages without issuing the B loads
     if (gate_flag && *gate_flag != gate_want) return;
@@ -651,6 +654,11 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
         // (float_pred) because the foreign column may have the higher train index.
         const uint32_t share = smem_base + OFF_SHARE;
         const uint32_t my_share = share + (uint32_t)(part * TILE_M + row_in_tile) * 8u;
+        // the accumulator barriers' addresses, held in a register: left to itself the compiler re-derives the shared-memory
+        // window base (S2UR SR_CgaCtaId + four dependent instructions) in front of every tile's wait
+        uint32_t t_full_r = t_full, t_empty_r = t_empty;
+        uint32_t tmem_q = tmem_base + ((uint32_t)(quarter * 32) << 16);      // this warp's TMEM lane quarter (same treatment)
+        asm volatile("" : "+r"(t_full_r), "+r"(t_empty_r), "+r"(tmem_q));
         share_store(my_share, -INFINITY, -INFINITY);
         asm volatile("bar.sync 1, %0;" :: "n"(32 * TC_EPI_WARPS) : "memory");
         if constexpr (KP == 2) {
@@ -716,7 +724,12 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                             const float m2 = fmaxf(o1[1], o1[2]), n2 = fminf(o1[1], o1[2]);
                             const float second_best = fmaxf(fminf(m1, m2), fmaxf(n1, n2));
                             const float foreign = fmaxf(fmaxf(second_best, o2[0]), fmaxf(o2[1], o2[2]));
-                            f = fmaxf(f, float_pred(foreign));
+                            // Strictly below the foreign bound, so that values equal to it pass the `>` tests.  This instance only ever
+                            // sees integer-valued accumulators below 2^24 (section 4.1): foreign - 1 is exact and is the
+                            // largest value of that lattice below the bound; padded columns (-2^30, where - 1 rounds away) are
+                            // discarded at the flush anyway, and -inf stays -inf.  One FADD instead of float_pred's ten
+                            // instructions and a divergent branch per tile.
+                            f = fmaxf(f, foreign - 1.0f);
                         }
                     };
 #ifndef TC_SHARE_AFTER_WAIT
@@ -726,11 +739,11 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                     // stale, it enters the slow path far more often and falls further behind: 1.11 -> 1.27 ms per 64 pairs.)
                     if (!TC_SHARE_AFTER_WAIT) update_filter();
                     if (prof) { t1 = clock64(); c_share += t1 - t0; t0 = t1; }
-                    mbar_wait(t_full + 8 * acc, (tc >> 1) & 1, dbg, 6);
+                    mbar_wait(t_full_r + 8 * acc, (tc >> 1) & 1, dbg, 6);
                     tc_fence_after();
                     if (prof) { t1 = clock64(); c_wait += t1 - t0; t0 = t1; c_tiles++; }
                     if (TC_SHARE_AFTER_WAIT) update_filter();
-                    const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TILE_N + dpart * 64;
+                    const uint32_t tbase = tmem_q + acc * TILE_N + dpart * 64;
                     const int col_base = un.t_local0 + t * TILE_N + dpart * 64;
                     if (!(exp_mode & 1)) {
                         uint32_t ra[32], rb[32];
@@ -743,7 +756,7 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                         // can (the MMA issuer waited 394 cycles per tile for this arrival when the filter update came first).
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) { if constexpr (PAIR) mbar_arrive_leader(t_empty + 8 * acc); else mbar_arrive(t_empty + 8 * acc); }
+                        if (lane == 0) { if constexpr (PAIR) mbar_arrive_leader(t_empty_r + 8 * acc); else mbar_arrive(t_empty_r + 8 * acc); }
                         if (exp_mode & 16) {                          // exp bit 4: loads, no scan (the values are consumed by one OR chain)
                             uint32_t acc_or = 0;
                             #pragma unroll
@@ -767,7 +780,7 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                     } else {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) { if constexpr (PAIR) mbar_arrive_leader(t_empty + 8 * acc); else mbar_arrive(t_empty + 8 * acc); }
+                        if (lane == 0) { if constexpr (PAIR) mbar_arrive_leader(t_empty_r + 8 * acc); else mbar_arrive(t_empty_r + 8 * acc); }
                     }
                 }
                 tc = tc_unit0 + (uint32_t)un.n_tiles;
@@ -820,7 +833,7 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                 int ix[4] = { -1, -1, -1, -1 };
                 for (int t = 0; t < un.n_tiles; t++, tc++) {
                     const uint32_t acc = tc & 1;
-                    mbar_wait(t_full + 8 * acc, (tc >> 1) & 1, dbg, 6);
+                    mbar_wait(t_full_r + 8 * acc, (tc >> 1) & 1, dbg, 6);
                     tc_fence_after();
                     if (t > 0) {
                         // a part's fourth best is a lower bound of the row's fourth best: columns at or below it are no candidates
@@ -834,7 +847,7 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                         }
                         f = fmaxf(f, foreign);
                     }
-                    const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * TILE_N + part * 64;
+                    const uint32_t tbase = tmem_q + acc * TILE_N + part * 64;
                     const int col_base = un.t_local0 + t * TILE_N + part * 64;
                     if (!(exp_mode & 1)) {
                         uint32_t ra[32], rb[32];
@@ -847,7 +860,7 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) { if constexpr (PAIR) mbar_arrive_leader(t_empty + 8 * acc); else mbar_arrive(t_empty + 8 * acc); }
+                    if (lane == 0) { if constexpr (PAIR) mbar_arrive_leader(t_empty_r + 8 * acc); else mbar_arrive(t_empty_r + 8 * acc); }
                 }
                 // ---- unit flush: every column part writes its own candidate record ----
                 share_store(my_share, -INFINITY, -INFINITY);
@@ -895,11 +908,12 @@ int tc_init(char* err, size_t errlen)
 // context is created on (api.cu, under its own mutex), with that device current.
 int tc_set_device_attrs(char* err, size_t errlen)
 {
-    cudaError_t e = cudaFuncSetAttribute(match_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(match_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(match_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
+    const void* fns[6] = { (const void*)match_tc_kernel<2, false, false>, (const void*)match_tc_kernel<2, false, true>,
+                           (const void*)match_tc_kernel<4, false, false>, (const void*)match_tc_kernel<4, false, true>,
+                           (const void*)match_tc_kernel<2, true, false>, (const void*)match_tc_kernel<2, true, true> };
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 6 && e == cudaSuccess; i++)
+        e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES);
     if (e != cudaSuccess) {
         snprintf(err, errlen, "cudaFuncSetAttribute(match_tc_kernel): %s", cudaGetErrorString(e));
         return 1;
@@ -964,8 +978,10 @@ int launch_match_tc(const TcOperands& op, const TcMapsOpaque* encoded, const Mat
     const int grid = n_units < n_sms ? n_units : n_sms;
     static int exp_mode = -1;
     if (exp_mode < 0) { const char* e = getenv("CVG_TC_EXP"); exp_mode = e ? atoi(e) : 0; }
-    if (candidates == 4)
-        match_tc_kernel<4, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, op.qnorm, units, n_units, parts, gate_flag, gate_want, dbg, exp_mode);
+    if (candidates == 4) {
+        if (exp_mode) match_tc_kernel<4, false, true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, op.qnorm, units, n_units, parts, gate_flag, gate_want, dbg, exp_mode);
+        else match_tc_kernel<4, false, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, op.qnorm, units, n_units, parts, gate_flag, gate_want, dbg, 0);
+    }
     else if (paired && (n_units % 2) == 0 && n_sms >= 2) {
         // clusters of two CTAs (cta_group::2): consecutive units (2p, 2p + 1) share their train tiles
         const int n_pairs = n_units / 2;
@@ -980,20 +996,24 @@ int launch_match_tc(const TcOperands& op, const TcMapsOpaque* encoded, const Mat
         static int max_clusters = -1;
         if (max_clusters < 0) {
             int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, match_tc_kernel<2, true>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = n_sms / 2; }
+            if (cudaOccupancyMaxActiveClusters(&n, match_tc_kernel<2, true, false>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = n_sms / 2; }
             max_clusters = n < n_sms / 2 ? n : n_sms / 2;
             if (getenv("CVG_TC_PAIR_CLUSTERS")) max_clusters = atoi(getenv("CVG_TC_PAIR_CLUSTERS"));
             if (dbg_print_clusters()) fprintf(stderr, "cvgraft: match pair mode runs %d clusters of 2 CTAs (%d SMs)\n", max_clusters, n_sms);
         }
         const int clusters = n_pairs < max_clusters ? n_pairs : max_clusters;
         cfg.gridDim = dim3((unsigned)(2 * clusters));
-        cudaError_t le = cudaLaunchKernelEx(&cfg, match_tc_kernel<2, true>, maps, op.qnorm, units, n_units, parts, gate_flag, gate_want, dbg, exp_mode);
+        cudaError_t le = exp_mode
+            ? cudaLaunchKernelEx(&cfg, match_tc_kernel<2, true, true>, maps, op.qnorm, units, n_units, parts, gate_flag, gate_want, dbg, exp_mode)
+            : cudaLaunchKernelEx(&cfg, match_tc_kernel<2, true, false>, maps, op.qnorm, units, n_units, parts, gate_flag, gate_want, dbg, 0);
         if (le != cudaSuccess) {
             snprintf(err, errlen, "match_tc_kernel (pair mode) launch: %s", cudaGetErrorString(le));
             return 1;
         }
-    } else
-        match_tc_kernel<2, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, op.qnorm, units, n_units, parts, gate_flag, gate_want, dbg, exp_mode);
+    } else if (exp_mode)
+        match_tc_kernel<2, false, true><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, op.qnorm, units, n_units, parts, gate_flag, gate_want, dbg, exp_mode);
+    else
+        match_tc_kernel<2, false, false><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(maps, op.qnorm, units, n_units, parts, gate_flag, gate_want, dbg, 0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(err, errlen, "match_tc_kernel launch: %s", cudaGetErrorString(e));
