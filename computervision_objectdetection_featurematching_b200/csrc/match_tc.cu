@@ -355,15 +355,6 @@ __device__ __forceinline__ void share_load(uint32_t addr, float& a, float& b)
     asm volatile("ld.volatile.shared.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "r"(addr) : "memory");
 }
 
-// largest float below x (x finite or -inf; -inf stays -inf)
-__device__ __forceinline__ float float_pred(float x)
-{
-    const int b = __float_as_int(x);
-    if (x == -INFINITY) return x;
-    if (x == 0.f) return __int_as_float((int)0x80000001u);
-    return __int_as_float(x > 0.f ? b - 1 : b + 1);
-}
-
 // Candidate form for non-integer descriptors (the accumulator is then an approximation of 2 q.t - ||t||^2): the four
 // largest values per row are kept; the fp32 re-rank (match_exact.cu) decides among them and proves, with an error
 // bound, that no other column can belong to the two nearest.  Ties need no care here: a column that is dropped has
@@ -651,7 +642,7 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
         // filter to the second largest value any part has seen for the row.  Unsynchronised on purpose: a stale or
         // torn pair still consists of values of real columns with "second <= some other column of that part", so
         // the bound below is always <= the row's true second best.  Values equal to a foreign bound are kept
-        // (float_pred) because the foreign column may have the higher train index.
+        // (the bound is lowered by one lattice step) because the foreign column may have the higher train index.
         const uint32_t share = smem_base + OFF_SHARE;
         const uint32_t my_share = share + (uint32_t)(part * TILE_M + row_in_tile) * 8u;
         // the accumulator barriers' addresses, held in a register: left to itself the compiler re-derives the shared-memory
@@ -727,8 +718,8 @@ match_tc_kernel(const __grid_constant__ TcMaps maps, const float* __restrict__ q
                             // Strictly below the foreign bound, so that values equal to it pass the `>` tests.  This instance only ever
                             // sees integer-valued accumulators below 2^24 (section 4.1): foreign - 1 is exact and is the
                             // largest value of that lattice below the bound; padded columns (-2^30, where - 1 rounds away) are
-                            // discarded at the flush anyway, and -inf stays -inf.  One FADD instead of float_pred's ten
-                            // instructions and a divergent branch per tile.
+                            // discarded at the flush anyway, and -inf stays -inf.  One FADD; the general form (largest float
+                            // below the bound) cost ten instructions and a divergent branch per tile.
                             f = fmaxf(f, foreign - 1.0f);
                         }
                     };
