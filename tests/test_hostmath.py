@@ -111,3 +111,19 @@ def test_thread_per_hypothesis_run_kernel_bit_exact(hm):
             assert np.array_equal(H1, H2, equal_nan=True), (case, H1, H2)
             n_ok += 1
     assert n_ok > 3000
+
+
+def test_foreign_filter_bound_is_the_lattice_predecessor():
+    """match_tc_kernel (exact instance) lowers a foreign column part's bound with `foreign - 1.0f` so that equal values
+    still pass its strict `>` tests (csrc/match_tc.cu, update_filter).  The accumulator 2 q.t - ||t||^2 of integer
+    descriptors in 0..255 over 128 dimensions is an integer with |acc'| <= 2 * 128 * 255^2 < 2^24: on that lattice the
+    fp32 subtraction is exact, keeps every value >= the bound and drops every value below it."""
+    hi = 2 * 128 * 255 * 255
+    assert hi < 2 ** 24
+    rng = np.random.default_rng(7)
+    v = np.concatenate([rng.integers(-hi, hi + 1, 200000), [-hi, -hi + 1, -1, 0, 1, hi - 1, hi,
+                                                           -(2 ** 23), 2 ** 23, 2 ** 23 + 1, -(2 ** 23) - 1]]).astype(np.float32)
+    f = (v - np.float32(1.0)).astype(np.float32)
+    assert np.all(f.astype(np.float64) == v.astype(np.float64) - 1.0)          # exact
+    assert np.all(v > f) and np.all((v - np.float32(1.0)) <= f)                 # equal passes, the next lower integer does not
+    assert np.float32(-np.inf) - np.float32(1.0) == np.float32(-np.inf)         # a part that has seen nothing yet
